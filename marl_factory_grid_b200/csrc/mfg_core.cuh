@@ -1,0 +1,1021 @@
+// mfg_core.cuh - per-environment semantics of the batched marl-factory-grid engine.
+//
+// One C++ restatement of the reference's hot path, written so that ONE THREAD advances ONE
+// environment (struct-of-arrays state, env index fastest => coalesced across the warp):
+//   env_step()        Gamestate.tick + check_done + reward fold   (utils/states.py:170-226, factory.py:189-259)
+//   env_reset()       Factory.reset spawn rules                    (environment/rules.py:163-199, collection.py:102-130)
+//   obs_agent_direct  OBSBuilder.build_for_agent + RayCaster        (utils/observation_builder.py:138-220, ray_caster.py:66-104)
+// The normative behaviour is the reference's ACTUAL one, including the
+// uid-equality artefact when spec.faithful != 0.
+//
+// The functions are __host__ __device__ so that tests/hostsim can compile the very same code with g++
+// and replay reference traces without a GPU.  That host build is test-only; the product library
+// (mfg_kernels.cu) only ever launches them as CUDA kernels.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+#include <math.h>
+#include "../../include/mfg_b200.h"
+
+#if defined(__CUDACC__)
+#define MFG_HD __host__ __device__ __forceinline__
+#define MFG_HDN __host__ __device__
+#else
+#define MFG_HD inline
+#define MFG_HDN inline
+#endif
+
+namespace mfg {
+
+constexpr int DOOR_INTERVAL = 10;        // modules/doors/entitites.py:69 auto_close_interval
+constexpr double DIRT_PILE_MAX = 5.0;    // modules/clean_up/entitites.py: DirtPile max_local_amount default
+constexpr double CHARGE_RATE = 0.4;      // modules/batteries/entitites.py:98
+constexpr double ENC_DOOR_OPEN = 0.4444, ENC_DOOR_CLOSED = 0.6666, ENC_MACHINE = 15.0;
+constexpr uint16_t NO_POS = 0xFFFF;
+constexpr int RESPAWN_TAPE_W = 8;
+
+// entity classes with an integer uid (object.py:103-113)
+enum { C_DOOR = 0, C_DIRT, C_ITEM, C_POD, C_DEST, C_DROP, C_MACH, C_MAINT, C_NONE };
+
+// ------------------------------------------------------------------------------------------------
+// state layout: every field is a [rows][N] array inside one caller-owned buffer
+// ------------------------------------------------------------------------------------------------
+#define MFG_STATE_FIELDS(F)                                                        \
+  F(uint16_t, step, 1)                                                             \
+  F(uint32_t, episode, 1)                                                          \
+  F(uint32_t, clock, 1)                                                            \
+  F(uint16_t, apos, sp.n_agents)                                                   \
+  F(uint32_t, astamp, sp.n_agents)                                                 \
+  F(uint8_t, aflag, sp.n_agents)                                                   \
+  F(double, bat, sp.has_batteries ? sp.n_agents : 0)                               \
+  F(double, ep_ret, sp.n_agents)                                                   \
+  F(uint64_t, door_open, sp.n_doors ? 1 : 0)                                       \
+  F(uint64_t, door_listed, sp.n_doors ? 1 : 0)                                     \
+  F(uint8_t, door_timer, sp.n_doors)                                               \
+  F(uint16_t, dirt_pos, sp.has_dirt ? sp.dirt_slots : 0)                           \
+  F(double, dirt_amt, sp.has_dirt ? sp.dirt_slots : 0)                             \
+  F(uint16_t, dirt_uid, sp.has_dirt ? sp.dirt_slots : 0)                           \
+  F(uint64_t, dirt_listed, sp.has_dirt ? 1 : 0)                                    \
+  F(uint8_t, dirt_end, sp.has_dirt ? 1 : 0)                                        \
+  F(uint8_t, dirt_n, sp.has_dirt ? 1 : 0)                                          \
+  F(uint16_t, dirt_next_uid, sp.has_dirt ? 1 : 0)                                  \
+  F(int16_t, dirt_next_spawn, sp.has_dirt ? 1 : 0)                                 \
+  F(uint16_t, item_pos, sp.n_items)                                                \
+  F(uint16_t, pod_pos, sp.n_pods)                                                  \
+  F(uint16_t, dest_pos, sp.n_dest)                                                 \
+  F(uint16_t, drop_pos, sp.n_dropoff)                                              \
+  F(uint16_t, mach_pos, sp.n_machines)                                             \
+  F(uint16_t, maint_pos, sp.n_maint)                                               \
+  F(uint32_t, item_listed, sp.n_items ? 1 : 0)                                     \
+  F(uint32_t, pod_listed, sp.n_pods ? 1 : 0)                                       \
+  F(uint32_t, dest_listed, sp.n_dest ? 1 : 0)                                      \
+  F(uint32_t, drop_listed, sp.n_dropoff ? 1 : 0)                                   \
+  F(uint32_t, mach_listed, sp.n_machines ? 1 : 0)                                  \
+  F(uint32_t, maint_listed, sp.n_maint ? 1 : 0)                                    \
+  F(uint32_t, dest_reached, sp.n_dest ? 1 : 0)                                     \
+  F(uint16_t, maint_target, sp.n_maint)                                            \
+  F(uint16_t, maint_rand, sp.n_maint)                                              \
+  F(uint32_t, maint_remaining, sp.n_maint)                                         \
+  F(uint8_t, maint_last, sp.n_maint)
+
+struct State {
+  int64_t N;
+#define F(type, name, rows) type* name;
+  MFG_STATE_FIELDS(F)
+#undef F
+};
+
+// derived level tables (device memory, built by mfg_create)
+struct Tables {
+  const uint8_t* wall;         // [H*W]
+  const uint8_t* door_map;     // [H*W] door index or 0xFF
+  const uint16_t* floor_pos;   // [F] pos16
+  const uint16_t* floor_index; // [H*W] floor index or 0xFFFF
+  const uint16_t* wall_uid;    // [H*W] row-major wall index or 0xFFFF
+  const uint16_t* wall_pos;    // [n_walls] pos16
+  const uint16_t* door_pos;    // [ND] pos16
+  const uint8_t* nexthop;      // [F*F] or null
+  const uint64_t* wall_win;    // [H*W] (2r+1)^2-bit wall mask of the window centred on the tile (r <= 3)
+  int64_t env_id_offset;
+  unsigned long long* stats;   // [MFG_N_STATS]
+};
+
+MFG_HD int px(uint16_t p) { return p >> 8; }
+MFG_HD int py(uint16_t p) { return p & 255; }
+MFG_HD uint16_t mkpos(int x, int y) { return (uint16_t)((x << 8) | y); }
+
+MFG_HD int dir_dx(int d) { return d == 0 || d == 4 || d == 7 ? -1 : (d == 2 || d == 5 || d == 6 ? 1 : 0); }
+MFG_HD int dir_dy(int d) { return d == 1 || d == 4 || d == 5 ? 1 : (d == 3 || d == 6 || d == 7 ? -1 : 0); }
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10, counter-based: key = seed ^ global env id, counter = (block, step, episode, stream)
+// ------------------------------------------------------------------------------------------------
+enum { RS_RESET = 0, RS_RESPAWN = 1, RS_ACTIONS = 2, RS_MAINT0 = 8 };
+
+struct Philox {
+  uint32_t k0, k1, c1, c2, c3, block;
+  uint32_t out[4];
+  int have;
+  MFG_HD void init(uint64_t seed, uint64_t gid, uint32_t stream, uint32_t episode, uint32_t step) {
+    uint64_t k = seed ^ (gid * 0x9E3779B97F4A7C15ull);
+    k0 = (uint32_t)k; k1 = (uint32_t)(k >> 32);
+    c1 = step; c2 = episode; c3 = stream; block = 0; have = 0;
+  }
+  static MFG_HD void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+    uint64_t p = (uint64_t)a * (uint64_t)b;
+    hi = (uint32_t)(p >> 32); lo = (uint32_t)p;
+  }
+  MFG_HD void refill() {
+    uint32_t x0 = block, x1 = c1, x2 = c2, x3 = c3, a = k0, b = k1;
+    for (int r = 0; r < 10; ++r) {
+      uint32_t hi0, lo0, hi1, lo1;
+      mulhilo(0xD2511F53u, x0, hi0, lo0);
+      mulhilo(0xCD9E8D57u, x2, hi1, lo1);
+      uint32_t y0 = hi1 ^ x1 ^ a, y1 = lo1, y2 = hi0 ^ x3 ^ b, y3 = lo0;
+      x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+      a += 0x9E3779B9u; b += 0xBB67AE85u;
+    }
+    out[0] = x0; out[1] = x1; out[2] = x2; out[3] = x3;
+    ++block; have = 4;
+  }
+  MFG_HD uint32_t next() {
+    if (have == 0) refill();
+    uint32_t v = have == 4 ? out[0] : have == 3 ? out[1] : have == 2 ? out[2] : out[3];
+    --have;
+    return v;
+  }
+  MFG_HD uint32_t below(uint32_t n) { return (uint32_t)(((uint64_t)next() * (uint64_t)n) >> 32); }
+  MFG_HD double uniform(double lo, double hi) { return lo + (hi - lo) * ((double)next() * 2.3283064365386963e-10); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// per-environment context: hot fields live in registers, the rest is touched in the SoA buffers
+// ------------------------------------------------------------------------------------------------
+template <int AMAX>
+struct Env {
+  const MfgSpec& sp;
+  const Tables& tb;
+  const State& st;
+  int64_t e;
+  int A;
+  uint16_t apos[AMAX];
+  uint64_t dopen, dlisted, dirt_listed;
+  int dirt_end, dirt_n;
+
+  MFG_HD Env(const MfgSpec& sp_, const Tables& tb_, const State& st_, int64_t e_) : sp(sp_), tb(tb_), st(st_), e(e_) {
+    A = sp.n_agents;
+    dopen = dlisted = dirt_listed = 0;
+    dirt_end = dirt_n = 0;
+  }
+  template <typename T> MFG_HD T& at(T* base, int row) const { return base[(size_t)row * (size_t)st.N + (size_t)e]; }
+
+  MFG_HD void load() {
+#pragma unroll
+    for (int i = 0; i < AMAX; ++i) apos[i] = i < A ? at(st.apos, i) : NO_POS;
+    if (sp.n_doors) { dopen = at(st.door_open, 0); dlisted = at(st.door_listed, 0); }
+    if (sp.has_dirt) { dirt_listed = at(st.dirt_listed, 0); dirt_end = at(st.dirt_end, 0); dirt_n = at(st.dirt_n, 0); }
+  }
+  MFG_HD void store() {
+#pragma unroll
+    for (int i = 0; i < AMAX; ++i) if (i < A) at(st.apos, i) = apos[i];
+    if (sp.n_doors) { at(st.door_open, 0) = dopen; at(st.door_listed, 0) = dlisted; }
+    if (sp.has_dirt) { at(st.dirt_listed, 0) = dirt_listed; at(st.dirt_end, 0) = (uint8_t)dirt_end; at(st.dirt_n, 0) = (uint8_t)dirt_n; }
+  }
+
+  // ---------------------------------------------------------------- small-group access by class
+  MFG_HD int cls_count(int c) const {
+    return c == C_ITEM ? sp.n_items : c == C_POD ? sp.n_pods : c == C_DEST ? sp.n_dest : c == C_DROP ? sp.n_dropoff
+         : c == C_MACH ? sp.n_machines : c == C_MAINT ? sp.n_maint : 0;
+  }
+  MFG_HD uint16_t* cls_pos(int c) const {
+    return c == C_ITEM ? st.item_pos : c == C_POD ? st.pod_pos : c == C_DEST ? st.dest_pos : c == C_DROP ? st.drop_pos
+         : c == C_MACH ? st.mach_pos : st.maint_pos;
+  }
+  MFG_HD uint32_t* cls_listed(int c) const {
+    return c == C_ITEM ? st.item_listed : c == C_POD ? st.pod_listed : c == C_DEST ? st.dest_listed
+         : c == C_DROP ? st.drop_listed : c == C_MACH ? st.mach_listed : st.maint_listed;
+  }
+
+  // ---------------------------------------------------------------- tile queries
+  MFG_HD bool in_grid(int x, int y) const { return x >= 0 && y >= 0 && x < sp.H && y < sp.W; }
+  MFG_HD int door_at(int x, int y) const { int d = tb.door_map[x * sp.W + y]; return d == 0xFF ? -1 : d; }
+  MFG_HD bool closed_listed_door(int x, int y) const {
+    if (!sp.n_doors) return false;
+    int d = door_at(x, y);
+    return d >= 0 && !((dopen >> d) & 1) && ((dlisted >> d) & 1);
+  }
+  MFG_HD int agents_at(uint16_t p) const {
+    int n = 0;
+#pragma unroll
+    for (int i = 0; i < AMAX; ++i) n += (i < A && apos[i] == p) ? 1 : 0;
+    return n;
+  }
+  MFG_HD int listed_maints_at(uint16_t p) const {
+    int n = 0;
+    if (sp.n_maint) {
+      uint32_t l = at(st.maint_listed, 0);
+      for (int k = 0; k < sp.n_maint; ++k) n += (((l >> k) & 1) && at(st.maint_pos, k) == p) ? 1 : 0;
+    }
+    return n;
+  }
+  // states.py:259-270 check_pos_validity (negated): wall / off-grid / closed listed door / blocking agent
+  MFG_HD bool blocked(int x, int y) const {
+    if (!in_grid(x, y) || tb.wall[x * sp.W + y]) return true;
+    if (closed_listed_door(x, y)) return true;
+    uint16_t p = mkpos(x, y);
+#pragma unroll
+    for (int i = 0; i < AMAX; ++i) if (i < A && sp.agent_blocking[i] && apos[i] == p) return true;
+    return false;
+  }
+  // number of collidable LISTED entities on an in-grid tile: agents, maintainers, closed doors, walls
+  MFG_HD int n_coll(int x, int y) const {
+    uint16_t p = mkpos(x, y);
+    return agents_at(p) + listed_maints_at(p) + (closed_listed_door(x, y) ? 1 : 0) + (tb.wall[x * sp.W + y] ? 1 : 0);
+  }
+  MFG_HD bool is_free(int x, int y) const { return !blocked(x, y) && n_coll(x, y) == 0; }
+
+  // ---------------------------------------------------------------- uid listing (objects.py:193-214)
+  MFG_HD bool find_listed(int uid, uint16_t p, int& cls, int& idx) const {
+    if (uid < sp.n_doors && tb.door_pos[uid] == p && ((dlisted >> uid) & 1)) { cls = C_DOOR; idx = uid; return true; }
+    if (sp.has_dirt && uid < (int)at(st.dirt_next_uid, 0)) {
+      for (int k = 0; k < dirt_end; ++k)
+        if (at(st.dirt_pos, k) == p && at(st.dirt_uid, k) == uid && ((dirt_listed >> k) & 1)) { cls = C_DIRT; idx = k; return true; }
+    }
+    for (int c = C_ITEM; c <= C_MAINT; ++c) {
+      if (uid < cls_count(c) && at(cls_pos(c), uid) == p && ((at(cls_listed(c), 0) >> uid) & 1)) { cls = c; idx = uid; return true; }
+    }
+    return false;
+  }
+  MFG_HD void set_listed(int cls, int idx, bool v) {
+    if (cls == C_DOOR) dlisted = v ? (dlisted | (1ull << idx)) : (dlisted & ~(1ull << idx));
+    else if (cls == C_DIRT) dirt_listed = v ? (dirt_listed | (1ull << idx)) : (dirt_listed & ~(1ull << idx));
+    else { uint32_t& l = at(cls_listed(cls), 0); l = v ? (l | (1u << idx)) : (l & ~(1u << idx)); }
+  }
+  MFG_HD void l_add(int cls, int idx, int uid, uint16_t p) {
+    int c2, i2;
+    if (sp.faithful && find_listed(uid, p, c2, i2)) set_listed(cls, idx, false);
+    else set_listed(cls, idx, true);
+  }
+  MFG_HD void l_del(int cls, int idx, int uid, uint16_t p) {
+    if (sp.faithful) {
+      int c2, i2;
+      if (find_listed(uid, p, c2, i2)) set_listed(c2, i2, false);
+    } else {
+      set_listed(cls, idx, false);
+    }
+  }
+
+  // ---------------------------------------------------------------- doors (doors/actions.py:18-34, entitites.py:97-140)
+  MFG_HD bool toggle_near(uint16_t p) {
+    bool valid = false;
+    int x = px(p), y = py(p);
+    for (int d = 0; d < sp.n_doors; ++d) {
+      uint16_t q = tb.door_pos[d];
+      int dx = px(q) - x, dy = py(q) - y;
+      if (((dlisted >> d) & 1) && dx >= -1 && dx <= 1 && dy >= -1 && dy <= 1) {
+        if ((dopen >> d) & 1) dopen &= ~(1ull << d);
+        else { dopen |= (1ull << d); at(st.door_timer, d) = DOOR_INTERVAL; }
+        valid = true;
+      }
+    }
+    return valid;
+  }
+
+  // ---------------------------------------------------------------- dirt (clean_up/groups.py:70-95, actions.py:19-36)
+  MFG_HD int dirt_at(uint16_t p) const {
+    for (int k = 0; k < dirt_end; ++k) if (at(st.dirt_pos, k) == p) return k;
+    return -1;
+  }
+  MFG_HD double dirt_sum() const {
+    double s = 0.0;
+    for (int k = 0; k < dirt_end; ++k) if (at(st.dirt_pos, k) != NO_POS) s += at(st.dirt_amt, k);
+    return s;
+  }
+  MFG_HD void dirt_compact() {
+    int w = 0;
+    uint64_t nl = 0;
+    for (int k = 0; k < dirt_end; ++k) {
+      uint16_t p = at(st.dirt_pos, k);
+      if (p == NO_POS) continue;
+      if (w != k) { at(st.dirt_pos, w) = p; at(st.dirt_amt, w) = at(st.dirt_amt, k); at(st.dirt_uid, w) = at(st.dirt_uid, k); }
+      if ((dirt_listed >> k) & 1) nl |= 1ull << w;
+      ++w;
+    }
+    for (int k = w; k < dirt_end; ++k) at(st.dirt_pos, k) = NO_POS;
+    dirt_end = w; dirt_listed = nl;
+  }
+  MFG_HD void dirt_create(uint16_t p, double amount) {
+    if (dirt_end == sp.dirt_slots) dirt_compact();
+    uint16_t uid = at(st.dirt_next_uid, 0);
+    at(st.dirt_next_uid, 0) = (uint16_t)(uid + 1);      // the reference's uid counter advances regardless
+    if (dirt_end == sp.dirt_slots) {
+#if defined(__CUDA_ARCH__)
+      atomicAdd(&tb.stats[MFG_ST_DIRT_OVERFLOW], 1ull);
+#else
+      tb.stats[MFG_ST_DIRT_OVERFLOW] += 1;
+#endif
+      return;
+    }
+    int k = dirt_end++;
+    at(st.dirt_pos, k) = p; at(st.dirt_amt, k) = amount; at(st.dirt_uid, k) = uid;
+    ++dirt_n;
+    l_add(C_DIRT, k, uid, p);
+  }
+  MFG_HD void dirt_delete(int k) {
+    l_del(C_DIRT, k, at(st.dirt_uid, k), at(st.dirt_pos, k));
+    dirt_listed &= ~(1ull << k);
+    at(st.dirt_pos, k) = NO_POS;
+    --dirt_n;
+  }
+  // trigger_spawn body after the random draws: tiles/amounts zipped
+  template <typename TileFn, typename AmtFn>
+  MFG_HD void dirt_spawn(int n, TileFn tile, AmtFn amount) {
+    for (int j = 0; j < n; ++j) {
+      if (dirt_sum() > sp.dirt_max_global) return;
+      uint16_t p = tile(j);
+      double a = amount(j);
+      int k = dirt_at(p);
+      if (k >= 0) at(st.dirt_amt, k) = fmin(at(st.dirt_amt, k) + a, DIRT_PILE_MAX);
+      else dirt_create(p, a);
+    }
+  }
+
+  // ---------------------------------------------------------------- moves (actions.py:77-100, states.py:240-257)
+  MFG_HD bool try_move(uint16_t p, int d, bool mover_blocks, uint16_t& target) const {
+    int x = px(p) + dir_dx(d), y = py(p) + dir_dy(d);
+    if (blocked(x, y)) return false;
+    if (mover_blocks && n_coll(x, y) >= 1) return false;      // is_occupied (global_entities.py:187-194)
+    target = mkpos(x, y);
+    return true;
+  }
+
+  // ---------------------------------------------------------------- free tile sampling (global_entities.py:111-121)
+  MFG_HD uint16_t sample_free(Philox& rng, const uint16_t* taken, int n_taken, bool must_be_empty) const {
+    for (int attempt = 0; attempt < 64 + 16 * sp.n_floor; ++attempt) {
+      uint16_t p = tb.floor_pos[rng.below((uint32_t)sp.n_floor)];
+      int x = px(p), y = py(p);
+      bool ok = must_be_empty ? (agents_at(p) == 0 && (sp.n_doors == 0 || door_at(x, y) < 0)) : is_free(x, y);
+      for (int j = 0; ok && j < n_taken; ++j) ok = taken[j] != p;
+      if (ok) return p;
+    }
+    return NO_POS;
+  }
+};
+
+MFG_HD void stat_add(const Tables& tb, int idx, unsigned long long v) {
+#if defined(__CUDA_ARCH__)
+  atomicAdd(&tb.stats[idx], v);
+#else
+  tb.stats[idx] += v;
+#endif
+}
+MFG_HD void stat_add_f64(const Tables& tb, int idx, double v) {
+#if defined(__CUDA_ARCH__)
+  atomicAdd(reinterpret_cast<double*>(&tb.stats[idx]), v);
+#else
+  *reinterpret_cast<double*>(&tb.stats[idx]) += v;
+#endif
+}
+
+// ================================================================================================
+// reset: Factory.reset with a fresh Factory: SpawnAgents, then the groups in Entities order
+// ================================================================================================
+template <int AMAX>
+MFG_HDN void env_reset(const MfgSpec& sp, const Tables& tb, const State& st, int64_t e, uint32_t episode) {
+  Env<AMAX> v(sp, tb, st, e);
+  const int A = v.A;
+  Philox rng;
+  rng.init(sp.seed, (uint64_t)(tb.env_id_offset + e), RS_RESET, episode, 0);
+
+  v.at(st.step, 0) = 0;
+  v.at(st.episode, 0) = episode;
+  v.at(st.clock, 0) = (uint32_t)A;
+  for (int i = 0; i < A; ++i) {
+    v.at(st.astamp, i) = (uint32_t)i;
+    v.at(st.aflag, i) = 0;
+    v.at(st.ep_ret, i) = 0.0;
+    if (sp.has_batteries) v.at(st.bat, i) = sp.battery_initial;
+    v.apos[i] = NO_POS;
+  }
+  // doors: closed, timer = interval, listed (doors/entitites.py:150-156 Door.reset)
+  if (sp.n_doors) {
+    v.dopen = 0;
+    v.dlisted = sp.n_doors == 64 ? ~0ull : ((1ull << sp.n_doors) - 1);
+    for (int d = 0; d < sp.n_doors; ++d) v.at(st.door_timer, d) = DOOR_INTERVAL;
+  }
+  if (sp.has_dirt) {
+    for (int k = 0; k < sp.dirt_slots; ++k) v.at(st.dirt_pos, k) = NO_POS;
+    v.dirt_listed = 0; v.dirt_end = 0; v.dirt_n = 0;
+    v.at(st.dirt_next_uid, 0) = 0;
+    int16_t next = -1;
+    for (int r = 0; r < sp.n_rules; ++r) if (sp.rule_op[r] == MFG_R_RESPAWN_DIRT) next = (int16_t)sp.rule_param[r][0];
+    v.at(st.dirt_next_spawn, 0) = next;              // clean_up/rules.py:47 (fresh rule object)
+  }
+  for (int c = C_ITEM; c <= C_MAINT; ++c) {
+    int n = v.cls_count(c);
+    for (int k = 0; k < n; ++k) v.at(v.cls_pos(c), k) = NO_POS;
+    if (n) v.at(v.cls_listed(c), 0) = 0;
+  }
+  if (sp.n_dest) v.at(st.dest_reached, 0) = 0;
+  for (int k = 0; k < sp.n_maint; ++k) {
+    v.at(st.maint_target, k) = NO_POS; v.at(st.maint_rand, k) = NO_POS;
+    v.at(st.maint_remaining, k) = 0; v.at(st.maint_last, k) = 0xFF;
+  }
+
+  // ---- SpawnAgents (rules.py:182-199): configured position if still empty, else a random EMPTY tile
+  for (int i = 0; i < A; ++i) {
+    uint16_t p = NO_POS;
+    if (sp.agent_n_fixed[i] > 0) {
+      for (int j = 0; j < sp.agent_n_fixed[i] && p == NO_POS; ++j) {
+        uint16_t q = sp.agent_fixed_pos[i][j];
+        if (v.agents_at(q) == 0 && (sp.n_doors == 0 || v.door_at(px(q), py(q)) < 0)) p = q;
+      }
+    } else {
+      p = v.sample_free(rng, nullptr, 0, true);
+    }
+    if (p == NO_POS) { stat_add(tb, MFG_ST_SPAWN_FAIL, 1); p = tb.floor_pos[0]; }
+    v.apos[i] = p;
+  }
+
+  // ---- SpawnEntity rules in Entities order (rules.py:163-167 -> collection.py:102-130)
+  uint16_t chosen[MFG_MAX_DIRT];
+  for (int g = 0; g < sp.n_groups; ++g) {
+    int gid = sp.group_id[g];
+    if (gid == MFG_SP_DIRT) {
+      // clean_up/groups.py:70-95: count draw, positions, then `quantity` amount draws
+      int q = sp.dirt_quantity;
+      int n_new = (int)fabs((double)q + rng.uniform(-sp.dirt_n_var, sp.dirt_n_var));
+      if (n_new > MFG_MAX_DIRT) n_new = MFG_MAX_DIRT;
+      int got = 0;
+      for (int j = 0; j < n_new; ++j) {
+        uint16_t p = v.sample_free(rng, chosen, got, false);
+        if (p == NO_POS) break;
+        chosen[got++] = p;
+      }
+      double amounts[MFG_MAX_DIRT];
+      int qa = q < MFG_MAX_DIRT ? q : MFG_MAX_DIRT;
+      for (int j = 0; j < qa; ++j) amounts[j] = sp.dirt_initial_amount + rng.uniform(-sp.dirt_amount_var, sp.dirt_amount_var);
+      int n = got < qa ? got : qa;
+      v.dirt_spawn(n, [&](int j) { return chosen[j]; }, [&](int j) { return amounts[j]; });
+    } else if (gid == MFG_SP_PODS || gid == MFG_SP_DEST || gid == MFG_SP_ITEMS || gid == MFG_SP_DROPOFF ||
+               gid == MFG_SP_MACHINES || gid == MFG_SP_MAINT) {
+      int c = gid == MFG_SP_PODS ? C_POD : gid == MFG_SP_DEST ? C_DEST : gid == MFG_SP_ITEMS ? C_ITEM
+            : gid == MFG_SP_DROPOFF ? C_DROP : gid == MFG_SP_MACHINES ? C_MACH : C_MAINT;
+      int n = sp.group_quantity[g];
+      int got = 0;
+      for (int j = 0; j < n; ++j) {
+        uint16_t p = sp.group_n_fixed[g] > 0 ? sp.group_fixed_pos[g][j] : v.sample_free(rng, chosen, got, false);
+        if (p == NO_POS) { stat_add(tb, MFG_ST_SPAWN_FAIL, 1); break; }
+        chosen[got++] = p;
+      }
+      // all tiles are picked against the pre-spawn state (islice over the generator), then entities are created
+      for (int j = 0; j < got; ++j) {
+        v.at(v.cls_pos(c), j) = chosen[j];
+        v.l_add(c, j, j, chosen[j]);
+      }
+    }
+  }
+  v.store();
+}
+
+// ================================================================================================
+// step
+// ================================================================================================
+struct StepIO {
+  const int32_t* actions;     // [N][A]
+  const uint8_t* maint_act;   // [N][NM] or null
+  const int8_t* respawn_n;    // [N] or null
+  const uint16_t* respawn_pos;// [N][8] or null
+  float* reward;              // [N][A] (or [N][1])
+  uint8_t* done;              // [N]
+  int auto_reset;
+};
+
+// maintainer policy when no tape is given (maintenance/entities.py:37-136), next hop from the BFS table
+template <int AMAX>
+MFG_HD int maint_policy(Env<AMAX>& v, int k, uint32_t step) {
+  const MfgSpec& sp = v.sp; const State& st = v.st; const Tables& tb = v.tb;
+  uint16_t p = v.at(st.maint_pos, k);
+  int here = -1;
+  for (int m = 0; m < sp.n_machines && here < 0; ++m) if (v.at(st.mach_pos, m) == p) here = m;
+  if (here >= 0 && here != (int)v.at(st.maint_last, k)) { v.at(st.maint_last, k) = (uint8_t)here; return MFG_MAINT_MACHINE; }
+  uint16_t target = v.at(st.maint_target, k);
+  if (target == NO_POS || target == p) {
+    Philox rng;
+    rng.init(sp.seed, (uint64_t)(tb.env_id_offset + v.e), RS_MAINT0 + k, v.at(st.episode, 0), step);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      uint32_t rem = v.at(st.maint_remaining, k);
+      if (rem == 0) {
+        if (attempt == 1) break;                       // reference would raise IndexError here
+        v.at(st.maint_rand, k) = v.sample_free(rng, nullptr, 0, false);
+        rem = (sp.n_machines >= 31 ? 0x7FFFFFFFu : ((1u << (sp.n_machines + 1)) - 1));
+      }
+      int cnt = 0;
+      for (int b = 0; b <= sp.n_machines; ++b) cnt += (rem >> b) & 1;
+      int pick = (int)rng.below((uint32_t)cnt), sel = 0;
+      for (int b = 0; b <= sp.n_machines; ++b) if ((rem >> b) & 1) { if (pick-- == 0) { sel = b; break; } }
+      v.at(st.maint_remaining, k) = rem & ~(1u << sel);
+      target = sel < sp.n_machines ? v.at(st.mach_pos, sel) : v.at(st.maint_rand, k);
+      if (target != NO_POS && target != p) break;
+    }
+    v.at(st.maint_target, k) = target;
+    if (target == NO_POS || target == p) return MFG_MAINT_NOOP;
+  }
+  int fi = tb.floor_index[px(p) * sp.W + py(p)], fj = tb.floor_index[px(target) * sp.W + py(target)];
+  int d = tb.nexthop ? tb.nexthop[(size_t)fi * sp.n_floor + fj] : 255;
+  if (d > 7) return MFG_MAINT_NOOP;
+  int nx = px(p) + dir_dx(d), ny = py(p) + dir_dy(d);
+  int door = sp.n_doors ? v.door_at(nx, ny) : -1;
+  if (door >= 0 && !((v.dopen >> door) & 1)) return MFG_MAINT_DOORUSE;     // Doors.by_pos: listing ignored
+  if (v.n_coll(nx, ny) > 0) return MFG_MAINT_NOOP;
+  return d;
+}
+
+template <int AMAX>
+MFG_HDN void env_step(const MfgSpec& sp, const Tables& tb, const State& st, int64_t e, const StepIO& io) {
+  Env<AMAX> v(sp, tb, st, e);
+  v.load();
+  const int A = v.A;
+  const int step = (int)v.at(st.step, 0) + 1;
+  v.at(st.step, 0) = (uint16_t)step;
+
+  double rew[AMAX];
+#pragma unroll
+  for (int i = 0; i < AMAX; ++i) rew[i] = 0.0;
+  double glob = 0.0, other = 0.0;
+
+  // ---- agents act sequentially against the live state (states.py:189-198)
+#pragma unroll
+  for (int i = 0; i < AMAX; ++i) {
+    if (i >= A) break;
+    if (v.at(st.aflag, i) & 1) continue;                       // paralysed: skipped entirely
+    int a = io.actions[(size_t)e * A + i];
+    if (a < 0 || a >= sp.n_actions[i]) a = 0;
+    const int op = sp.act_opcode[i][a];
+    const uint16_t p = v.apos[i];
+    bool ok = false;
+    double r_extra = 0.0;
+    bool use_extra = false;
+    if (op == MFG_OP_MOVE) {
+      uint16_t t;
+      ok = v.try_move(p, sp.act_dir[i][a], sp.agent_blocking[i] != 0, t);
+      if (ok) {
+        v.apos[i] = t;
+        uint32_t c = v.at(st.clock, 0);
+        v.at(st.astamp, i) = c;
+        v.at(st.clock, 0) = c + 1;
+      }
+    } else if (op == MFG_OP_NOOP) {
+      ok = true;
+    } else if (op == MFG_OP_DOORUSE) {
+      ok = v.toggle_near(p);
+    } else if (op == MFG_OP_CLEAN) {                           // clean_up/actions.py:19-36 (global index => listed pile)
+      int k = v.dirt_at(p);
+      ok = k >= 0 && ((v.dirt_listed >> k) & 1);
+      if (ok) {
+        double nw = v.at(st.dirt_amt, k) - sp.dirt_clean_amount;
+        if (nw <= 0) v.dirt_delete(k);
+        else v.at(st.dirt_amt, k) = fmin(fmax(nw, 0.0), DIRT_PILE_MAX);
+      }
+    } else if (op == MFG_OP_ITEM) {                            // items/actions.py:41-63
+      bool on_drop = false;
+      for (int k = 0; k < sp.n_dropoff; ++k) on_drop |= v.at(st.drop_pos, k) == p;
+      if (on_drop) { use_extra = true; r_extra = sp.act_aux[i][a]; }
+      else {
+        int it = -1;
+        for (int k = 0; k < sp.n_items && it < 0; ++k) if (v.at(st.item_pos, k) == p) it = k;
+        ok = it >= 0;
+        if (ok) { v.l_del(C_ITEM, it, it, p); v.set_listed(C_ITEM, it, false); v.at(st.item_pos, it) = NO_POS; }
+      }
+    } else if (op == MFG_OP_CHARGE) {                          // batteries/actions.py:20-31, entitites.py:98-111
+      bool on_pod = false;
+      for (int k = 0; k < sp.n_pods; ++k) on_pod |= v.at(st.pod_pos, k) == p;
+      if (on_pod) {
+        double b = v.at(st.bat, i);
+        if (!(b >= 1.0) && !(v.agents_at(p) > 1)) { v.at(st.bat, i) = fmin(1.0, CHARGE_RATE + b); ok = true; }
+      }
+    } else if (op == MFG_OP_DEST) {                            // destinations/actions.py:17-24 (reference raises on a dest)
+      ok = false;
+    } else if (op == MFG_OP_MACHINE) {                         // machines/actions.py:19-25
+      for (int k = 0; k < sp.n_machines; ++k) ok |= v.at(st.mach_pos, k) == p;
+    }
+    rew[i] += use_extra ? r_extra : (ok ? sp.act_valid[i][a] : sp.act_fail[i][a]);
+  }
+
+  // ---- tick_step hooks in yaml order (states.py:56-61)
+  for (int r = 0; r < sp.n_rules; ++r) {
+    const int op = sp.rule_op[r];
+    const double* P = sp.rule_param[r];
+    if (op == MFG_R_DOOR_AUTO_CLOSE) {
+      // doors/entitites.py:108-122: len(global pos_dict[door.pos]) = agents + listed entities, 2-bit saturating counters
+      uint64_t c0 = v.dlisted, c1 = 0;
+      auto add = [&](uint16_t q) {
+        if (q == NO_POS) return;
+        int d = tb.door_map[px(q) * sp.W + py(q)];
+        if (d == 0xFF) return;
+        uint64_t b = 1ull << d, carry = c0 & b;
+        c0 ^= b;
+        uint64_t carry2 = c1 & carry;
+        c1 ^= carry;
+        c0 |= carry2; c1 |= carry2;
+      };
+#pragma unroll
+      for (int i = 0; i < AMAX; ++i) if (i < A) add(v.apos[i]);
+      if (sp.has_dirt) for (int k = 0; k < v.dirt_end; ++k) if ((v.dirt_listed >> k) & 1) add(v.at(st.dirt_pos, k));
+      for (int c = C_ITEM; c <= C_MAINT; ++c) {
+        int n = v.cls_count(c);
+        if (!n) continue;
+        uint32_t l = v.at(v.cls_listed(c), 0);
+        for (int k = 0; k < n; ++k) if ((l >> k) & 1) add(v.at(v.cls_pos(c), k));
+      }
+      for (int d = 0; d < sp.n_doors; ++d) {
+        int n = (int)((c0 >> d) & 1) + 2 * (int)((c1 >> d) & 1);
+        if (n <= 2) {
+          if ((v.dopen >> d) & 1) {
+            uint8_t t = v.at(st.door_timer, d);
+            if (t) v.at(st.door_timer, d) = (uint8_t)(t - 1);
+            else v.dopen &= ~(1ull << d);
+          }
+        } else {
+          v.at(st.door_timer, d) = DOOR_INTERVAL;
+        }
+      }
+    } else if (op == MFG_R_MOVE_MAINTAINERS) {
+      for (int k = 0; k < sp.n_maint; ++k) {
+        int code = io.maint_act ? (int)io.maint_act[(size_t)e * sp.n_maint + k] : maint_policy<AMAX>(v, k, (uint32_t)step);
+        uint16_t p = v.at(st.maint_pos, k);
+        if (code < 8) {
+          uint16_t t;
+          if (v.try_move(p, code, false, t)) {
+            v.l_del(C_MAINT, k, k, p);
+            v.set_listed(C_MAINT, k, false);
+            v.at(st.maint_pos, k) = t;
+            v.l_add(C_MAINT, k, k, t);
+          }
+        } else if (code == MFG_MAINT_DOORUSE) {
+          v.toggle_near(p);
+        }
+      }
+    } else if (op == MFG_R_RESPAWN_DIRT) {                      // clean_up/rules.py:49-59
+      int16_t next = v.at(st.dirt_next_spawn, 0);
+      if (next < 0) {
+      } else if (next == 0) {
+        const int n_resp = (int)P[1];
+        const double amt = P[2];
+        if (io.respawn_n) {
+          int n = io.respawn_n[e];
+          if (n > n_resp) n = n_resp;
+          const uint16_t* tiles = io.respawn_pos + (size_t)e * RESPAWN_TAPE_W;
+          v.dirt_spawn(n, [&](int j) { return tiles[j]; }, [&](int) { return amt; });
+        } else {
+          Philox rng;
+          rng.init(sp.seed, (uint64_t)(tb.env_id_offset + e), RS_RESPAWN, v.at(st.episode, 0), (uint32_t)step);
+          int n_new = (int)fabs((double)n_resp + rng.uniform(-sp.dirt_n_var, sp.dirt_n_var));
+          if (n_new > MFG_MAX_DIRT) n_new = MFG_MAX_DIRT;
+          uint16_t chosen[MFG_MAX_DIRT];
+          int got = 0;
+          for (int j = 0; j < n_new; ++j) {
+            uint16_t q = v.sample_free(rng, chosen, got, false);
+            if (q == NO_POS) break;
+            chosen[got++] = q;
+          }
+          int n = got < n_resp ? got : n_resp;
+          v.dirt_spawn(n, [&](int j) { return chosen[j]; }, [&](int) { return amt; });
+        }
+        v.at(st.dirt_next_spawn, 0) = (int16_t)P[0];
+      } else {
+        v.at(st.dirt_next_spawn, 0) = (int16_t)(next - 1);
+      }
+    } else if (op == MFG_R_BATTERY_DECHARGE || op == MFG_R_DONE_BATTERY) {   // batteries/rules.py:50-63
+      for (int i = 0; i < A; ++i) {
+        double b = v.at(st.bat, i);
+        if (b != 0) v.at(st.bat, i) = fmax(0.0, P[0] + b);
+      }
+    } else if (op == MFG_R_DEST_REACH_REWARD || op == MFG_R_DONE_DEST) {     // destinations/rules.py:34-54
+      uint32_t reached = v.at(st.dest_reached, 0);
+      for (int k = 0; k < sp.n_dest; ++k) {
+        if ((reached >> k) & 1) continue;
+        uint16_t q = v.at(st.dest_pos, k);
+        int last = -1;
+        uint32_t best = 0;
+#pragma unroll
+        for (int i = 0; i < AMAX; ++i) {
+          if (i < A && v.apos[i] == q) {
+            uint32_t s = v.at(st.astamp, i);
+            if (last < 0 || s > best) { last = i; best = s; }
+          }
+        }
+        if (last >= 0) {
+          reached |= 1u << k;
+#pragma unroll
+          for (int i = 0; i < AMAX; ++i) if (i == last) rew[i] += P[0];
+        }
+      }
+      v.at(st.dest_reached, 0) = reached;
+    }
+  }
+
+  // ---- tick_post_step hooks (states.py:70-75)
+  int n_collisions = 0;
+  for (int r = 0; r < sp.n_rules; ++r) {
+    const int op = sp.rule_op[r];
+    const double* P = sp.rule_param[r];
+    if (op == MFG_R_WATCH_COLLISIONS) {                          // rules.py:276-306, states.py:228-238
+#pragma unroll
+      for (int i = 0; i < AMAX; ++i) {
+        if (i < A && v.n_coll(px(v.apos[i]), py(v.apos[i])) >= 2) { rew[i] += P[0]; ++n_collisions; }
+      }
+      if (!sp.individual_rewards) {
+        // non-agent guests of collision tiles also collect the penalty when rewards are summed (factory.py:256)
+        int n_other = 0;
+        uint32_t seen = 0;
+        if (sp.n_maint) {
+          uint32_t l = v.at(st.maint_listed, 0);
+          for (int k = 0; k < sp.n_maint; ++k) {
+            uint16_t q = v.at(st.maint_pos, k);
+            if (((l >> k) & 1) && v.n_coll(px(q), py(q)) >= 2) { ++n_other; seen |= 1u << k; }
+          }
+        }
+        for (int d = 0; d < sp.n_doors; ++d) {
+          uint16_t q = tb.door_pos[d];
+          if (((v.dlisted >> d) & 1) && !((v.dopen >> d) & 1) && v.n_coll(px(q), py(q)) >= 2) {
+            if (sp.faithful && d < 32 && ((seen >> d) & 1)) continue;   // `x.entity == guest` is uid equality
+            ++n_other;
+          }
+        }
+        other += P[0] * n_other;
+      }
+    } else if (op == MFG_R_BATTERY_DECHARGE || op == MFG_R_DONE_BATTERY) {   // batteries/rules.py:66-87
+      for (int i = 0; i < A; ++i) {
+        bool discharged = v.at(st.bat, i) == 0;
+        uint8_t f = v.at(st.aflag, i);
+        if (discharged) {
+#pragma unroll
+          for (int j = 0; j < AMAX; ++j) if (j == i) rew[j] += P[1];
+          if (P[2] != 0) f |= 1;
+        }
+        if ((f & 1) && !discharged) f &= ~1;
+        v.at(st.aflag, i) = f;
+      }
+    }
+  }
+
+  // ---- on_check_done hooks (states.py:216-226)
+  bool done = false;
+  int reason = -1;
+  for (int r = 0; r < sp.n_rules; ++r) {
+    const int op = sp.rule_op[r];
+    const double* P = sp.rule_param[r];
+    bool fired = false;
+    if (op == MFG_R_DONE_MAX_STEPS) {
+      fired = (int)P[0] <= step;
+      if (fired && reason < 0) reason = MFG_ST_DONE_MAX_STEPS;
+    } else if (op == MFG_R_DONE_ALL_DIRT) {
+      fired = v.dirt_n == 0 && step > 0;
+      if (fired) { glob += P[0]; if (reason < 0) reason = MFG_ST_DONE_ALL_DIRT; }
+    } else if (op == MFG_R_DONE_BATTERY) {
+      bool any = false;
+      for (int i = 0; i < A; ++i) any |= v.at(st.bat, i) == 0;
+      fired = P[4] != 0 && any;
+      if (fired) { glob += P[3]; if (reason < 0) reason = MFG_ST_DONE_BATTERY; }
+    } else if (op == MFG_R_DONE_DEST) {
+      uint32_t reached = v.at(st.dest_reached, 0);
+      uint32_t all = sp.n_dest >= 32 ? 0xFFFFFFFFu : ((1u << sp.n_dest) - 1);
+      int cond = (int)P[1];
+      fired = cond == 0 ? reached != 0 : reached == all;
+      if (fired) { glob += P[2]; if (reason < 0) reason = MFG_ST_DONE_DEST; }
+      else if (cond == 2) v.at(st.dest_reached, 0) = 0;
+    } else if (op == MFG_R_DONE_MAINT_COLLISION) {               // maintenance/rules.py:32-40 (group-local positions)
+#pragma unroll
+      for (int i = 0; i < AMAX; ++i) {
+        if (i >= A) continue;
+        bool hit = false;
+        for (int k = 0; k < sp.n_maint; ++k) hit |= v.at(st.maint_pos, k) == v.apos[i];
+        if (hit) { fired = true; rew[i] += -5.0; }
+      }
+      if (fired && reason < 0) reason = MFG_ST_DONE_MAINT;
+    } else if (op == MFG_R_WATCH_COLLISIONS && P[1] != 0) {      // rules.py:308-325
+      bool any = n_collisions > 0;
+      if (!any && sp.n_maint) {
+        uint32_t l = v.at(st.maint_listed, 0);
+        for (int k = 0; k < sp.n_maint; ++k) {
+          uint16_t q = v.at(st.maint_pos, k);
+          any |= ((l >> k) & 1) && v.n_coll(px(q), py(q)) >= 2;
+        }
+      }
+      fired = any;
+      if (fired) { glob += P[2]; if (reason < 0) reason = MFG_ST_DONE_COLLISION; }
+    }
+    done |= fired;
+  }
+
+  // ---- reward fold (factory.py:222-259)
+  if (sp.individual_rewards) {
+#pragma unroll
+    for (int i = 0; i < AMAX; ++i) {
+      if (i < A) {
+        double r = rew[i] + glob;
+        io.reward[(size_t)e * A + i] = (float)r;
+        v.at(st.ep_ret, i) += r;
+      }
+    }
+  } else {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < AMAX; ++i) if (i < A) s += rew[i];
+    s += other;
+    s += glob;
+    io.reward[e] = (float)s;
+    v.at(st.ep_ret, 0) += s;
+  }
+  io.done[e] = done ? 1 : 0;
+  v.store();
+
+  // ---- episode statistics + optional in-kernel auto reset
+  if (n_collisions) stat_add(tb, MFG_ST_COLLISIONS, (unsigned long long)n_collisions);
+  if (done) {
+    stat_add(tb, MFG_ST_EPISODES, 1);
+    stat_add(tb, MFG_ST_STEPS, (unsigned long long)step);
+    if (reason >= 0) stat_add(tb, reason, 1);
+    double tot = 0.0;
+    const int nr = sp.individual_rewards ? A : 1;
+    for (int i = 0; i < nr; ++i) { double x = v.at(st.ep_ret, i); tot += x; stat_add_f64(tb, MFG_ST_RETURN_AGENT0 + i, x); }
+    stat_add_f64(tb, MFG_ST_RETURN_SUM, tot);
+    if (io.auto_reset) env_reset<AMAX>(sp, tb, st, e, v.at(st.episode, 0) + 1);
+  }
+}
+
+// ================================================================================================
+// observation, one (env, agent) per thread, all parity modes (the tiled fast path lives in mfg_kernels.cu)
+// ================================================================================================
+constexpr int RANK_INF = 0xFFFF;
+
+template <int AMAX>
+struct ObsCtx {
+  Env<AMAX>& v;
+  int a, ax, ay, r, D, R, BW;
+  uint16_t rank[(2 * 2 * 3 + 3) * (2 * 2 * 3 + 3)];      // (2*radius+1)^2 with radius = D = 7 for pomdp_r = 3
+  MFG_HD ObsCtx(Env<AMAX>& v_) : v(v_) {}
+  MFG_HD bool blocks_light(int x, int y) const {
+    if (!v.in_grid(x, y)) return false;
+    return v.tb.wall[x * v.sp.W + y] || v.closed_listed_door(x, y);
+  }
+  MFG_HD int rank_of(uint16_t p) const {
+    if (p == NO_POS) return RANK_INF;
+    int dx = px(p) - ax, dy = py(p) - ay;
+    if (dx < -R || dx > R || dy < -R || dy > R) return RANK_INF;
+    return rank[(dx + R) * BW + (dy + R)];
+  }
+};
+
+// Does some OTHER visible listed entity with the same uid precede (cls, idx) in first-visit order?
+// (observation_builder.py:155 `set(visible_entities)` with uid equality)
+template <int AMAX>
+MFG_HD bool uid_shadowed(const ObsCtx<AMAX>& o, int cls, int idx, int uid, int my_rank) {
+  const Env<AMAX>& v = o.v; const MfgSpec& sp = v.sp; const State& st = v.st; const Tables& tb = v.tb;
+  if (uid < sp.n_walls && o.rank_of(tb.wall_pos[uid]) < my_rank) return true;      // walls are always listed
+  if (uid < sp.n_doors && cls != C_DOOR && ((v.dlisted >> uid) & 1) && o.rank_of(tb.door_pos[uid]) < my_rank) return true;
+  if (sp.has_dirt && uid < (int)v.at(st.dirt_next_uid, 0)) {
+    for (int k = 0; k < v.dirt_end; ++k) {
+      if (cls == C_DIRT && k == idx) continue;
+      if (v.at(st.dirt_uid, k) == uid && ((v.dirt_listed >> k) & 1) && o.rank_of(v.at(st.dirt_pos, k)) < my_rank) return true;
+    }
+  }
+  for (int c = C_ITEM; c <= C_MAINT; ++c) {
+    if (c == cls || uid >= v.cls_count(c)) continue;
+    if (((v.at(v.cls_listed(c), 0) >> uid) & 1) && o.rank_of(v.at(v.cls_pos(c), uid)) < my_rank) return true;
+  }
+  return false;
+}
+
+// out points at this agent's first channel: [C_a][D*D] floats, contiguous
+template <int AMAX>
+MFG_HDN void obs_agent_direct(const MfgSpec& sp, const Tables& tb, const State& st, int64_t e, int a, float* out) {
+  Env<AMAX> v(sp, tb, st, e);
+  v.load();
+  ObsCtx<AMAX> o(v);
+  const int r = sp.pomdp_r, D = 2 * r + 1, R = D, BW = 2 * R + 1, DD = D * D;
+  o.a = a; o.ax = px(v.apos[a]); o.ay = py(v.apos[a]); o.r = r; o.D = D; o.R = R; o.BW = BW;
+  const int C = sp.n_channels[a];
+  for (int i = 0; i < C * DD; ++i) out[i] = 0.0f;
+  for (int i = 0; i < BW * BW; ++i) o.rank[i] = RANK_INF;
+
+  // ---- ray walk (ray_caster.py:66-104): first-visit rank per cell of the radius box
+  int visit = 0;
+  for (int ray = 0; ray < sp.n_rays; ++ray) {
+    int pxr = o.ax, pyr = o.ay;
+    for (int s = 0; s < sp.ray_len[ray]; ++s) {
+      int dx = sp.ray_dx[ray][s], dy = sp.ray_dy[ray][s];
+      int x = o.ax + dx, y = o.ay + dy;
+      int cx = x - pxr, cy = y - pyr;
+      bool hits = o.blocks_light(x, y);
+      bool diag = (cx != 0 && cy != 0) && o.blocks_light(x, y - cy) && o.blocks_light(x - cx, y);
+      if (!diag) {
+        uint16_t& rk = o.rank[(dx + R) * BW + (dy + R)];
+        if (rk == RANK_INF) rk = (uint16_t)visit;
+      }
+      ++visit;
+      if (hits || diag) break;
+      pxr = x; pyr = y;
+    }
+  }
+
+  const uint32_t* chm = sp.term_chmask[a];
+  auto in_window = [&](uint16_t p, int& cell) {
+    int dx = px(p) - o.ax + r, dy = py(p) - o.ay + r;
+    if (dx < 0 || dy < 0 || dx >= D || dy >= D) return false;
+    cell = dx * D + dy;
+    return true;
+  };
+  auto add = [&](uint32_t mask, int cell, double val) {
+    while (mask) {
+      int c = 0;
+      while (!((mask >> c) & 1)) ++c;
+      mask &= mask - 1;
+      float& f = out[c * DD + cell];
+      f = (float)((double)f + val);
+    }
+  };
+
+  // ---- walls (uid = row-major wall index)
+  if (chm[MFG_G_WALLS]) {
+    for (int dx = -r; dx <= r; ++dx) for (int dy = -r; dy <= r; ++dy) {
+      int x = o.ax + dx, y = o.ay + dy;
+      if (!v.in_grid(x, y) || !tb.wall[x * sp.W + y]) continue;
+      int rk = o.rank[(dx + R) * BW + (dy + R)];
+      if (rk == RANK_INF) continue;
+      if (sp.faithful) {
+        // walls are never shadowed by other walls; only a dynamic entity with the same uid seen earlier hides it
+        int uid = tb.wall_uid[x * sp.W + y];
+        bool sh = false;
+        if (uid < sp.n_doors && ((v.dlisted >> uid) & 1) && o.rank_of(tb.door_pos[uid]) < rk) sh = true;
+        if (!sh && sp.has_dirt && uid < (int)v.at(st.dirt_next_uid, 0))
+          for (int k = 0; k < v.dirt_end && !sh; ++k)
+            sh = v.at(st.dirt_uid, k) == uid && ((v.dirt_listed >> k) & 1) && o.rank_of(v.at(st.dirt_pos, k)) < rk;
+        for (int c = C_ITEM; c <= C_MAINT && !sh; ++c)
+          sh = uid < v.cls_count(c) && ((v.at(v.cls_listed(c), 0) >> uid) & 1) && o.rank_of(v.at(v.cls_pos(c), uid)) < rk;
+        if (sh) continue;
+      }
+      add(chm[MFG_G_WALLS], (dx + r) * D + (dy + r), 1.0);
+    }
+  }
+  // ---- agents (string identifiers: never shadowed)
+  for (int j = 0; j < v.A; ++j) {
+    int cell;
+    if (!chm[MFG_G_AGENT0 + j] || !in_window(v.apos[j], cell)) continue;
+    if (o.rank_of(v.apos[j]) == RANK_INF) continue;
+    add(chm[MFG_G_AGENT0 + j], cell, 1.0);
+  }
+  // ---- small groups with constant encodings
+  const int term_of[8] = {MFG_G_DOORS, MFG_G_DIRT, MFG_G_ITEMS, MFG_G_PODS, MFG_G_DEST, MFG_G_DROPOFF, MFG_G_MACHINES, MFG_G_MAINT};
+  for (int c = C_ITEM; c <= C_MAINT; ++c) {
+    uint32_t m = chm[term_of[c]];
+    int n = v.cls_count(c);
+    if (!m || !n) continue;
+    uint32_t l = v.at(v.cls_listed(c), 0);
+    for (int k = 0; k < n; ++k) {
+      uint16_t p = v.at(v.cls_pos(c), k);
+      int cell;
+      if (!((l >> k) & 1) || p == NO_POS || !in_window(p, cell)) continue;
+      int rk = o.rank_of(p);
+      if (rk == RANK_INF) continue;
+      if (sp.faithful && uid_shadowed(o, c, k, k, rk)) continue;
+      double enc = c == C_MACH ? ENC_MACHINE : (c == C_DEST && ((v.at(st.dest_reached, 0) >> k) & 1)) ? 0.0 : 1.0;
+      add(m, cell, enc);
+    }
+  }
+  // ---- doors, then dirt (fractional encodings go last so that integer stacks are summed exactly first)
+  if (chm[MFG_G_DOORS]) {
+    for (int d = 0; d < sp.n_doors; ++d) {
+      uint16_t p = tb.door_pos[d];
+      int cell;
+      if (!((v.dlisted >> d) & 1) || !in_window(p, cell)) continue;
+      int rk = o.rank_of(p);
+      if (rk == RANK_INF) continue;
+      if (sp.faithful && uid_shadowed(o, C_DOOR, d, d, rk)) continue;
+      add(chm[MFG_G_DOORS], cell, ((v.dopen >> d) & 1) ? ENC_DOOR_OPEN : ENC_DOOR_CLOSED);
+    }
+  }
+  if (sp.has_dirt && chm[MFG_G_DIRT]) {
+    for (int k = 0; k < v.dirt_end; ++k) {
+      uint16_t p = v.at(st.dirt_pos, k);
+      int cell;
+      if (p == NO_POS || !((v.dirt_listed >> k) & 1) || !in_window(p, cell)) continue;
+      int rk = o.rank_of(p);
+      if (rk == RANK_INF) continue;
+      if (sp.faithful && uid_shadowed(o, C_DIRT, k, v.at(st.dirt_uid, k), rk)) continue;
+      add(chm[MFG_G_DIRT], cell, v.at(st.dirt_amt, k));
+    }
+  }
+  // ---- scalar channels (observation_builder.py:205-218, entity/util.py:56-66)
+  for (int c = 0; c < C; ++c) {
+    int kind = sp.ch_kind[a][c];
+    if (kind == MFG_CH_BATTERY) out[c * DD] = (float)v.at(st.bat, a);
+    else if (kind == MFG_CH_GLOBALPOS) {
+      out[c * DD] = (float)((double)o.ax / (double)sp.H);
+      out[c * DD + 1] = (float)((double)o.ay / (double)sp.W);
+    }
+  }
+}
+
+}  // namespace mfg

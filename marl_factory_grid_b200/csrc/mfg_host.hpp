@@ -1,0 +1,123 @@
+// mfg_host.hpp - host-side helpers shared by the CUDA library (mfg_abi.cu) and the test-only host
+// build (tests/hostsim): state layout computation and the derived level tables.
+#pragma once
+#include <cstring>
+#include <string>
+#include <vector>
+#include "mfg_core.cuh"
+
+namespace mfg {
+
+struct FieldInfo {
+  const char* name;
+  size_t offset;
+  int rows;
+  int elem_size;
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// field-major layout: each field [rows][N], every field start 256-byte aligned
+inline size_t compute_layout(const MfgSpec& sp, int64_t N, std::vector<FieldInfo>& fields) {
+  fields.clear();
+  size_t off = 0;
+#define F(type, name, rows_expr)                                            \
+  {                                                                         \
+    int rows = (int)(rows_expr);                                            \
+    fields.push_back(FieldInfo{#name, off, rows, (int)sizeof(type)});       \
+    off = align_up(off + (size_t)rows * (size_t)N * sizeof(type), 256);     \
+  }
+  MFG_STATE_FIELDS(F)
+#undef F
+  return off;
+}
+
+inline void bind_state(const MfgSpec& sp, int64_t N, void* base, State& st) {
+  std::vector<FieldInfo> fields;
+  compute_layout(sp, N, fields);
+  st.N = N;
+  size_t i = 0;
+  char* b = static_cast<char*>(base);
+#define F(type, name, rows_expr) st.name = reinterpret_cast<type*>(b + fields[i++].offset);
+  MFG_STATE_FIELDS(F)
+#undef F
+}
+
+// derived tables, built on the host from the spec's level arrays
+struct HostTables {
+  std::vector<uint8_t> wall, door_map, nexthop;
+  std::vector<uint16_t> floor_pos, floor_index, wall_uid, wall_pos, door_pos;
+  std::vector<uint64_t> wall_win;
+};
+
+inline std::string build_tables(const MfgSpec& sp, HostTables& t) {
+  const int H = sp.H, W = sp.W;
+  if (H <= 0 || W <= 0 || H > 255 || W > 255) return "level shape must be within 1..255";
+  if (!sp.walls || !sp.floor_pos) return "walls / floor_pos must not be NULL";
+  if (sp.n_doors && !sp.door_pos) return "door_pos must not be NULL when n_doors > 0";
+  t.wall.assign(sp.walls, sp.walls + (size_t)H * W);
+  t.floor_pos.assign(sp.floor_pos, sp.floor_pos + sp.n_floor);
+  t.door_pos.assign(sp.door_pos, sp.door_pos + sp.n_doors);
+  if (t.door_pos.empty()) t.door_pos.push_back(NO_POS);
+  t.door_map.assign((size_t)H * W, 0xFF);
+  for (int d = 0; d < sp.n_doors; ++d) {
+    int x = px(sp.door_pos[d]), y = py(sp.door_pos[d]);
+    if (x >= H || y >= W) return "door position outside the level";
+    t.door_map[(size_t)x * W + y] = (uint8_t)d;
+  }
+  t.floor_index.assign((size_t)H * W, 0xFFFF);
+  for (int f = 0; f < sp.n_floor; ++f) {
+    int x = px(sp.floor_pos[f]), y = py(sp.floor_pos[f]);
+    if (x >= H || y >= W || t.wall[(size_t)x * W + y]) return "floor_pos entry is not a floor tile";
+    t.floor_index[(size_t)x * W + y] = (uint16_t)f;
+  }
+  t.wall_uid.assign((size_t)H * W, 0xFFFF);
+  t.wall_pos.clear();
+  for (int x = 0; x < H; ++x)
+    for (int y = 0; y < W; ++y)
+      if (t.wall[(size_t)x * W + y]) {
+        t.wall_uid[(size_t)x * W + y] = (uint16_t)t.wall_pos.size();
+        t.wall_pos.push_back(mkpos(x, y));
+      }
+  if ((int)t.wall_pos.size() != sp.n_walls) return "n_walls does not match the wall map";
+  if (t.wall_pos.empty()) t.wall_pos.push_back(NO_POS);
+  if (sp.nexthop) t.nexthop.assign(sp.nexthop, sp.nexthop + (size_t)sp.n_floor * sp.n_floor);
+  // per-tile window wall masks (bit = dx_idx * D + dy_idx), used by the tiled observation kernel
+  const int r = sp.pomdp_r, D = 2 * r + 1;
+  t.wall_win.assign((size_t)H * W, 0);
+  if (r >= 1 && r <= 3) {
+    for (int x = 0; x < H; ++x)
+      for (int y = 0; y < W; ++y) {
+        uint64_t m = 0;
+        for (int dx = -r; dx <= r; ++dx)
+          for (int dy = -r; dy <= r; ++dy) {
+            int xx = x + dx, yy = y + dy;
+            if (xx >= 0 && yy >= 0 && xx < H && yy < W && t.wall[(size_t)xx * W + yy])
+              m |= 1ull << ((dx + r) * D + (dy + r));
+          }
+        t.wall_win[(size_t)x * W + y] = m;
+      }
+  }
+  return "";
+}
+
+inline std::string validate_spec(const MfgSpec& sp) {
+  if (sp.n_agents < 1 || sp.n_agents > MFG_MAX_AGENTS) return "n_agents out of range";
+  if (sp.pomdp_r < 1 || sp.pomdp_r > 3) return "pomdp_r must be 1..3 (full observability is not supported yet)";
+  if (sp.n_doors < 0 || sp.n_doors > MFG_MAX_DOORS) return "n_doors out of range";
+  if (sp.has_dirt && (sp.dirt_slots < 1 || sp.dirt_slots > MFG_MAX_DIRT)) return "dirt_slots out of range";
+  if (sp.n_rules < 0 || sp.n_rules > MFG_MAX_RULES) return "n_rules out of range";
+  if (sp.n_groups < 0 || sp.n_groups > MFG_MAX_GROUPS) return "n_groups out of range";
+  if (sp.n_rays < 1 || sp.n_rays > MFG_MAX_RAYS) return "n_rays out of range";
+  const int small[] = {sp.n_items, sp.n_dropoff, sp.n_pods, sp.n_dest, sp.n_machines, sp.n_maint};
+  for (int n : small) if (n < 0 || n > MFG_MAX_SMALL) return "small group size out of range";
+  for (int a = 0; a < sp.n_agents; ++a) {
+    if (sp.n_actions[a] < 1 || sp.n_actions[a] > MFG_MAX_ACTIONS) return "n_actions out of range";
+    if (sp.n_channels[a] < 1 || sp.n_channels[a] > MFG_MAX_CHANNELS) return "n_channels out of range";
+  }
+  for (int r = 0; r < sp.n_rays; ++r) if (sp.ray_len[r] < 1 || sp.ray_len[r] > MFG_MAX_RAY_LEN) return "ray_len out of range";
+  if (sp.n_floor < sp.n_agents) return "fewer floor tiles than agents";
+  return "";
+}
+
+}  // namespace mfg
