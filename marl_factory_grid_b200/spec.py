@@ -175,7 +175,13 @@ class EnvSpec:
 
     @property
     def obs_d(self) -> int:
+        """Window diameter of the egocentric POMDP observation (pomdp_r >= 1)."""
         return 2 * self.pomdp_r + 1
+
+    @property
+    def obs_shape(self) -> Tuple[int, int]:
+        """observation_builder.py:51: (D, D) for POMDP, the whole level when pomdp_r == 0."""
+        return (self.obs_d, self.obs_d) if self.pomdp_r else (self.H, self.W)
 
     @property
     def channels_per_agent(self) -> List[int]:

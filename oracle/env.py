@@ -36,7 +36,10 @@ class OracleEnv:
         self.A = spec.n_agents
         self.wall = spec.walls
         self.H, self.W = spec.H, spec.W
-        self.rays = full_rays(spec.obs_d)                 # radius == window diameter (defect B14)
+        # radius handed to RayCaster = min(obs_shape): the window DIAMETER for POMDP (defect B14), min(H, W) when
+        # pomdp_r == 0 (full observability, observation_builder.py:51, 244)
+        self.full_obs = spec.pomdp_r == 0
+        self.rays = full_rays(min(spec.H, spec.W) if self.full_obs else spec.obs_d)
         # wall uid = row-major wall index (walls are created first, level_parser.py:77-78)
         self.wall_uid = {tuple(p): k for k, p in enumerate(np.argwhere(spec.walls).tolist())}
         self._rules = spec.rules
@@ -413,17 +416,18 @@ class OracleEnv:
     def observe_agent(self, a):
         """observation_builder.py:138-220.  Returns f64 [C_a, D, D]."""
         sp = self.spec
-        r, D = sp.pomdp_r, sp.obs_d
+        r = sp.pomdp_r
+        shape = (self.H, self.W) if self.full_obs else (sp.obs_d, sp.obs_d)
         ax, ay = self.apos[a]
         planes = {}
         for tag, (ex, ey), enc in self.visible(a):
             term = tag if isinstance(tag, int) else self._CLS_GROUP[tag]
-            pl = planes.setdefault(term, np.zeros((D, D)))
-            x, y = ex - ax + r, ey - ay + r
-            if 0 <= x < D and 0 <= y < D:
+            pl = planes.setdefault(term, np.zeros(shape))
+            x, y = (ex, ey) if self.full_obs else (ex - ax + r, ey - ay + r)      # observation_builder.py:156-160
+            if 0 <= x < shape[0] and 0 <= y < shape[1]:
                 pl[x, y] += enc
         chans = sp.agents[a].channels
-        obs = np.zeros((len(chans), D, D))
+        obs = np.zeros((len(chans),) + shape)
         for c, ch in enumerate(chans):
             if ch.kind == S.CH_TERMS:
                 if len(ch.terms) == 1 and not ch.name.startswith('Combined('):

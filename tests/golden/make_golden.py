@@ -227,6 +227,7 @@ PLAN = {
     'cfg3': [(0, 'U', 300), (1, 'U', 300), (3, 'I', 200)],
     'cfg4': [(0, 'U', 500), (1, 'U', 500), (2, 'U', 500), (3, 'U', 500), (4, 'I', 300), (5, 'I', 300)],
     'stress': [(s, 'U', 200) for s in range(8)] + [(s, 'I', 200) for s in range(8, 12)],
+    'obs_test': [(0, 'U', 3), (1, 'I', 3)],
     'stress2': [(s, 'U', 150) for s in range(4)] + [(s, 'I', 150) for s in range(4, 6)],
 }
 

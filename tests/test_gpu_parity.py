@@ -1,0 +1,204 @@
+"""GPU parity tests (run with `-m gpu` on the B200 box).  Everything goes through the C ABI
+(libmfg_b200.so via marl_factory_grid_b200.engine); the checkers are the committed reference traces
+(tests/golden), the oracle and the test-only host build of the device code.
+
+Bars: integer state, door timers, f64 dirt amounts / battery levels, done flags and observations are
+compared bit-exactly; rewards (emitted as f32) within rtol 1e-6 of the reference's f64 value.
+"""
+import numpy as np
+import pytest
+
+from golden_util import ALL_CFGS, episodes, snap_at, spec_for
+from hostsim_util import HostSim, tape_respawn
+
+torch = pytest.importorskip('torch')
+pytestmark = pytest.mark.gpu
+
+CMP_KEYS = ['agent_pos', 'door_open', 'door_timer', 'door_listed', 'dirt_n', 'dirt_pos', 'dirt_amt', 'dirt_uid',
+            'dirt_listed', 'item_pos', 'item_listed', 'pod_listed', 'dest_listed', 'drop_listed', 'machine_listed',
+            'maint_pos', 'maint_listed', 'dest_reached', 'battery', 'step', 'dirt_next_uid', 'dirt_next_spawn',
+            'paralysed']
+
+
+def _engine(es, n, **kw):
+    from marl_factory_grid_b200.engine import Engine
+    return Engine(es, n, device='cuda:0', **kw)
+
+
+def _replay_batch(cfg, mode, obs_kernels):
+    """All episodes of (cfg, mode) as ONE batch: env i replays episode i; finished episodes idle."""
+    es = spec_for(cfg)
+    eps = [ep for ep in episodes(cfg) if ep['meta']['mode'] == mode]
+    if not eps:
+        pytest.skip(f'no {mode} episodes for {cfg}')
+    N, A, NM = len(eps), es.n_agents, es.n_maint
+    eng = _engine(es, N, faithful=mode == 'U')
+    for i, ep in enumerate(eps):
+        eng.load_snapshot(i, snap_at(ep, 0))
+    T = [len(ep['actions']) for ep in eps]
+
+    def check_obs(t):
+        for kern in obs_kernels:
+            eng.set_option('obs_kernel', kern)
+            obs = eng.observe().cpu().numpy()
+            for i, ep in enumerate(eps):
+                if t <= T[i]:
+                    np.testing.assert_array_equal(obs[i], ep['obs'][t], err_msg=f'{cfg}/{mode} env{i} t={t} obs kernel {kern}')
+
+    check_obs(0)
+    for t in range(max(T)):
+        acts = np.zeros((N, A), np.int32)
+        ma = np.full((N, max(NM, 1)), 8, np.uint8)
+        rn = np.zeros(N, np.int8)
+        rp = np.zeros((N, 8), np.uint16)
+        for i, ep in enumerate(eps):
+            if t < T[i]:
+                acts[i] = ep['actions'][t]
+                if NM:
+                    ma[i, :NM] = ep['maint_act'][t]
+                rn[i], rp[i] = tape_respawn(ep, t)
+        tape = dict(maint_action=ma[:, :NM] if NM else None, respawn_n=rn, respawn_pos=rp)
+        rew, done = eng.step(acts, tape=tape)
+        rew, done = rew.cpu().numpy(), done.cpu().numpy()
+        fields = eng.fields_numpy()
+        for i, ep in enumerate(eps):
+            if t >= T[i]:
+                continue
+            got, want = eng.snapshot(i, fields), snap_at(ep, t + 1)
+            for key in CMP_KEYS:
+                np.testing.assert_array_equal(got[key], want[key], err_msg=f'{cfg}/{mode} env{i} step {t + 1}: {key}')
+            np.testing.assert_allclose(rew[i], ep['reward'][t], rtol=1e-6, atol=1e-7, err_msg=f'{cfg}/{mode} env{i} step {t + 1}')
+            assert bool(done[i]) == bool(ep['done'][t]), f'{cfg}/{mode} env{i} step {t + 1} done'
+        check_obs(t + 1)
+    eng.close()
+
+
+@pytest.mark.parametrize('cfg', ALL_CFGS)
+def test_replay_untouched_reference(cfg):
+    """faithful mode == the unmodified reference (uid-equality artefact included); direct observation kernel."""
+    _replay_batch(cfg, 'U', obs_kernels=[1])
+
+
+@pytest.mark.parametrize('cfg', ALL_CFGS)
+def test_replay_identity_reference(cfg):
+    """identity mode == identity-patched reference; BOTH observation kernels (direct and tiled)."""
+    _replay_batch(cfg, 'I', obs_kernels=[1, 2])
+
+
+@pytest.mark.parametrize('cfg', ['cfg1', 'cfg2', 'cfg3', 'cfg4', 'stress2'])
+@pytest.mark.parametrize('faithful', [False, True])
+def test_freerun_matches_host_build_of_device_code(cfg, faithful):
+    """Free-running (Philox spawn, dirt respawn, maintainer policy, in-kernel auto reset): the CUDA kernels and the
+    g++ build of the same per-env code must agree bit-for-bit on every field, reward, done and observation."""
+    es = spec_for(cfg)
+    N, steps = 96, 70
+    eng = _engine(es, N, faithful=faithful, seed=1234)
+    sim = HostSim(es, N, faithful=faithful, seed=1234)
+    eng.reset()
+    sim.reset()
+    acts = torch.zeros((N, es.n_agents), dtype=torch.int32, device='cuda:0')
+    for t in range(steps):
+        eng.random_actions(acts, seed=99, step_index=t)
+        a = acts.cpu().numpy()
+        obs, rew, done = eng.step_observe(acts, auto_reset=True)
+        r2, d2 = sim.step(a, auto_reset=True)
+        f = eng.fields_numpy()
+        for name, arr in sim.fields.items():
+            if name == 'ep_ret':
+                np.testing.assert_allclose(f[name], arr, rtol=1e-12, atol=1e-12)
+            else:
+                np.testing.assert_array_equal(f[name], arr, err_msg=f'{cfg} t={t} field {name}')
+        np.testing.assert_array_equal(rew.cpu().numpy(), r2, err_msg=f'{cfg} t={t} reward')
+        np.testing.assert_array_equal(done.cpu().numpy(), d2, err_msg=f'{cfg} t={t} done')
+        np.testing.assert_array_equal(obs.cpu().numpy(), sim.observe(), err_msg=f'{cfg} t={t} obs')
+    s1, s2 = eng.stats(), sim.stats()
+    np.testing.assert_array_equal(s1[:11], s2[:11])
+    eng.close()
+
+
+@pytest.mark.parametrize('cfg', ['cfg2', 'cfg4'])
+def test_tiled_observation_kernel_equals_direct_kernel_at_scale(cfg):
+    """Size-independent property at a larger batch: both observation kernels produce identical tensors, agents never
+    stand on walls, door timers stay within the auto-close interval, dirt amounts within (0, 5]."""
+    es = spec_for(cfg)
+    N = 8192 + 5                     # ragged: not a multiple of the 32-env CTA tile
+    eng = _engine(es, N, faithful=False, seed=7)
+    eng.reset()
+    acts = torch.zeros((N, es.n_agents), dtype=torch.int32, device='cuda:0')
+    walls = torch.as_tensor(es.walls, device='cuda:0')
+    for t in range(40):
+        eng.random_actions(acts, seed=3, step_index=t)
+        eng.step(acts, auto_reset=True)
+        if t % 8 == 7:
+            eng.set_option('obs_kernel', 1)
+            o1 = eng.observe().clone()
+            eng.set_option('obs_kernel', 2)
+            o2 = eng.observe().clone()
+            assert torch.equal(o1, o2), f'{cfg} t={t}: tiled != direct'
+            apos = eng.fields['apos'].to(torch.int64) & 0xFFFF
+            assert not walls[apos >> 8, apos & 255].any()
+            if es.n_doors:
+                assert int(eng.fields['door_timer'].max()) <= 10
+            if es.has_dirt:
+                live = (eng.fields['dirt_pos'].to(torch.int64) & 0xFFFF) != 0xFFFF
+                amt = eng.fields['dirt_amt'][live]
+                assert float(amt.min()) > 0 and float(amt.max()) <= 5.0
+    eng.close()
+
+
+def test_env_shards_are_independent_of_the_partition():
+    """Multi-GPU property on one device: envs [0, 256) as one engine == two engines of 128 with env_id_offset 0 / 128."""
+    es = spec_for('cfg4')
+    whole = _engine(es, 256, faithful=False, seed=5)
+    parts = [_engine(es, 128, faithful=False, seed=5, env_id_offset=o) for o in (0, 128)]
+    for e in [whole] + parts:
+        e.reset()
+    acts = torch.zeros((256, es.n_agents), dtype=torch.int32, device='cuda:0')
+    for t in range(30):
+        whole.random_actions(acts, seed=11, step_index=t)
+        o, r, d = whole.step_observe(acts, auto_reset=True)
+        for k, p in enumerate(parts):
+            sl = slice(128 * k, 128 * (k + 1))
+            o2, r2, d2 = p.step_observe(acts[sl].contiguous(), auto_reset=True)
+            assert torch.equal(o[sl], o2) and torch.equal(r[sl], r2) and torch.equal(d[sl], d2)
+    tot = whole.stats()
+    np.testing.assert_array_equal(tot[:11], sum(p.stats()[:11] for p in parts))
+    for e in [whole] + parts:
+        e.close()
+
+
+def test_factory_surface_unbatched_matches_reference_shapes():
+    from marl_factory_grid_b200 import Factory
+    from golden_util import CONFIGS
+    f = Factory(CONFIGS / 'cfg4.yaml', device='cuda:0')
+    ep = episodes('cfg4')[0]
+    assert list(f.named_action_space) == ep['meta']['agent_names']
+    assert f.named_action_space == ep['meta']['named_action_space']
+    obs = f.reset()
+    assert list(obs) == ep['meta']['agent_names']
+    assert [o.shape for o in obs.values()] == [(7, 7, 7), (8, 7, 7), (7, 7, 7), (14, 7, 7)]
+    _, o, r, d, info = f.step([0, 1, 2, 3])
+    assert len(o) == 4 and len(r) == 4 and isinstance(d, bool) and info['step'] == 1
+    f.close()
+
+
+def test_factory_batched_host_path_and_stats():
+    from marl_factory_grid_b200 import Factory
+    from golden_util import CONFIGS
+    N = 1024
+    f = Factory(CONFIGS / 'cfg3.yaml', n_envs=N, device='cuda:0', parity='identity', auto_reset=True)
+    obs = f.reset()
+    assert obs['Agent[Wolfgang]'].shape == (N, 5, 7, 7)
+    A = f.spec.n_agents
+    h_act = torch.zeros((N, A), dtype=torch.int32).pin_memory()
+    h_rew = torch.zeros((N, A), dtype=torch.float32).pin_memory()
+    h_done = torch.zeros(N, dtype=torch.uint8).pin_memory()
+    h_obs = torch.zeros((N, f.spec.total_channels, 7, 7), dtype=torch.float32).pin_memory()
+    g = torch.Generator().manual_seed(0)
+    for t in range(120):
+        h_act.copy_(torch.randint(0, 12, (N, A), generator=g, dtype=torch.int32))
+        f.engine.step_host(h_act, h_rew, h_done, h_obs, auto_reset=True)
+    assert torch.equal(h_obs, f.engine.obs.cpu())
+    st = f.episode_stats()
+    assert st['episodes'] > 0 and st['steps'] >= st['episodes']
+    f.close()

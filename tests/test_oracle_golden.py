@@ -17,7 +17,7 @@ CMP_KEYS = ['agent_pos', 'door_open', 'door_timer', 'door_listed', 'dirt_n', 'di
             'paralysed']
 
 
-@pytest.mark.parametrize('cfg,k', episode_ids())
+@pytest.mark.parametrize('cfg,k', episode_ids(include_oracle_only=True))
 def test_oracle_replays_reference_episode(cfg, k):
     ep = episodes(cfg)[k]
     spec = spec_for(cfg)
