@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py - agent-steps/s including observations for the batched marl-factory-grid stepping engine.
+
+One "step" = one pass of the hot path over the whole batch: draw uniform random actions on the device (Philox),
+`mfg_step` (actions, rule hooks, done/reward, in-kernel auto reset) and `mfg_observe` (ray-cast observation
+tensor).  Workload at every N: BASELINE.json configs[3]/[4], the all-modules config (cfg4: level `large`,
+4 heterogeneous agents, POMDP r=3, every module incl. machines + maintainer) with 1,048,576 envs PER GPU
+(the 1M..8M sweep of configs[4] => weak scaling; envs shard by global env id, no per-step collective, only the
+episode-statistics vector is all-reduced over NCCL).
+
+    python bench.py --gpus 1 --steps 50 --warmup 10            # this engine
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1   # CPU reference arm (oracle port, all host cores)
+
+Prints ONE JSON line (rank 0).  Extra keys: `roofline` (dominant kernel vs measured HBM peak), `cpu_baseline`
+(oracle port on the host cores, bounded sample), `e2e` (host buffers through mfg_step_host, copies timed),
+`clocks`, `gpu_launches`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = 'agent-steps/sec incl. obs'
+UNIT = 'agent-steps/s'
+CONFIGS = ROOT / 'marl_factory_grid_b200' / 'configs'
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's CPU path, multiprocess over the host cores
+# ---------------------------------------------------------------------------------------------------------------
+class CpuPool:
+    """Persistent multiprocess pool of oracle environments (one per host core)."""
+
+    def __init__(self, cfg: str, faithful: bool, procs: int):
+        import multiprocessing as mp
+        from oracle.freerun import worker_init
+        self.procs = procs
+        self.pool = mp.get_context('spawn').Pool(procs, initializer=worker_init,
+                                                 initargs=(str(CONFIGS / f'{cfg}.yaml'), faithful, 1000))
+
+    def run(self, steps_per_worker: int):
+        """Every worker advances its env by steps_per_worker; returns (agent_steps, slowest worker seconds)."""
+        from oracle.freerun import worker_run
+        res = self.pool.map(worker_run, [steps_per_worker] * self.procs, chunksize=1)
+        return sum(r[0] for r in res), max(r[1] for r in res)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def run_reference(args):
+    """--impl reference: times the CPU path (oracle port; the Python reference itself cannot travel to the GPU box)."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    procs = os.cpu_count() or 1
+    per_step = max(20, args.cpu_steps // max(args.steps, 1))     # env-steps per worker per bench "step"
+    pool = CpuPool(args.config, args.parity == 'faithful', procs)
+    for _ in range(max(args.warmup, 1)):
+        pool.run(per_step)
+    tot_steps, tot_time = 0, 0.0
+    for _ in range(args.steps):
+        agent_steps, slowest = pool.run(per_step)
+        tot_steps += agent_steps
+        tot_time += slowest
+    pool.close()
+    value = tot_steps / tot_time
+    sample = (f'{procs} procs x {per_step} env-steps of {args.config} per bench step (random actions, obs built every '
+              f'step, in-place reset)')
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': 1e3 * tot_time / max(args.steps, 1), 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': f'{args.config} all-modules, CPU oracle port of the reference step+obs', 'parity': args.parity},
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': procs, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md: sample nvidia-smi DURING the timed region)
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(',')])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = max((int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()), default=None)
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith('active')})
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': reasons, 'samples': len(self.rows)}
+
+
+def hbm_peak():
+    p = ROOT / 'MEASURED_PEAKS.json'
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------
+def run_engine(args):
+    import torch
+    import torch.distributed as dist
+    from marl_factory_grid_b200 import FactoryConfigParser
+    from marl_factory_grid_b200.engine import Engine
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    es = FactoryConfigParser(CONFIGS / f'{args.config}.yaml').compile()
+    n_local = args.envs_per_gpu
+    A = es.n_agents
+    eng = Engine(es, n_local, device=dev, faithful=args.parity == 'faithful', seed=es.env_seed,
+                 env_id_offset=rank * n_local)
+    if args.obs_kernel:
+        eng.set_option('obs_kernel', args.obs_kernel)
+    acts = torch.zeros((n_local, A), dtype=torch.int32, device=dev)
+    eng.reset()
+
+    def one_step(i, ev=None):
+        eng.random_actions(acts, seed=0, step_index=i)
+        eng.step(acts, auto_reset=True)
+        if ev is not None:
+            ev[0].record()
+        eng.observe()
+        if ev is not None:
+            ev[1].record()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(args.warmup):
+        one_step(i)
+    barrier()
+    launches0 = eng.info('launches')
+    obs_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        start.record()
+        for i in range(args.steps):
+            one_step(args.warmup + i, obs_events[i])
+        stop.record()
+        barrier()
+    elapsed_ms = start.elapsed_time(stop)
+    obs_ms = sum(a.elapsed_time(b) for a, b in obs_events) / max(args.steps, 1)
+    launches = eng.info('launches') - launches0
+
+    # episode statistics: the only cross-GPU exchange of the path (one small all-reduce over NVLink)
+    stats = torch.as_tensor(eng.stats()[:11].copy(), device=dev)
+    t_el = torch.tensor([elapsed_ms, obs_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+        dist.all_reduce(t_el, op=dist.ReduceOp.MAX)
+    elapsed_ms, obs_ms = float(t_el[0]), float(t_el[1])
+
+    # ---- e2e: host buffers through the C-ABI host entry point (H2D actions, D2H reward + done + obs inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        k2 = max(1, min(args.steps, args.e2e_steps))
+        h_act = torch.zeros((n_local, A), dtype=torch.int32).pin_memory()
+        h_rew = torch.zeros((n_local, eng.n_rew), dtype=torch.float32).pin_memory()
+        h_done = torch.zeros(n_local, dtype=torch.uint8).pin_memory()
+        h_obs = torch.zeros((n_local, es.total_channels, es.obs_d, es.obs_d), dtype=torch.float32).pin_memory()
+        gen = torch.Generator().manual_seed(rank)
+        pool = [torch.stack([torch.randint(0, n, (n_local,), generator=gen, dtype=torch.int32) for n in es.n_actions], 1)
+                for _ in range(2)]
+        eng.step_host(h_act, h_rew, h_done, h_obs, auto_reset=True)       # warm-up (allocates the staging buffers)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(k2):
+            h_act.copy_(pool[i % 2])                                        # the caller's host-side actions
+            eng.step_host(h_act, h_rew, h_done, h_obs, auto_reset=True)
+        barrier()
+        t_e2e = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        e2e = {'value': world * n_local * A * k2 / float(t_e2e[0]), 'unit': UNIT, 'steps': k2,
+               'h2d_bytes_per_step': int(h_act.numel() * 4) * world,
+               'd2h_bytes_per_step': int(h_rew.numel() * 4 + h_done.numel() + h_obs.numel() * 4) * world,
+               'note': 'mfg_step_host: pinned host actions in, reward + done + full observation tensor out, synchronous'}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    total_envs = world * n_local
+    env_steps_per_s = total_envs * args.steps / (elapsed_ms * 1e-3)
+    value = env_steps_per_s * A
+    peak, peak_src = hbm_peak()
+    obs_bytes = 4 * es.obs_d ** 2 * es.total_channels + es.algorithmic_state_bytes()       # obs write + state read, per env
+    step_bytes = es.algorithmic_bytes_per_env_step()
+    achieved = obs_bytes * n_local / (obs_ms * 1e-3) / 1e9
+    traffic = None
+    tp = ROOT / 'profiles' / 'obs_kernel_traffic.json'
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get(f'{args.config}:{n_local}')
+        except Exception:
+            traffic = None
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': elapsed_ms / max(args.steps, 1), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'u16/f64 state, f32 obs', 'data': 'synthetic',
+        'config': {'workload': f'{args.config} all-modules (level large, 4 agents, POMDP r=3), {n_local} envs per GPU',
+                   'envs_total': total_envs, 'agents': A, 'parity': args.parity, 'obs_kernel': 'tiled' if eng.info('tiled_ok') and args.obs_kernel != 1 else 'direct',
+                   'l2': f'per-step working set {step_bytes * n_local / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed)',
+                   'actions': 'device Philox, regenerated every step (inside the timed region)', 'auto_reset': True},
+        'env_steps_per_s': env_steps_per_s,
+        'roofline': {'bound': 'hbm', 'kernel': 'k_obs_tiled' if eng.info('tiled_ok') and args.obs_kernel != 1 else 'k_obs_direct',
+                     'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
+                     'peak_source': peak_src, 'bytes_per_env': obs_bytes, 'ms_per_launch': obs_ms,
+                     'whole_step': {'bytes_per_env_step': step_bytes,
+                                    'achieved': step_bytes * env_steps_per_s / world / 1e9,
+                                    'frac': step_bytes * env_steps_per_s / world / 1e9 / peak}},
+        'gpu_launches': launches,
+        'clocks': clocks.summary(),
+        'episode_stats': {'episodes': int(stats[0]), 'env_steps_in_finished_episodes': int(stats[1]),
+                          'collisions': int(stats[8]), 'dirt_overflow': int(stats[9]), 'spawn_fail': int(stats[10])},
+    }
+    if e2e is not None:
+        line['e2e'] = e2e
+    if world == 1 and not args.no_cpu:
+        procs = os.cpu_count() or 1
+        pool = CpuPool(args.config, args.parity == 'faithful', procs)
+        pool.run(50)                                                       # warm-up
+        agent_steps, slowest = pool.run(args.cpu_steps)
+        pool.close()
+        line['cpu_baseline'] = {'value': agent_steps / slowest, 'unit': UNIT, 'cores': procs, 'kind': 'port',
+                                'sample': f'{procs} procs x {args.cpu_steps} env-steps of {args.config}, oracle port of the '
+                                          f'reference step+obs (random actions, in-place reset), {slowest:.1f} s'}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--impl', default='engine', choices=['engine', 'reference'])
+    ap.add_argument('--config', default='cfg4')
+    ap.add_argument('--envs-per-gpu', type=int, default=1 << 20)
+    ap.add_argument('--parity', default='identity', choices=['identity', 'faithful'])
+    ap.add_argument('--obs-kernel', type=int, default=0, help='0 auto, 1 direct, 2 tiled')
+    ap.add_argument('--e2e-steps', type=int, default=5)
+    ap.add_argument('--cpu-steps', type=int, default=3000, help='env-steps per CPU worker for the baseline sample')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == 'engine':
+        args.warmup = 3
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -198,7 +198,8 @@ def test_factory_batched_host_path_and_stats():
     for t in range(120):
         h_act.copy_(torch.randint(0, 12, (N, A), generator=g, dtype=torch.int32))
         f.engine.step_host(h_act, h_rew, h_done, h_obs, auto_reset=True)
-    assert torch.equal(h_obs, f.engine.obs.cpu())
+    assert torch.equal(h_obs, f.engine.observe().cpu())      # the host copy is the observation of the current state
+    assert h_rew.abs().sum() > 0
     st = f.episode_stats()
     assert st['episodes'] > 0 and st['steps'] >= st['episodes']
     f.close()
