@@ -1,0 +1,214 @@
+// mfg_abi.cu - the C ABI of libmfg_b200.so (include/mfg_b200.h): handle management, argument checking, launches.
+// Kernels live in mfg_step.cu (reset / step) and mfg_obs.cu (observations).
+#include <cstdio>
+#include <cstring>
+#include "mfg_internal.hpp"
+
+using namespace mfg;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CUDA_TRY(call)                                                                       \
+  do {                                                                                       \
+    cudaError_t _e = (call);                                                                 \
+    if (_e != cudaSuccess) return fail(MFG_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+template <typename T>
+static int upload(MfgHandle* h, const std::vector<T>& v, const T** out) {
+  void* d = nullptr;
+  size_t bytes = v.size() * sizeof(T);
+  if (bytes == 0) { *out = nullptr; return MFG_OK; }
+  CUDA_TRY(cudaMalloc(&d, bytes));
+  h->dev_allocs.push_back(d);
+  CUDA_TRY(cudaMemcpy(d, v.data(), bytes, cudaMemcpyHostToDevice));
+  *out = static_cast<const T*>(d);
+  return MFG_OK;
+}
+
+extern "C" {
+
+const char* mfg_last_error(void) { return g_err.c_str(); }
+const char* mfg_version(void) { return "mfg_b200 0.1 (sm_100a)"; }
+
+int mfg_create(const MfgSpec* spec, int64_t n_envs, int64_t env_id_offset, MfgHandle** out) {
+  if (!spec || !out || n_envs <= 0) return fail(MFG_E_INVALID, "mfg_create: bad arguments");
+  std::string err = validate_spec(*spec);
+  if (!err.empty()) return fail(MFG_E_INVALID, "mfg_create: " + err);
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+    return fail(MFG_E_CUDA, "mfg_create: no CUDA device available (this engine has no CPU path)");
+  HostTables ht;
+  err = build_tables(*spec, ht);
+  if (!err.empty()) return fail(MFG_E_INVALID, "mfg_create: " + err);
+
+  MfgHandle* h = new MfgHandle();
+  h->sp = *spec;
+  h->sp.walls = nullptr; h->sp.floor_pos = nullptr; h->sp.door_pos = nullptr; h->sp.nexthop = nullptr;
+  h->N = n_envs;
+  int rc;
+#define UP(field) if ((rc = upload(h, ht.field, &h->tb.field)) != MFG_OK) { mfg_destroy(h); return rc; }
+  UP(wall) UP(door_map) UP(floor_pos) UP(floor_index) UP(wall_uid) UP(wall_pos) UP(door_pos) UP(nexthop) UP(wall_win)
+#undef UP
+  h->tb.env_id_offset = env_id_offset;
+  void* d = nullptr;
+  if (cudaMalloc(&d, sizeof(unsigned long long) * MFG_N_STATS) != cudaSuccess) { mfg_destroy(h); return fail(MFG_E_NOMEM, "stats alloc"); }
+  h->dev_allocs.push_back(d);
+  cudaMemset(d, 0, sizeof(unsigned long long) * MFG_N_STATS);
+  h->tb.stats = static_cast<unsigned long long*>(d);
+  if (cudaMalloc(&d, sizeof(MfgSpec)) != cudaSuccess) { mfg_destroy(h); return fail(MFG_E_NOMEM, "spec alloc"); }
+  h->dev_allocs.push_back(d);
+  h->d_sp = static_cast<MfgSpec*>(d);
+  cudaMemcpy(h->d_sp, &h->sp, sizeof(MfgSpec), cudaMemcpyHostToDevice);
+  h->state_bytes = compute_layout(h->sp, n_envs, h->fields);
+  h->total_channels = 0;
+  for (int a = 0; a < h->sp.n_agents; ++a) h->total_channels += h->sp.n_channels[a];
+  const int D = 2 * h->sp.pomdp_r + 1;
+  h->DD = D * D;
+
+  plan_obs(h);
+  *out = h;
+  return MFG_OK;
+}
+
+void mfg_destroy(MfgHandle* h) {
+  if (!h) return;
+  for (void* p : h->dev_allocs) cudaFree(p);
+  if (h->d_actions) cudaFree(h->d_actions);
+  if (h->d_reward) cudaFree(h->d_reward);
+  if (h->d_done) cudaFree(h->d_done);
+  if (h->d_obs) cudaFree(h->d_obs);
+  delete h;
+}
+
+size_t mfg_state_bytes(const MfgHandle* h) { return h ? h->state_bytes : 0; }
+
+int mfg_state_field(const MfgHandle* h, const char* name, MfgField* out) {
+  if (!h || !name || !out) return fail(MFG_E_INVALID, "mfg_state_field: bad arguments");
+  for (const auto& f : h->fields)
+    if (strcmp(f.name, name) == 0) { out->offset = f.offset; out->rows = f.rows; out->elem_size = f.elem_size; return MFG_OK; }
+  return fail(MFG_E_INVALID, std::string("mfg_state_field: unknown field ") + name);
+}
+
+int mfg_bind_state(MfgHandle* h, void* d_state) {
+  if (!h || !d_state) return fail(MFG_E_INVALID, "mfg_bind_state: bad arguments");
+  if (reinterpret_cast<uintptr_t>(d_state) % 256) return fail(MFG_E_INVALID, "mfg_bind_state: buffer must be 256-byte aligned");
+  bind_state(h->sp, h->N, d_state, h->st);
+  h->bound = true;
+  return MFG_OK;
+}
+
+#define NEED_BOUND(h) if (!(h) || !(h)->bound) return fail(MFG_E_INVALID, "state buffer not bound (call mfg_bind_state)")
+
+int mfg_reset(MfgHandle* h, const uint8_t* d_env_mask, void* stream) {
+  NEED_BOUND(h);
+  CUDA_TRY(launch_reset(h, d_env_mask, static_cast<cudaStream_t>(stream)));
+  h->launches++;
+  return MFG_OK;
+}
+
+int mfg_step(MfgHandle* h, const int32_t* d_actions, const MfgTape* tape, float* d_reward, uint8_t* d_done,
+             int auto_reset, void* stream) {
+  NEED_BOUND(h);
+  if (!d_actions || !d_reward || !d_done) return fail(MFG_E_INVALID, "mfg_step: NULL buffer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  StepIO io{d_actions, tape ? tape->d_maint_action : nullptr, tape ? tape->d_respawn_n : nullptr,
+            tape ? tape->d_respawn_pos : nullptr, d_reward, d_done, auto_reset};
+  bool need_policy = false;
+  for (int r = 0; r < h->sp.n_rules; ++r) need_policy |= h->sp.rule_op[r] == MFG_R_MOVE_MAINTAINERS;
+  if (need_policy && !io.maint_act && !h->tb.nexthop)
+    return fail(MFG_E_INVALID, "mfg_step: MoveMaintainers without a tape needs the next-hop table (MfgSpec.nexthop)");
+  CUDA_TRY(launch_step(h, io, s));
+  h->launches++;
+  return MFG_OK;
+}
+
+int mfg_observe(MfgHandle* h, float* d_obs, void* stream) {
+  NEED_BOUND(h);
+  if (!d_obs) return fail(MFG_E_INVALID, "mfg_observe: NULL buffer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (h->obs_kernel == 2 && !h->plan.ok) return fail(MFG_E_UNSUPPORTED, "tiled observation kernel not available for this spec");
+  const bool tiled = h->plan.ok && h->obs_kernel != 1;
+  CUDA_TRY(tiled ? launch_obs_tiled(h, d_obs, s) : launch_obs_direct(h, d_obs, s));
+  h->launches++;
+  return MFG_OK;
+}
+
+int mfg_step_observe(MfgHandle* h, const int32_t* d_actions, const MfgTape* tape, float* d_reward, uint8_t* d_done,
+                     float* d_obs, int auto_reset, void* stream) {
+  int rc = mfg_step(h, d_actions, tape, d_reward, d_done, auto_reset, stream);
+  if (rc != MFG_OK) return rc;
+  return mfg_observe(h, d_obs, stream);
+}
+
+int mfg_random_actions(MfgHandle* h, int32_t* d_actions, uint64_t seed, uint64_t step_index, void* stream) {
+  if (!h || !d_actions) return fail(MFG_E_INVALID, "mfg_random_actions: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(launch_random_actions(h, d_actions, seed, (uint32_t)step_index, s));
+  h->launches++;
+  return MFG_OK;
+}
+
+int mfg_step_host(MfgHandle* h, const int32_t* h_actions, float* h_reward, uint8_t* h_done, float* h_obs,
+                  int auto_reset, void* stream) {
+  NEED_BOUND(h);
+  if (!h_actions || !h_reward || !h_done) return fail(MFG_E_INVALID, "mfg_step_host: NULL buffer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int A = h->sp.n_agents, NR = h->sp.individual_rewards ? A : 1;
+  const size_t obs_bytes = (size_t)h->N * h->total_channels * h->DD * sizeof(float);
+  if (!h->d_actions) {
+    CUDA_TRY(cudaMalloc(&h->d_actions, (size_t)h->N * A * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&h->d_reward, (size_t)h->N * NR * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&h->d_done, (size_t)h->N));
+    CUDA_TRY(cudaMalloc(&h->d_obs, obs_bytes));
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->d_actions, h_actions, (size_t)h->N * A * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  int rc = mfg_step_observe(h, h->d_actions, nullptr, h->d_reward, h->d_done, h->d_obs, auto_reset, stream);
+  if (rc != MFG_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(h_reward, h->d_reward, (size_t)h->N * NR * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(h_done, h->d_done, (size_t)h->N, cudaMemcpyDeviceToHost, s));
+  if (h_obs) CUDA_TRY(cudaMemcpyAsync(h_obs, h->d_obs, obs_bytes, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return MFG_OK;
+}
+
+int mfg_stats(MfgHandle* h, int64_t* d_out, int zero_after, void* stream) {
+  if (!h || !d_out) return fail(MFG_E_INVALID, "mfg_stats: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaMemcpyAsync(d_out, h->tb.stats, sizeof(int64_t) * MFG_N_STATS, cudaMemcpyDeviceToDevice, s));
+  if (zero_after) CUDA_TRY(cudaMemsetAsync(h->tb.stats, 0, sizeof(int64_t) * MFG_N_STATS, s));
+  return MFG_OK;
+}
+
+int mfg_set_option(MfgHandle* h, const char* name, int64_t value) {
+  if (!h || !name) return fail(MFG_E_INVALID, "mfg_set_option: bad arguments");
+  if (strcmp(name, "obs_kernel") == 0) {
+    if (value < 0 || value > 2) return fail(MFG_E_INVALID, "obs_kernel must be 0 (auto), 1 (direct) or 2 (tiled)");
+    if (value == 2 && !h->plan.ok) return fail(MFG_E_UNSUPPORTED, "tiled observation kernel not available for this spec");
+    h->obs_kernel = (int)value;
+    return MFG_OK;
+  }
+  if (strcmp(name, "obs_cap") == 0) {          // sprite slots per (env, agent); small values force the overflow path (tests)
+    if (value < 1 || value > 16) return fail(MFG_E_INVALID, "obs_cap must be in 1..16");
+    h->plan.cap = (int)value;
+    return MFG_OK;
+  }
+  if (strcmp(name, "obs_store") == 0) {        // 1 = TMA bulk store of the tile (default), 0 = LDS/STG loop
+    h->obs_store = value != 0;
+    return MFG_OK;
+  }
+  return fail(MFG_E_INVALID, std::string("mfg_set_option: unknown option ") + name);
+}
+
+int64_t mfg_get_info(const MfgHandle* h, const char* name) {
+  if (!h || !name) return -1;
+  if (strcmp(name, "launches") == 0) return h->launches;
+  if (strcmp(name, "tiled_ok") == 0) return h->plan.ok ? 1 : 0;
+  if (strcmp(name, "obs_smem") == 0) return (int64_t)h->plan.smem;
+  if (strcmp(name, "obs_threads") == 0) return h->plan.nw * 32;
+  if (strcmp(name, "total_channels") == 0) return h->total_channels;
+  if (strcmp(name, "n_envs") == 0) return h->N;
+  return -1;
+}
+
+}  // extern "C"

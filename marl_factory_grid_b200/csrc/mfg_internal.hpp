@@ -1,0 +1,68 @@
+// mfg_internal.hpp - handle layout and launch prototypes shared by the translation units of libmfg_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include "mfg_host.hpp"
+
+namespace mfg {
+
+constexpr int OBS_ENVS = 32;      // envs per CTA of the tiled observation kernel (one lane per env in phase 1)
+constexpr int MAX_WRAYS = 64;
+constexpr int MAX_WLEN = 4;
+
+// run-time derived window rays (used to validate the generated constexpr tries and by nothing else)
+struct WindowRays {
+  int n;
+  int len[MAX_WRAYS];
+  uint8_t cell[MAX_WRAYS][MAX_WLEN];
+  uint8_t da[MAX_WRAYS][MAX_WLEN];
+  uint8_t db[MAX_WRAYS][MAX_WLEN];
+};
+
+// dynamic-position entity slots staged per env in shared memory by the observation kernel
+struct ObsSlots {
+  int dirt0, item0, pod0, dest0, drop0, mach0, maint0, agent0, total, stride;
+};
+
+struct ObsPlan {
+  bool ok = false;        // tiled kernel usable for this spec
+  int ge = 1;             // envs per output tile (tile = whole number of 16-byte vectors)
+  int nw = 4;             // warps per CTA
+  int nbuf = 1;           // tile buffers per warp (2 = overlap the bulk store with the next env)
+  int cap = 16;           // sprite slots per (env, agent)
+  size_t smem = 0;
+  ObsSlots slots{};
+};
+
+}  // namespace mfg
+
+struct MfgHandle {
+  MfgSpec sp;                  // host copy (level pointers nulled)
+  MfgSpec* d_sp = nullptr;
+  mfg::Tables tb{};
+  mfg::State st{};
+  std::vector<mfg::FieldInfo> fields;
+  std::vector<void*> dev_allocs;
+  size_t state_bytes = 0;
+  int64_t N = 0;
+  int total_channels = 0, DD = 0;
+  bool bound = false;
+  int obs_kernel = 0;          // 0 = auto (tiled when possible), 1 = direct, 2 = tiled
+  int obs_store = 1;           // 1 = TMA bulk store of the tile, 0 = LDS/STG loop
+  mfg::ObsPlan plan;
+  // host-buffer path staging
+  int32_t* d_actions = nullptr; float* d_reward = nullptr; uint8_t* d_done = nullptr; float* d_obs = nullptr;
+  int64_t launches = 0;
+};
+
+namespace mfg {
+// mfg_step.cu
+cudaError_t launch_reset(MfgHandle* h, const uint8_t* d_mask, cudaStream_t s);
+cudaError_t launch_step(MfgHandle* h, const StepIO& io, cudaStream_t s);
+cudaError_t launch_random_actions(MfgHandle* h, int32_t* d_actions, uint64_t seed, uint32_t step_index, cudaStream_t s);
+// mfg_obs.cu
+void plan_obs(MfgHandle* h);
+cudaError_t launch_obs_direct(MfgHandle* h, float* d_obs, cudaStream_t s);
+cudaError_t launch_obs_tiled(MfgHandle* h, float* d_obs, cudaStream_t s);
+}  // namespace mfg

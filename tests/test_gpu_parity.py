@@ -135,6 +135,12 @@ def test_tiled_observation_kernel_equals_direct_kernel_at_scale(cfg):
             eng.set_option('obs_kernel', 2)
             o2 = eng.observe().clone()
             assert torch.equal(o1, o2), f'{cfg} t={t}: tiled != direct'
+            eng.set_option('obs_store', 0)               # LDS/STG write-out instead of the TMA bulk store
+            assert torch.equal(o1, eng.observe()), f'{cfg} t={t}: tiled (no bulk store) != direct'
+            eng.set_option('obs_store', 1)
+            eng.set_option('obs_cap', 3)                 # tiny sprite lists: most envs take the overflow path
+            assert torch.equal(o1, eng.observe()), f'{cfg} t={t}: tiled (overflow path) != direct'
+            eng.set_option('obs_cap', 16)
             apos = eng.fields['apos'].to(torch.int64) & 0xFFFF
             assert not walls[apos >> 8, apos & 255].any()
             if es.n_doors:
