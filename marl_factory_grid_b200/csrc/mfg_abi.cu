@@ -189,7 +189,7 @@ int mfg_set_option(MfgHandle* h, const char* name, int64_t value) {
     return MFG_OK;
   }
   if (strcmp(name, "obs_cap") == 0) {          // sprite slots per (env, agent); small values force the overflow path (tests)
-    if (value < 1 || value > 16) return fail(MFG_E_INVALID, "obs_cap must be in 1..16");
+    if (value < 1 || value > h->plan.cap_max) return fail(MFG_E_INVALID, "obs_cap must be in 1..cap_max");
     h->plan.cap = (int)value;
     return MFG_OK;
   }
@@ -208,6 +208,7 @@ int64_t mfg_get_info(const MfgHandle* h, const char* name) {
   if (strcmp(name, "obs_threads") == 0) return h->plan.nw * 32;
   if (strcmp(name, "total_channels") == 0) return h->total_channels;
   if (strcmp(name, "n_envs") == 0) return h->N;
+  if (strcmp(name, "obs_cap_max") == 0) return h->plan.cap_max;
   return -1;
 }
 

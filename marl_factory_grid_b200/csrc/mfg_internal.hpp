@@ -25,12 +25,21 @@ struct ObsSlots {
   int dirt0, item0, pod0, dest0, drop0, mach0, maint0, agent0, total, stride;
 };
 
+constexpr int MAX_WALL_PLANES = 48;
+struct WallPlanes {               // channels that contain Walls, as (agent, plane index in the packed tensor)
+  int n;
+  uint16_t plane[MAX_WALL_PLANES];
+  uint8_t agent[MAX_WALL_PLANES];
+};
+
 struct ObsPlan {
   bool ok = false;        // tiled kernel usable for this spec
   int ge = 1;             // envs per output tile (tile = whole number of 16-byte vectors)
   int nw = 4;             // warps per CTA
   int nbuf = 1;           // tile buffers per warp (2 = overlap the bulk store with the next env)
-  int cap = 16;           // sprite slots per (env, agent)
+  int cap = 48;           // sprite slots per env (all agents share one list)
+  int cap_max = 48;
+  WallPlanes walls{};
   size_t smem = 0;
   ObsSlots slots{};
 };

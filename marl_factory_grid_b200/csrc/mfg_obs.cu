@@ -162,8 +162,8 @@ __device__ void slow_fill_env(const MfgSpec* __restrict__ sp, const Tables& tb, 
 }
 
 template <int R, int GE, int NBUF, bool BULK>
-__global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st, ObsSlots sl, float* __restrict__ obs,
-                            int total_channels, int cap) {
+__global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st, ObsSlots sl, WallPlanes wp,
+                            float* __restrict__ obs, int total_channels, int cap) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int D = 2 * R + 1, DD = D * D;
   const int A = sp->n_agents;
@@ -177,11 +177,10 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
   unsigned long long* s_vis = reinterpret_cast<unsigned long long*>(tiles + (size_t)NW * NBUF * tile_floats);  // [32][A]
   unsigned long long* s_wv = s_vis + OBS_ENVS * A;                                          // [32][A]
   unsigned long long* s_dopen = s_wv + OBS_ENVS * A;                                        // [32]
-  Sprite* s_spr = reinterpret_cast<Sprite*>(s_dopen + OBS_ENVS);                            // [32][A][cap]
-  uint32_t* s_reached = reinterpret_cast<uint32_t*>(s_spr + (size_t)OBS_ENVS * A * cap);    // [32]
-  uint32_t* s_ovf = s_reached + OBS_ENVS;                                                   // [32]
-  uint8_t* s_cnt = reinterpret_cast<uint8_t*>(s_ovf + OBS_ENVS);                            // [32][A]
-  uint16_t* s_pos = reinterpret_cast<uint16_t*>(s_cnt + ((OBS_ENVS * A + 15) & ~15));       // [32][stride]
+  Sprite* s_spr = reinterpret_cast<Sprite*>(s_dopen + OBS_ENVS);                            // [32][cap]  one list per env
+  uint32_t* s_reached = reinterpret_cast<uint32_t*>(s_spr + (size_t)OBS_ENVS * cap);        // [32]
+  int* s_cnt = reinterpret_cast<int*>(s_reached + OBS_ENVS);                                // [32] sprites emitted per env
+  uint16_t* s_pos = reinterpret_cast<uint16_t*>(s_cnt + OBS_ENVS);                          // [32][stride]
 
   // ---------------- phase 1 ------------------------------------------------------------------------------------
   {
@@ -192,7 +191,7 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
     if (warp == 0) {
       s_dopen[lane] = (live && sp->n_doors) ? st.door_open[e] : 0ull;
       s_reached[lane] = (live && sp->n_dest) ? st.dest_reached[e] : 0u;
-      s_ovf[lane] = 0u;
+      s_cnt[lane] = 0;
     }
     __syncthreads();
     const uint16_t* pos = s_pos + lane * sl.stride;
@@ -200,7 +199,6 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
     const uint32_t reached = s_reached[lane];
     for (int a = warp; a < A; a += NW) {
       unsigned long long vis = 0ull, wv = 0ull;
-      int n = 0;
       if (live) {
         const uint16_t p = pos[sl.agent0 + a];
         const int ax = px(p), ay = py(p);
@@ -216,13 +214,17 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
 
         const uint32_t* chm = sp->term_chmask[a];
         const int coff = sp->ch_offset[a];
-        Sprite* spr = s_spr + ((size_t)lane * A + a) * cap;
+        Sprite* spr = s_spr + (size_t)lane * cap;
+        int* cnt = s_cnt + lane;
+        auto put = [&](uint32_t w, float val) {      // the A agent-threads of an env append to one list
+          const int slot = atomicAdd(cnt, 1);
+          if (slot < cap) spr[slot] = Sprite{w, val};
+        };
         auto emit = [&](uint32_t m, int cell, uint32_t kind, uint32_t aux, float val) {
           while (m) {
             const int c = __ffs(m) - 1;
             m &= m - 1;
-            if (n < cap) spr[n] = Sprite{(uint32_t)((coff + c) * DD + cell) | (kind << 16) | (aux << 24), val};
-            ++n;
+            put((uint32_t)((coff + c) * DD + cell) | (kind << 16) | (aux << 24), val);
           }
         };
         auto cell_of = [&](uint16_t q) -> int {        // window cell if inside the window and visible, else -1
@@ -277,20 +279,15 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
         for (int c = 0; c < C; ++c) {
           const int kind = sp->ch_kind[a][c];
           if (kind == MFG_CH_BATTERY) {
-            if (n < cap) spr[n] = Sprite{(uint32_t)((coff + c) * DD) | (SK_STORE << 16), (float)st.bat[(size_t)a * st.N + e]};
-            ++n;
+            put((uint32_t)((coff + c) * DD) | (SK_STORE << 16), (float)st.bat[(size_t)a * st.N + e]);
           } else if (kind == MFG_CH_GLOBALPOS) {
-            if (n < cap) spr[n] = Sprite{(uint32_t)((coff + c) * DD) | (SK_STORE << 16), (float)((double)ax / (double)sp->H)};
-            ++n;
-            if (n < cap) spr[n] = Sprite{(uint32_t)((coff + c) * DD + 1) | (SK_STORE << 16), (float)((double)ay / (double)sp->W)};
-            ++n;
+            put((uint32_t)((coff + c) * DD) | (SK_STORE << 16), (float)((double)ax / (double)sp->H));
+            put((uint32_t)((coff + c) * DD + 1) | (SK_STORE << 16), (float)((double)ay / (double)sp->W));
           }
         }
-        if (n > cap) s_ovf[lane] = 1u;
       }
       s_vis[lane * A + a] = vis;
       s_wv[lane * A + a] = wv;
-      s_cnt[lane * A + a] = (uint8_t)(n > cap ? 0 : n);
     }
   }
   __syncthreads();
@@ -322,33 +319,26 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
       const int64_t e = env0 + el;
       if (e >= st.N) break;
       float* te = tile + (size_t)ge * total_channels * DD;
-      if (s_ovf[el]) {
+      const int cnt = s_cnt[el];
+      if (cnt > cap) {                      // sprite list overflowed: generic lanes-over-slots fill of the whole env
         slow_fill_env(sp, tb, st, sl, s_pos + el * sl.stride, s_vis + el * A, s_dopen[el], s_reached[el], te, e, lane);
         continue;
       }
-      for (int a = 0; a < A; ++a) {
-        // walls: 49-bit mask -> 1.0 in every channel of this agent that contains Walls (unique writer per cell)
-        const uint32_t mw = sp->term_chmask[a][MFG_G_WALLS];
-        if (mw) {
-          const unsigned long long wv = s_wv[el * A + a];
-          const int coff = sp->ch_offset[a];
-          for (int cell = lane; cell < DD; cell += 32) {
-            if ((wv >> cell) & 1) {
-              uint32_t m = mw;
-              while (m) { const int c = __ffs(m) - 1; m &= m - 1; te[(coff + c) * DD + cell] = 1.0f; }
-            }
-          }
-        }
-        // integer-valued sprites (stacks add up exactly) and direct stores
-        const int cnt = s_cnt[el * A + a];
-        if (lane < cnt) {
-          const Sprite s = s_spr[((size_t)el * A + a) * cap + lane];
-          const uint32_t kind = (s.w >> 16) & 0xFF;
-          if (kind == SK_INT) atomicAdd(&te[s.w & 0xFFFF], s.val);
-          else if (kind == SK_STORE) te[s.w & 0xFFFF] = s.val;
-          else if (kind == SK_DOOR) any_door = true;
-          else any_dirt = true;
-        }
+      // wall planes: 1.0 where a visible wall is.  Nothing else can be on a wall cell, so the (predicated) store has a
+      // unique writer and needs no ordering against the sprite adds below.
+      for (int w = 0; w < wp.n; ++w) {
+        const unsigned long long wv = s_wv[el * A + wp.agent[w]];
+        float* plane = te + (int)wp.plane[w] * DD;
+        for (int cell = lane; cell < DD; cell += 32) if ((wv >> cell) & 1) plane[cell] = 1.0f;
+      }
+      // integer-valued sprites (stacks add up exactly) and direct stores
+      for (int i = lane; i < cnt; i += 32) {
+        const Sprite s = s_spr[(size_t)el * cap + i];
+        const uint32_t kind = (s.w >> 16) & 0xFF;
+        if (kind == SK_INT) atomicAdd(&te[s.w & 0xFFFF], s.val);
+        else if (kind == SK_STORE) te[s.w & 0xFFFF] = s.val;
+        else if (kind == SK_DOOR) any_door = true;
+        else any_dirt = true;
       }
     }
     any_door = __any_sync(0xffffffffu, any_door);
@@ -359,14 +349,14 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
       for (int ge = 0; ge < GE; ++ge) {
         const int el = g * GE + ge;
         if (env0 + el >= st.N) break;
+        const int cnt = s_cnt[el];
+        if (cnt > cap) continue;                     // filled completely by the overflow path
         float* te = tile + (size_t)ge * total_channels * DD;
-        for (int a = 0; a < A; ++a) {
-          if (lane < s_cnt[el * A + a]) {
-            const Sprite s = s_spr[((size_t)el * A + a) * cap + lane];
-            if (((s.w >> 16) & 0xFF) == SK_DOOR) {
-              float* f = &te[s.w & 0xFFFF];
-              *f = (float)((double)*f + ((s.w >> 24) ? ENC_DOOR_OPEN : ENC_DOOR_CLOSED));
-            }
+        for (int i = lane; i < cnt; i += 32) {
+          const Sprite s = s_spr[(size_t)el * cap + i];
+          if (((s.w >> 16) & 0xFF) == SK_DOOR) {
+            float* f = &te[s.w & 0xFFFF];
+            *f = (float)((double)*f + ((s.w >> 24) ? ENC_DOOR_OPEN : ENC_DOOR_CLOSED));
           }
         }
       }
@@ -377,14 +367,14 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
         const int el = g * GE + ge;
         const int64_t e = env0 + el;
         if (e >= st.N) break;
+        const int cnt = s_cnt[el];
+        if (cnt > cap) continue;
         float* te = tile + (size_t)ge * total_channels * DD;
-        for (int a = 0; a < A; ++a) {
-          if (lane < s_cnt[el * A + a]) {
-            const Sprite s = s_spr[((size_t)el * A + a) * cap + lane];
-            if (((s.w >> 16) & 0xFF) == SK_DIRT) {
-              float* f = &te[s.w & 0xFFFF];
-              *f = (float)((double)*f + st.dirt_amt[(size_t)(s.w >> 24) * st.N + e]);
-            }
+        for (int i = lane; i < cnt; i += 32) {
+          const Sprite s = s_spr[(size_t)el * cap + i];
+          if (((s.w >> 16) & 0xFF) == SK_DIRT) {
+            float* f = &te[s.w & 0xFFFF];
+            *f = (float)((double)*f + st.dirt_amt[(size_t)(s.w >> 24) * st.N + e]);
           }
         }
       }
@@ -501,12 +491,13 @@ void plan_obs(MfgHandle* h) {
   const int tcdd = h->total_channels * h->DD;
   p.ge = (tcdd % 4 == 0) ? 1 : (tcdd % 2 == 0) ? 2 : 4;
   p.nw = sp.n_agents < 2 ? 2 : (sp.n_agents > 8 ? 8 : sp.n_agents);
-  p.cap = 16;
+  p.cap = 12 * sp.n_agents < 16 ? 16 : 12 * sp.n_agents;      // sprite slots per env
+  p.cap_max = p.cap;
   auto smem_for = [&](int nbuf) {
     size_t b = (size_t)p.nw * nbuf * p.ge * tcdd * sizeof(float);
     b += (size_t)OBS_ENVS * sp.n_agents * 8 * 2 + OBS_ENVS * 8;            // vis, wv, dopen
-    b += (size_t)OBS_ENVS * sp.n_agents * p.cap * 8;                       // sprites
-    b += OBS_ENVS * 4 * 2 + ((OBS_ENVS * sp.n_agents + 15) & ~15);         // reached, ovf, cnt
+    b += (size_t)OBS_ENVS * p.cap * 8;                                     // sprites (one list per env)
+    b += OBS_ENVS * 4 * 2;                                                 // reached, cnt
     b += (size_t)OBS_ENVS * sl.stride * 2 + 32;
     return b;
   };
@@ -516,7 +507,18 @@ void plan_obs(MfgHandle* h) {
   build_window_rays(sp, wr);
   bool trie_ok = sp.pomdp_r == 1 ? trie_matches<1>(wr) : sp.pomdp_r == 2 ? trie_matches<2>(wr)
                : sp.pomdp_r == 3 ? trie_matches<3>(wr) : false;
-  p.ok = !sp.faithful && trie_ok && p.smem <= 200 * 1024 && tcdd * p.ge <= 0xFFFF;
+  // wall planes: (agent, packed channel) of every channel that contains Walls
+  p.walls.n = 0;
+  bool walls_fit = true;
+  for (int a = 0; a < sp.n_agents; ++a)
+    for (int c = 0; c < sp.n_channels[a]; ++c)
+      if ((sp.term_chmask[a][MFG_G_WALLS] >> c) & 1) {
+        if (p.walls.n >= MAX_WALL_PLANES) { walls_fit = false; continue; }
+        p.walls.agent[p.walls.n] = (uint8_t)a;
+        p.walls.plane[p.walls.n] = (uint16_t)(sp.ch_offset[a] + c);
+        p.walls.n++;
+      }
+  p.ok = !sp.faithful && trie_ok && walls_fit && p.smem <= 200 * 1024 && tcdd * p.ge <= 0xFFFF;
 }
 
 template <int R, int GE, int NBUF, bool BULK>
@@ -528,7 +530,7 @@ static cudaError_t launch_tiled_t(MfgHandle* h, float* d_obs, cudaStream_t s) {
     if (e != cudaSuccess) return e;
   }
   const unsigned blocks = (unsigned)((h->N + OBS_ENVS - 1) / OBS_ENVS);
-  kern<<<blocks, p.nw * 32, p.smem, s>>>(h->d_sp, h->tb, h->st, p.slots, d_obs, h->total_channels, p.cap);
+  kern<<<blocks, p.nw * 32, p.smem, s>>>(h->d_sp, h->tb, h->st, p.slots, p.walls, d_obs, h->total_channels, p.cap);
   return cudaGetLastError();
 }
 

@@ -140,7 +140,7 @@ def test_tiled_observation_kernel_equals_direct_kernel_at_scale(cfg):
             eng.set_option('obs_store', 1)
             eng.set_option('obs_cap', 3)                 # tiny sprite lists: most envs take the overflow path
             assert torch.equal(o1, eng.observe()), f'{cfg} t={t}: tiled (overflow path) != direct'
-            eng.set_option('obs_cap', 16)
+            eng.set_option('obs_cap', eng.info('obs_cap_max'))
             apos = eng.fields['apos'].to(torch.int64) & 0xFFFF
             assert not walls[apos >> 8, apos & 255].any()
             if es.n_doors:
