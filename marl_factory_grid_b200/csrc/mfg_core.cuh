@@ -15,6 +15,7 @@
 #include <stdint.h>
 #include <stddef.h>
 #include <math.h>
+#include <type_traits>
 #include "../../include/mfg_b200.h"
 
 #if defined(__CUDACC__)
@@ -156,18 +157,24 @@ struct Env {
   const MfgSpec& sp;
   const Tables& tb;
   const State& st;
-  int64_t e;
+  int64_t e;        // env index inside `st` (== eg unless the integer fields were staged into a per-CTA copy)
+  int64_t eg;       // env index in the caller's global buffers: f64 fields, actions / reward / done, tape
+  int64_t Ng;       // env stride of the f64 fields (they are never staged)
   int A;
   uint16_t apos[AMAX];
   uint64_t dopen, dlisted, dirt_listed;
   int dirt_end, dirt_n;
 
-  MFG_HD Env(const MfgSpec& sp_, const Tables& tb_, const State& st_, int64_t e_) : sp(sp_), tb(tb_), st(st_), e(e_) {
+  MFG_HD Env(const MfgSpec& sp_, const Tables& tb_, const State& st_, int64_t e_, int64_t eg_ = -1, int64_t Ng_ = -1)
+      : sp(sp_), tb(tb_), st(st_), e(e_), eg(eg_ < 0 ? e_ : eg_), Ng(Ng_ < 0 ? st_.N : Ng_) {
     A = sp.n_agents;
     dopen = dlisted = dirt_listed = 0;
     dirt_end = dirt_n = 0;
   }
-  template <typename T> MFG_HD T& at(T* base, int row) const { return base[(size_t)row * (size_t)st.N + (size_t)e]; }
+  template <typename T> MFG_HD T& at(T* base, int row) const {
+    if constexpr (std::is_same<T, double>::value) return base[(size_t)row * (size_t)Ng + (size_t)eg];
+    else return base[(size_t)row * (size_t)st.N + (size_t)e];
+  }
 
   MFG_HD void load() {
 #pragma unroll
@@ -381,11 +388,12 @@ MFG_HD void stat_add_f64(const Tables& tb, int idx, double v) {
 // reset: Factory.reset with a fresh Factory: SpawnAgents, then the groups in Entities order
 // ================================================================================================
 template <int AMAX>
-MFG_HDN void env_reset(const MfgSpec& sp, const Tables& tb, const State& st, int64_t e, uint32_t episode) {
-  Env<AMAX> v(sp, tb, st, e);
+MFG_HDN void env_reset(const MfgSpec& sp, const Tables& tb, const State& st, int64_t e, uint32_t episode,
+                       int64_t eg = -1, int64_t Ng = -1) {
+  Env<AMAX> v(sp, tb, st, e, eg, Ng);
   const int A = v.A;
   Philox rng;
-  rng.init(sp.seed, (uint64_t)(tb.env_id_offset + e), RS_RESET, episode, 0);
+  rng.init(sp.seed, (uint64_t)(tb.env_id_offset + v.eg), RS_RESET, episode, 0);
 
   v.at(st.step, 0) = 0;
   v.at(st.episode, 0) = episode;
@@ -502,7 +510,7 @@ MFG_HD int maint_policy(Env<AMAX>& v, int k, uint32_t step) {
   uint16_t target = v.at(st.maint_target, k);
   if (target == NO_POS || target == p) {
     Philox rng;
-    rng.init(sp.seed, (uint64_t)(tb.env_id_offset + v.e), RS_MAINT0 + k, v.at(st.episode, 0), step);
+    rng.init(sp.seed, (uint64_t)(tb.env_id_offset + v.eg), RS_MAINT0 + k, v.at(st.episode, 0), step);
     for (int attempt = 0; attempt < 2; ++attempt) {
       uint32_t rem = v.at(st.maint_remaining, k);
       if (rem == 0) {
@@ -532,8 +540,10 @@ MFG_HD int maint_policy(Env<AMAX>& v, int k, uint32_t step) {
 }
 
 template <int AMAX>
-MFG_HDN void env_step(const MfgSpec& sp, const Tables& tb, const State& st, int64_t e, const StepIO& io) {
-  Env<AMAX> v(sp, tb, st, e);
+MFG_HDN void env_step(const MfgSpec& sp, const Tables& tb, const State& st, int64_t e_local, const StepIO& io,
+                      int64_t eg = -1, int64_t Ng = -1) {
+  Env<AMAX> v(sp, tb, st, e_local, eg, Ng);
+  const int64_t e = v.eg;            // index into the caller's actions / tape / reward / done buffers
   v.load();
   const int A = v.A;
   const int step = (int)v.at(st.step, 0) + 1;
@@ -841,7 +851,7 @@ MFG_HDN void env_step(const MfgSpec& sp, const Tables& tb, const State& st, int6
     const int nr = sp.individual_rewards ? A : 1;
     for (int i = 0; i < nr; ++i) { double x = v.at(st.ep_ret, i); tot += x; stat_add_f64(tb, MFG_ST_RETURN_AGENT0 + i, x); }
     stat_add_f64(tb, MFG_ST_RETURN_SUM, tot);
-    if (io.auto_reset) env_reset<AMAX>(sp, tb, st, e, v.at(st.episode, 0) + 1);
+    if (io.auto_reset) env_reset<AMAX>(sp, tb, st, v.e, v.at(st.episode, 0) + 1, v.eg, v.Ng);
   }
 }
 

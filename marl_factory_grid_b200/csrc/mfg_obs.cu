@@ -313,7 +313,9 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
       for (int i = lane; i < n4; i += 32) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncwarp();
-    bool any_door = false, any_dirt = false;
+    // Each lane keeps (up to) two sprites of the env in registers across the three passes; a third round (more than
+    // 64 sprites) only exists on the overflow path.  Dirt amounts (f64, uncoalesced) are requested as soon as the sprite
+    // is decoded so that their latency overlaps the integer pass.
     for (int ge = 0; ge < GE; ++ge) {
       const int el = g * GE + ge;
       const int64_t e = env0 + el;
@@ -324,58 +326,57 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
         slow_fill_env(sp, tb, st, sl, s_pos + el * sl.stride, s_vis + el * A, s_dopen[el], s_reached[el], te, e, lane);
         continue;
       }
+      Sprite s0{0u, 0.f}, s1{0u, 0.f};
+      uint32_t k0 = 0xFF, k1 = 0xFF;
+      double d0 = 0.0, d1 = 0.0;
+      if (lane < cnt) {
+        s0 = s_spr[(size_t)el * cap + lane];
+        k0 = (s0.w >> 16) & 0xFF;
+        if (k0 == SK_DIRT) d0 = st.dirt_amt[(size_t)(s0.w >> 24) * st.N + e];
+      }
+      if (lane + 32 < cnt) {
+        s1 = s_spr[(size_t)el * cap + lane + 32];
+        k1 = (s1.w >> 16) & 0xFF;
+        if (k1 == SK_DIRT) d1 = st.dirt_amt[(size_t)(s1.w >> 24) * st.N + e];
+      }
       // wall planes: 1.0 where a visible wall is.  Nothing else can be on a wall cell, so the (predicated) store has a
       // unique writer and needs no ordering against the sprite adds below.
       for (int w = 0; w < wp.n; ++w) {
-        const unsigned long long wv = s_wv[el * A + wp.agent[w]];
+        const uint32_t* wv32 = reinterpret_cast<const uint32_t*>(s_wv + el * A + wp.agent[w]);
         float* plane = te + (int)wp.plane[w] * DD;
-        for (int cell = lane; cell < DD; cell += 32) if ((wv >> cell) & 1) plane[cell] = 1.0f;
+        if ((wv32[0] >> lane) & 1u) plane[lane] = 1.0f;
+        if (lane + 32 < DD && ((wv32[1] >> lane) & 1u)) plane[lane + 32] = 1.0f;
       }
-      // integer-valued sprites (stacks add up exactly) and direct stores
-      for (int i = lane; i < cnt; i += 32) {
+      // pass A: integer-valued sprites (stacks add up exactly) and direct stores
+      if (k0 == SK_INT) atomicAdd(&te[s0.w & 0xFFFF], s0.val);
+      else if (k0 == SK_STORE) te[s0.w & 0xFFFF] = s0.val;
+      if (k1 == SK_INT) atomicAdd(&te[s1.w & 0xFFFF], s1.val);
+      else if (k1 == SK_STORE) te[s1.w & 0xFFFF] = s1.val;
+      for (int i = lane + 64; i < cnt; i += 32) {          // only reachable with a raised sprite capacity
         const Sprite s = s_spr[(size_t)el * cap + i];
         const uint32_t kind = (s.w >> 16) & 0xFF;
         if (kind == SK_INT) atomicAdd(&te[s.w & 0xFFFF], s.val);
         else if (kind == SK_STORE) te[s.w & 0xFFFF] = s.val;
-        else if (kind == SK_DOOR) any_door = true;
-        else any_dirt = true;
       }
-    }
-    any_door = __any_sync(0xffffffffu, any_door);
-    any_dirt = __any_sync(0xffffffffu, any_dirt);
-    // fractional encodings last: value = (float)((double)integer_stack + encoding), one rounding like the reference
-    if (any_door) {
-      __syncwarp();
-      for (int ge = 0; ge < GE; ++ge) {
-        const int el = g * GE + ge;
-        if (env0 + el >= st.N) break;
-        const int cnt = s_cnt[el];
-        if (cnt > cap) continue;                     // filled completely by the overflow path
-        float* te = tile + (size_t)ge * total_channels * DD;
-        for (int i = lane; i < cnt; i += 32) {
+      // fractional encodings last: value = (float)((double)integer_stack + encoding), one rounding like the reference
+      const bool door_here = k0 == SK_DOOR || k1 == SK_DOOR || cnt > 64;
+      const bool dirt_here = k0 == SK_DIRT || k1 == SK_DIRT || cnt > 64;
+      if (__any_sync(0xffffffffu, door_here)) {
+        __syncwarp();
+        if (k0 == SK_DOOR) { float* f = &te[s0.w & 0xFFFF]; *f = (float)((double)*f + ((s0.w >> 24) ? ENC_DOOR_OPEN : ENC_DOOR_CLOSED)); }
+        if (k1 == SK_DOOR) { float* f = &te[s1.w & 0xFFFF]; *f = (float)((double)*f + ((s1.w >> 24) ? ENC_DOOR_OPEN : ENC_DOOR_CLOSED)); }
+        for (int i = lane + 64; i < cnt; i += 32) {
           const Sprite s = s_spr[(size_t)el * cap + i];
-          if (((s.w >> 16) & 0xFF) == SK_DOOR) {
-            float* f = &te[s.w & 0xFFFF];
-            *f = (float)((double)*f + ((s.w >> 24) ? ENC_DOOR_OPEN : ENC_DOOR_CLOSED));
-          }
+          if (((s.w >> 16) & 0xFF) == SK_DOOR) { float* f = &te[s.w & 0xFFFF]; *f = (float)((double)*f + ((s.w >> 24) ? ENC_DOOR_OPEN : ENC_DOOR_CLOSED)); }
         }
       }
-    }
-    if (any_dirt) {
-      __syncwarp();
-      for (int ge = 0; ge < GE; ++ge) {
-        const int el = g * GE + ge;
-        const int64_t e = env0 + el;
-        if (e >= st.N) break;
-        const int cnt = s_cnt[el];
-        if (cnt > cap) continue;
-        float* te = tile + (size_t)ge * total_channels * DD;
-        for (int i = lane; i < cnt; i += 32) {
+      if (__any_sync(0xffffffffu, dirt_here)) {
+        __syncwarp();
+        if (k0 == SK_DIRT) { float* f = &te[s0.w & 0xFFFF]; *f = (float)((double)*f + d0); }
+        if (k1 == SK_DIRT) { float* f = &te[s1.w & 0xFFFF]; *f = (float)((double)*f + d1); }
+        for (int i = lane + 64; i < cnt; i += 32) {
           const Sprite s = s_spr[(size_t)el * cap + i];
-          if (((s.w >> 16) & 0xFF) == SK_DIRT) {
-            float* f = &te[s.w & 0xFFFF];
-            *f = (float)((double)*f + st.dirt_amt[(size_t)(s.w >> 24) * st.N + e]);
-          }
+          if (((s.w >> 16) & 0xFF) == SK_DIRT) { float* f = &te[s.w & 0xFFFF]; *f = (float)((double)*f + st.dirt_amt[(size_t)(s.w >> 24) * st.N + e]); }
         }
       }
     }
