@@ -129,8 +129,9 @@ typedef struct MfgTape {
 
 typedef struct MfgField {
   size_t offset;                   /* byte offset into the state buffer */
-  int32_t rows;                    /* field is [rows][N] */
+  int32_t rows;                    /* field is [rows][stride], the first N entries of a row are live */
   int32_t elem_size;               /* bytes per element */
+  int64_t stride;                  /* elements per row: N rounded up to a multiple of 128 */
 } MfgField;
 
 typedef struct MfgHandle MfgHandle;
@@ -141,7 +142,8 @@ const char* mfg_last_error(void);
 const char* mfg_version(void);
 
 /* State lives in ONE caller-owned device buffer of mfg_state_bytes(h) bytes, laid out field-major:
- * each field is a [rows][N] array (struct-of-arrays, the env index is the fastest one). */
+ * each field is a [rows][stride] array (struct-of-arrays, the env index is the fastest one; stride = N rounded up to
+ * 128 so that every row starts 16-byte aligned and can be moved by TMA bulk copies). */
 size_t mfg_state_bytes(const MfgHandle* h);
 int mfg_state_field(const MfgHandle* h, const char* name, MfgField* out);
 int mfg_bind_state(MfgHandle* h, void* d_state);

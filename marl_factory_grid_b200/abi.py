@@ -62,7 +62,7 @@ class MfgTape(C.Structure):
 
 
 class MfgField(C.Structure):
-    _fields_ = [('offset', C.c_size_t), ('rows', C.c_int32), ('elem_size', C.c_int32)]
+    _fields_ = [('offset', C.c_size_t), ('rows', C.c_int32), ('elem_size', C.c_int32), ('stride', C.c_int64)]
 
 
 def pos16(xy) -> int:

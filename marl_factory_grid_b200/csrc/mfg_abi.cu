@@ -86,7 +86,7 @@ size_t mfg_state_bytes(const MfgHandle* h) { return h ? h->state_bytes : 0; }
 int mfg_state_field(const MfgHandle* h, const char* name, MfgField* out) {
   if (!h || !name || !out) return fail(MFG_E_INVALID, "mfg_state_field: bad arguments");
   for (const auto& f : h->fields)
-    if (strcmp(f.name, name) == 0) { out->offset = f.offset; out->rows = f.rows; out->elem_size = f.elem_size; return MFG_OK; }
+    if (strcmp(f.name, name) == 0) { out->offset = f.offset; out->rows = f.rows; out->elem_size = f.elem_size; out->stride = env_stride(h->N); return MFG_OK; }
   return fail(MFG_E_INVALID, std::string("mfg_state_field: unknown field ") + name);
 }
 

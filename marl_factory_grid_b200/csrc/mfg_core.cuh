@@ -34,6 +34,7 @@ constexpr double CHARGE_RATE = 0.4;      // modules/batteries/entitites.py:98
 constexpr double ENC_DOOR_OPEN = 0.4444, ENC_DOOR_CLOSED = 0.6666, ENC_MACHINE = 15.0;
 constexpr uint16_t NO_POS = 0xFFFF;
 constexpr int RESPAWN_TAPE_W = 8;
+constexpr int ENV_PAD = 128;             // env stride granularity of the state buffer
 
 // entity classes with an integer uid (object.py:103-113)
 enum { C_DOOR = 0, C_DIRT, C_ITEM, C_POD, C_DEST, C_DROP, C_MACH, C_MAINT, C_NONE };
@@ -80,7 +81,8 @@ enum { C_DOOR = 0, C_DIRT, C_ITEM, C_POD, C_DEST, C_DROP, C_MACH, C_MAINT, C_NON
   F(uint8_t, maint_last, sp.n_maint)
 
 struct State {
-  int64_t N;
+  int64_t N;   // live environments
+  int64_t S;   // row stride in elements (N rounded up to ENV_PAD: every [row] starts 16-byte aligned for bulk copies)
 #define F(type, name, rows) type* name;
   MFG_STATE_FIELDS(F)
 #undef F
@@ -166,14 +168,14 @@ struct Env {
   int dirt_end, dirt_n;
 
   MFG_HD Env(const MfgSpec& sp_, const Tables& tb_, const State& st_, int64_t e_, int64_t eg_ = -1, int64_t Ng_ = -1)
-      : sp(sp_), tb(tb_), st(st_), e(e_), eg(eg_ < 0 ? e_ : eg_), Ng(Ng_ < 0 ? st_.N : Ng_) {
+      : sp(sp_), tb(tb_), st(st_), e(e_), eg(eg_ < 0 ? e_ : eg_), Ng(Ng_ < 0 ? st_.S : Ng_) {
     A = sp.n_agents;
     dopen = dlisted = dirt_listed = 0;
     dirt_end = dirt_n = 0;
   }
   template <typename T> MFG_HD T& at(T* base, int row) const {
     if constexpr (std::is_same<T, double>::value) return base[(size_t)row * (size_t)Ng + (size_t)eg];
-    else return base[(size_t)row * (size_t)st.N + (size_t)e];
+    else return base[(size_t)row * (size_t)st.S + (size_t)e];
   }
 
   MFG_HD void load() {

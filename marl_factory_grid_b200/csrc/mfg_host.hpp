@@ -18,9 +18,12 @@ struct FieldInfo {
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // field-major layout: each field [rows][N], every field start 256-byte aligned
-inline size_t compute_layout(const MfgSpec& sp, int64_t N, std::vector<FieldInfo>& fields) {
+inline int64_t env_stride(int64_t N) { return (N + ENV_PAD - 1) / ENV_PAD * ENV_PAD; }
+
+inline size_t compute_layout(const MfgSpec& sp, int64_t N_live, std::vector<FieldInfo>& fields) {
   fields.clear();
   size_t off = 0;
+  const int64_t N = env_stride(N_live);
 #define F(type, name, rows_expr)                                            \
   {                                                                         \
     int rows = (int)(rows_expr);                                            \
@@ -36,6 +39,7 @@ inline void bind_state(const MfgSpec& sp, int64_t N, void* base, State& st) {
   std::vector<FieldInfo> fields;
   compute_layout(sp, N, fields);
   st.N = N;
+  st.S = env_stride(N);
   size_t i = 0;
   char* b = static_cast<char*>(base);
 #define F(type, name, rows_expr) st.name = reinterpret_cast<type*>(b + fields[i++].offset);

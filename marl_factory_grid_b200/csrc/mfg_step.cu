@@ -19,44 +19,106 @@ __global__ void __launch_bounds__(128) k_reset(const MfgSpec* __restrict__ sp, T
   env_reset<AMAX>(*sp, tb, st, e, episode);
 }
 
-// k_step: CTA = 128 envs.  Every thread first copies the integer / byte fields of ITS env from the field-major global
-// buffer into shared memory (row after row: fully coalesced, all loads independent => deep memory-level parallelism),
-// runs the whole step against that copy (tile look-ups, slot scans and rule hooks hit shared memory instead of
-// dependent HBM round trips), then writes the fields back.  f64 fields (dirt amounts, battery, returns) stay in HBM:
-// they are touched by few actions / rules only.  No block-level synchronisation is needed: a thread only ever
-// touches its own column.
-constexpr int STEP_ENVS = 128;
+// k_step: CTA = 128 envs.  The integer / byte fields of the CTA's 128 envs are moved from the field-major global
+// buffer into shared memory by TMA bulk copies (one cp.async.bulk per field row, completion on an mbarrier: every
+// copy is in flight at once), the whole step runs against that copy (tile look-ups, slot scans and rule hooks hit
+// shared memory instead of dependent HBM round trips), then the rows are written back with bulk stores.
+// f64 fields (dirt amounts, battery, returns) stay in HBM: few actions / rules touch them.
+constexpr int STEP_ENVS = 128;      // == ENV_PAD: every staged row is a whole, 16-byte aligned 128-env slice
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MFG_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MFG_DONE_%=;\n"
+      "bra MFG_WAIT_%=;\n"
+      "MFG_DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst_smem)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
 
 template <int AMAX>
 __global__ void __launch_bounds__(STEP_ENVS) k_step(const MfgSpec* __restrict__ spp, Tables tb, State st, StepIO io) {
-  extern __shared__ __align__(16) unsigned char stage[];
+  extern __shared__ __align__(128) unsigned char stage[];
+  __shared__ __align__(8) unsigned long long bar;
+  static_assert(STEP_ENVS == ENV_PAD, "staged rows must be whole padded slices");
   const MfgSpec& sp = *spp;
-  const int el = threadIdx.x;
-  const int64_t eg = (int64_t)blockIdx.x * STEP_ENVS + el;
-  const bool live = eg < st.N;
-  const size_t Ng = (size_t)st.N;
+  const int el = threadIdx.x, warp = el >> 5;
+  const bool issuer = (el & 31) == 0;                     // one elected lane per warp issues a quarter of the bulk copies
+  const int64_t e0 = (int64_t)blockIdx.x * STEP_ENVS, eg = e0 + el;
+  const size_t S = (size_t)st.S;
+
   State ss = st;
   ss.N = STEP_ENVS;
-  size_t off = 0;
-#define F(type, name, rows_expr)                                                                   \
-  if constexpr (!std::is_same<type, double>::value) {                                              \
-    const int rows = (int)(rows_expr);                                                             \
-    type* s_ = reinterpret_cast<type*>(stage + off);                                               \
-    ss.name = s_;                                                                                  \
-    if (live) for (int r = 0; r < rows; ++r) s_[r * STEP_ENVS + el] = st.name[(size_t)r * Ng + eg]; \
-    off += ((size_t)rows * STEP_ENVS * sizeof(type) + 15) & ~(size_t)15;                           \
+  ss.S = STEP_ENVS;
+  if (el == 0) mbar_init(&bar, STEP_ENVS / 32);
+  __syncthreads();
+
+  // ---- global -> shared: every row slice of every non-f64 field
+  uint32_t off = 0, mine = 0;
+  int ri = 0;
+#define F(type, name, rows_expr)                                                                    \
+  if constexpr (!std::is_same<type, double>::value) {                                               \
+    const int rows = (int)(rows_expr);                                                              \
+    ss.name = reinterpret_cast<type*>(stage + off);                                                 \
+    if (issuer) for (int r = 0; r < rows; ++r) if (((ri + r) & 3) == warp) mine += STEP_ENVS * sizeof(type); \
+    ri += rows;                                                                                     \
+    off += (uint32_t)rows * STEP_ENVS * sizeof(type);                                               \
   }
   MFG_STATE_FIELDS(F)
 #undef F
-  if (!live) return;
-  env_step<AMAX>(sp, tb, ss, el, io, eg, (int64_t)Ng);
-#define F(type, name, rows_expr)                                                                   \
-  if constexpr (!std::is_same<type, double>::value) {                                              \
-    const int rows = (int)(rows_expr);                                                             \
-    for (int r = 0; r < rows; ++r) st.name[(size_t)r * Ng + eg] = ss.name[r * STEP_ENVS + el];     \
+  if (issuer) {
+    mbar_expect_tx(&bar, mine);
+    ri = 0;
+#define F(type, name, rows_expr)                                                                    \
+  if constexpr (!std::is_same<type, double>::value) {                                               \
+    const int rows = (int)(rows_expr);                                                              \
+    for (int r = 0; r < rows; ++r)                                                                  \
+      if (((ri + r) & 3) == warp)                                                                   \
+        bulk_g2s(ss.name + (size_t)r * STEP_ENVS, st.name + (size_t)r * S + e0, STEP_ENVS * sizeof(type), &bar); \
+    ri += rows;                                                                                     \
   }
-  MFG_STATE_FIELDS(F)
+    MFG_STATE_FIELDS(F)
 #undef F
+  }
+  mbar_wait(&bar, 0);
+
+  if (eg < st.N) env_step<AMAX>(sp, tb, ss, el, io, eg, (int64_t)S);
+
+  // ---- shared -> global
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  __syncthreads();
+  if (issuer) {
+    ri = 0;
+#define F(type, name, rows_expr)                                                                    \
+  if constexpr (!std::is_same<type, double>::value) {                                               \
+    const int rows = (int)(rows_expr);                                                              \
+    for (int r = 0; r < rows; ++r)                                                                  \
+      if (((ri + r) & 3) == warp)                                                                   \
+        bulk_s2g(st.name + (size_t)r * S + e0, ss.name + (size_t)r * STEP_ENVS, STEP_ENVS * sizeof(type)); \
+    ri += rows;                                                                                     \
+  }
+    MFG_STATE_FIELDS(F)
+#undef F
+    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");     // shared memory must outlive the copies
+  }
 }
 
 __global__ void __launch_bounds__(256) k_random_actions(const MfgSpec* __restrict__ sp, int64_t N, int64_t env_id_offset,
@@ -92,7 +154,7 @@ cudaError_t launch_reset(MfgHandle* h, const uint8_t* d_mask, cudaStream_t s) {
 size_t step_stage_bytes(const MfgSpec& sp) {
   size_t off = 0;
 #define F(type, name, rows_expr) \
-  if (!std::is_same<type, double>::value) off += ((size_t)(rows_expr) * STEP_ENVS * sizeof(type) + 15) & ~(size_t)15;
+  if (!std::is_same<type, double>::value) off += (size_t)(rows_expr) * STEP_ENVS * sizeof(type);
   MFG_STATE_FIELDS(F)
 #undef F
   return off;

@@ -106,8 +106,8 @@ class Engine:
             if f.rows == 0:
                 continue
             dt = FIELD_VIEW.get(name, FIELD_DTYPES[f.elem_size])
-            raw = self.state[f.offset:f.offset + f.rows * self.N * f.elem_size]
-            self.fields[name] = raw.view(_torch_dtype(dt)).view(f.rows, self.N)
+            raw = self.state[f.offset:f.offset + f.rows * f.stride * f.elem_size]
+            self.fields[name] = raw.view(_torch_dtype(dt)).view(f.rows, f.stride)[:, :self.N]   # rows are padded to 128 envs
         A = es.n_agents
         self.n_rew = A if es.individual_rewards else 1
         self.obs = torch.zeros((self.N, es.total_channels, es.obs_d, es.obs_d), dtype=torch.float32, device=self.device)

@@ -57,7 +57,7 @@ void hs_destroy(HsHandle* h) { delete h; }
 size_t hs_state_bytes(const HsHandle* h) { return h->bytes; }
 int hs_state_field(const HsHandle* h, const char* name, MfgField* out) {
   for (const auto& f : h->fields)
-    if (std::string(f.name) == name) { out->offset = f.offset; out->rows = f.rows; out->elem_size = f.elem_size; return 0; }
+    if (std::string(f.name) == name) { out->offset = f.offset; out->rows = f.rows; out->elem_size = f.elem_size; out->stride = env_stride(h->N); return 0; }
   return -1;
 }
 void hs_bind_state(HsHandle* h, void* base) { bind_state(h->sp, h->N, base, h->st); }

@@ -67,7 +67,7 @@ class HostSim:
             if f.rows == 0:
                 continue
             dt = FIELD_VIEW.get(name, FIELD_DTYPES[f.elem_size])
-            self.fields[name] = self.buf[f.offset:f.offset + f.rows * n_envs * f.elem_size].view(dt).reshape(f.rows, n_envs)
+            self.fields[name] = self.buf[f.offset:f.offset + f.rows * f.stride * f.elem_size].view(dt).reshape(f.rows, f.stride)[:, :n_envs]
         A = es.n_agents
         self.n_rew = A if es.individual_rewards else 1
         self.reward = np.zeros((n_envs, self.n_rew), np.float32)
