@@ -160,7 +160,11 @@ def run_engine(args):
     eng.reset()
 
     def one_step(i, ev=None):
+        if ev is not None:
+            ev[2].record()
         eng.random_actions(acts, seed=0, step_index=i)
+        if ev is not None:
+            ev[3].record()
         eng.step(acts, auto_reset=True)
         if ev is not None:
             ev[0].record()
@@ -177,7 +181,7 @@ def run_engine(args):
         one_step(i)
     barrier()
     launches0 = eng.info('launches')
-    obs_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    obs_events = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(4)) for _ in range(args.steps)]
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         barrier()
@@ -187,7 +191,9 @@ def run_engine(args):
         stop.record()
         barrier()
     elapsed_ms = start.elapsed_time(stop)
-    obs_ms = sum(a.elapsed_time(b) for a, b in obs_events) / max(args.steps, 1)
+    obs_ms = sum(ev[0].elapsed_time(ev[1]) for ev in obs_events) / max(args.steps, 1)
+    step_ms = sum(ev[3].elapsed_time(ev[0]) for ev in obs_events) / max(args.steps, 1)
+    rand_ms = sum(ev[2].elapsed_time(ev[3]) for ev in obs_events) / max(args.steps, 1)
     launches = eng.info('launches') - launches0
 
     # episode statistics: the only cross-GPU exchange of the path (one small all-reduce over NVLink)
@@ -259,6 +265,7 @@ def run_engine(args):
                                     'achieved': step_bytes * env_steps_per_s / world / 1e9,
                                     'frac': step_bytes * env_steps_per_s / world / 1e9 / peak}},
         'gpu_launches': launches,
+        'kernel_ms': {'k_random_actions': rand_ms, 'k_step': step_ms, 'k_obs': obs_ms},
         'clocks': clocks.summary(),
         'episode_stats': {'episodes': int(stats[0]), 'env_steps_in_finished_episodes': int(stats[1]),
                           'collisions': int(stats[8]), 'dirt_overflow': int(stats[9]), 'spawn_fail': int(stats[10])},

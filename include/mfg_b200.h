@@ -128,11 +128,11 @@ typedef struct MfgTape {
 } MfgTape;
 
 typedef struct MfgField {
-  size_t offset;                   /* byte offset into the state buffer */
-  int32_t rows;                    /* field is [rows][stride], the first N entries of a row are live */
+  size_t offset;                   /* byte offset of the field's [rows][128] slab of env block 0 in the state buffer */
+  int32_t rows;
   int32_t elem_size;               /* bytes per element */
-  int64_t stride;                  /* elements per row: N rounded up to a multiple of 128 */
-} MfgField;
+  size_t block_bytes;              /* distance between the slabs of consecutive 128-env blocks */
+} MfgField;                        /* element (row r, env e) lives at offset + (e / 128) * block_bytes + (r * 128 + e % 128) * elem_size */
 
 typedef struct MfgHandle MfgHandle;
 
@@ -142,8 +142,9 @@ const char* mfg_last_error(void);
 const char* mfg_version(void);
 
 /* State lives in ONE caller-owned device buffer of mfg_state_bytes(h) bytes, laid out field-major:
- * each field is a [rows][stride] array (struct-of-arrays, the env index is the fastest one; stride = N rounded up to
- * 128 so that every row starts 16-byte aligned and can be moved by TMA bulk copies). */
+ * BLOCKED struct-of-arrays: envs are grouped in blocks of 128; a block stores every row of every integer / byte field
+ * back to back as [rows][128] slabs (one contiguous range => one TMA bulk copy stages it), a second region stores the
+ * f64 fields the same way.  Within a slab the env index is the fastest one (coalesced per warp). */
 size_t mfg_state_bytes(const MfgHandle* h);
 int mfg_state_field(const MfgHandle* h, const char* name, MfgField* out);
 int mfg_bind_state(MfgHandle* h, void* d_state);

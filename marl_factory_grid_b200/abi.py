@@ -17,6 +17,7 @@ RULE_NPARAM = 6
 MAX_RAYS, MAX_RAY_LEN = 64, 16
 NO_POS = 0xFFFF
 N_STATS = 32
+ENV_BLOCK = 128          # envs per state block (blocked struct-of-arrays layout, include/mfg_b200.h)
 RESPAWN_TAPE_W = 8
 
 # spawn-program ids (MFG_SP_*)
@@ -62,7 +63,7 @@ class MfgTape(C.Structure):
 
 
 class MfgField(C.Structure):
-    _fields_ = [('offset', C.c_size_t), ('rows', C.c_int32), ('elem_size', C.c_int32), ('stride', C.c_int64)]
+    _fields_ = [('offset', C.c_size_t), ('rows', C.c_int32), ('elem_size', C.c_int32), ('block_bytes', C.c_size_t)]
 
 
 def pos16(xy) -> int:

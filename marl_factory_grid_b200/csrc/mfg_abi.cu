@@ -60,7 +60,11 @@ int mfg_create(const MfgSpec* spec, int64_t n_envs, int64_t env_id_offset, MfgHa
   h->dev_allocs.push_back(d);
   h->d_sp = static_cast<MfgSpec*>(d);
   cudaMemcpy(h->d_sp, &h->sp, sizeof(MfgSpec), cudaMemcpyHostToDevice);
-  h->state_bytes = compute_layout(h->sp, n_envs, h->fields);
+  {
+    Layout L = compute_layout(h->sp, n_envs);
+    h->fields = L.fields;
+    h->state_bytes = L.total;
+  }
   h->total_channels = 0;
   for (int a = 0; a < h->sp.n_agents; ++a) h->total_channels += h->sp.n_channels[a];
   const int D = 2 * h->sp.pomdp_r + 1;
@@ -86,7 +90,7 @@ size_t mfg_state_bytes(const MfgHandle* h) { return h ? h->state_bytes : 0; }
 int mfg_state_field(const MfgHandle* h, const char* name, MfgField* out) {
   if (!h || !name || !out) return fail(MFG_E_INVALID, "mfg_state_field: bad arguments");
   for (const auto& f : h->fields)
-    if (strcmp(f.name, name) == 0) { out->offset = f.offset; out->rows = f.rows; out->elem_size = f.elem_size; out->stride = env_stride(h->N); return MFG_OK; }
+    if (strcmp(f.name, name) == 0) { out->offset = f.offset; out->rows = f.rows; out->elem_size = f.elem_size; out->block_bytes = f.block_bytes; return MFG_OK; }
   return fail(MFG_E_INVALID, std::string("mfg_state_field: unknown field ") + name);
 }
 

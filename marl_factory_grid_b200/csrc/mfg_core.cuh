@@ -34,7 +34,7 @@ constexpr double CHARGE_RATE = 0.4;      // modules/batteries/entitites.py:98
 constexpr double ENC_DOOR_OPEN = 0.4444, ENC_DOOR_CLOSED = 0.6666, ENC_MACHINE = 15.0;
 constexpr uint16_t NO_POS = 0xFFFF;
 constexpr int RESPAWN_TAPE_W = 8;
-constexpr int ENV_PAD = 128;             // env stride granularity of the state buffer
+constexpr int ENV_BLOCK = 128;           // envs per state block (see State)
 
 // entity classes with an integer uid (object.py:103-113)
 enum { C_DOOR = 0, C_DIRT, C_ITEM, C_POD, C_DEST, C_DROP, C_MACH, C_MAINT, C_NONE };
@@ -80,9 +80,14 @@ enum { C_DOOR = 0, C_DIRT, C_ITEM, C_POD, C_DEST, C_DROP, C_MACH, C_MAINT, C_NON
   F(uint32_t, maint_remaining, sp.n_maint)                                         \
   F(uint8_t, maint_last, sp.n_maint)
 
+// The buffer is BLOCKED: envs are grouped in blocks of ENV_BLOCK = 128; one block holds, back to back, every row of
+// every integer / byte field as a [rows][128] slab (blk_i bytes per block, contiguous => one TMA bulk copy stages a
+// CTA's whole working set), a second region holds the f64 fields the same way (blk_f bytes per block).  Within a slab
+// the env index is the fastest one, so a warp's access to one field row is a single coalesced 32/64/128/256-byte segment.
 struct State {
-  int64_t N;   // live environments
-  int64_t S;   // row stride in elements (N rounded up to ENV_PAD: every [row] starts 16-byte aligned for bulk copies)
+  int64_t N;       // live environments
+  size_t blk_i;    // bytes per 128-env block of the integer region
+  size_t blk_f;    // bytes per 128-env block of the f64 region
 #define F(type, name, rows) type* name;
   MFG_STATE_FIELDS(F)
 #undef F
@@ -102,6 +107,14 @@ struct Tables {
   int64_t env_id_offset;
   unsigned long long* stats;   // [MFG_N_STATS]
 };
+
+// element (row, env e) of a field whose block-0 slab starts at `base`
+template <typename T>
+MFG_HD T& field_at(const State& st, T* base, int row, int64_t e) {
+  const size_t blk = std::is_same<T, double>::value ? st.blk_f : st.blk_i;
+  char* b = reinterpret_cast<char*>(base) + (size_t)(e >> 7) * blk;
+  return reinterpret_cast<T*>(b)[row * ENV_BLOCK + (int)(e & (ENV_BLOCK - 1))];
+}
 
 MFG_HD int px(uint16_t p) { return p >> 8; }
 MFG_HD int py(uint16_t p) { return p & 255; }
@@ -159,23 +172,22 @@ struct Env {
   const MfgSpec& sp;
   const Tables& tb;
   const State& st;
-  int64_t e;        // env index inside `st` (== eg unless the integer fields were staged into a per-CTA copy)
-  int64_t eg;       // env index in the caller's global buffers: f64 fields, actions / reward / done, tape
-  int64_t Ng;       // env stride of the f64 fields (they are never staged)
+  int64_t e;        // env index inside `st`'s integer region (== eg unless that region was staged into a per-CTA copy)
+  int64_t eg;       // global env index: f64 fields (never staged), actions / reward / done, tape, Philox key
   int A;
   uint16_t apos[AMAX];
   uint64_t dopen, dlisted, dirt_listed;
   int dirt_end, dirt_n;
 
-  MFG_HD Env(const MfgSpec& sp_, const Tables& tb_, const State& st_, int64_t e_, int64_t eg_ = -1, int64_t Ng_ = -1)
-      : sp(sp_), tb(tb_), st(st_), e(e_), eg(eg_ < 0 ? e_ : eg_), Ng(Ng_ < 0 ? st_.S : Ng_) {
+  MFG_HD Env(const MfgSpec& sp_, const Tables& tb_, const State& st_, int64_t e_, int64_t eg_ = -1)
+      : sp(sp_), tb(tb_), st(st_), e(e_), eg(eg_ < 0 ? e_ : eg_) {
     A = sp.n_agents;
     dopen = dlisted = dirt_listed = 0;
     dirt_end = dirt_n = 0;
   }
   template <typename T> MFG_HD T& at(T* base, int row) const {
-    if constexpr (std::is_same<T, double>::value) return base[(size_t)row * (size_t)Ng + (size_t)eg];
-    else return base[(size_t)row * (size_t)st.S + (size_t)e];
+    if constexpr (std::is_same<T, double>::value) return field_at(st, base, row, eg);
+    else return field_at(st, base, row, e);
   }
 
   MFG_HD void load() {
@@ -391,8 +403,8 @@ MFG_HD void stat_add_f64(const Tables& tb, int idx, double v) {
 // ================================================================================================
 template <int AMAX>
 MFG_HDN void env_reset(const MfgSpec& sp, const Tables& tb, const State& st, int64_t e, uint32_t episode,
-                       int64_t eg = -1, int64_t Ng = -1) {
-  Env<AMAX> v(sp, tb, st, e, eg, Ng);
+                       int64_t eg = -1) {
+  Env<AMAX> v(sp, tb, st, e, eg);
   const int A = v.A;
   Philox rng;
   rng.init(sp.seed, (uint64_t)(tb.env_id_offset + v.eg), RS_RESET, episode, 0);
@@ -543,8 +555,8 @@ MFG_HD int maint_policy(Env<AMAX>& v, int k, uint32_t step) {
 
 template <int AMAX>
 MFG_HDN void env_step(const MfgSpec& sp, const Tables& tb, const State& st, int64_t e_local, const StepIO& io,
-                      int64_t eg = -1, int64_t Ng = -1) {
-  Env<AMAX> v(sp, tb, st, e_local, eg, Ng);
+                      int64_t eg = -1) {
+  Env<AMAX> v(sp, tb, st, e_local, eg);
   const int64_t e = v.eg;            // index into the caller's actions / tape / reward / done buffers
   v.load();
   const int A = v.A;
@@ -853,7 +865,7 @@ MFG_HDN void env_step(const MfgSpec& sp, const Tables& tb, const State& st, int6
     const int nr = sp.individual_rewards ? A : 1;
     for (int i = 0; i < nr; ++i) { double x = v.at(st.ep_ret, i); tot += x; stat_add_f64(tb, MFG_ST_RETURN_AGENT0 + i, x); }
     stat_add_f64(tb, MFG_ST_RETURN_SUM, tot);
-    if (io.auto_reset) env_reset<AMAX>(sp, tb, st, v.e, v.at(st.episode, 0) + 1, v.eg, v.Ng);
+    if (io.auto_reset) env_reset<AMAX>(sp, tb, st, v.e, v.at(st.episode, 0) + 1, v.eg);
   }
 }
 

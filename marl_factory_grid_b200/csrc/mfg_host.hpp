@@ -10,39 +10,61 @@ namespace mfg {
 
 struct FieldInfo {
   const char* name;
-  size_t offset;
+  size_t offset;        // byte offset of the field's slab inside block 0 (relative to the buffer start)
   int rows;
   int elem_size;
+  size_t block_bytes;   // distance between the slabs of consecutive 128-env blocks
+};
+
+struct Layout {
+  std::vector<FieldInfo> fields;
+  size_t blk_i = 0, blk_f = 0;      // bytes per block: integer region / f64 region
+  size_t off_f = 0;                 // start of the f64 region
+  size_t total = 0;
+  int64_t n_blocks = 0;
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// field-major layout: each field [rows][N], every field start 256-byte aligned
-inline int64_t env_stride(int64_t N) { return (N + ENV_PAD - 1) / ENV_PAD * ENV_PAD; }
-
-inline size_t compute_layout(const MfgSpec& sp, int64_t N_live, std::vector<FieldInfo>& fields) {
-  fields.clear();
-  size_t off = 0;
-  const int64_t N = env_stride(N_live);
-#define F(type, name, rows_expr)                                            \
-  {                                                                         \
-    int rows = (int)(rows_expr);                                            \
-    fields.push_back(FieldInfo{#name, off, rows, (int)sizeof(type)});       \
-    off = align_up(off + (size_t)rows * (size_t)N * sizeof(type), 256);     \
+// blocked layout (see State in mfg_core.cuh): [block][field][row][128 envs], integer region first, f64 region second
+inline Layout compute_layout(const MfgSpec& sp, int64_t N) {
+  Layout L;
+  L.n_blocks = (N + ENV_BLOCK - 1) / ENV_BLOCK;
+  size_t oi = 0, of = 0;
+#define F(type, name, rows_expr)                                                                      \
+  {                                                                                                   \
+    const int rows = (int)(rows_expr);                                                                \
+    const bool f64 = std::is_same<type, double>::value;                                               \
+    L.fields.push_back(FieldInfo{#name, f64 ? of : oi, rows, (int)sizeof(type), 0});                  \
+    (f64 ? of : oi) += (size_t)rows * ENV_BLOCK * sizeof(type);                                       \
   }
   MFG_STATE_FIELDS(F)
 #undef F
-  return off;
+  L.blk_i = oi;                      // every slab is a multiple of 128 bytes => blocks stay 128-byte aligned
+  L.blk_f = of;
+  L.off_f = align_up((size_t)L.n_blocks * L.blk_i, 256);
+  L.total = align_up(L.off_f + (size_t)L.n_blocks * L.blk_f, 256);
+  size_t i = 0;
+#define F(type, name, rows_expr)                                                                      \
+  {                                                                                                   \
+    const bool f64 = std::is_same<type, double>::value;                                               \
+    if (f64) L.fields[i].offset += L.off_f;                                                           \
+    L.fields[i].block_bytes = f64 ? L.blk_f : L.blk_i;                                                \
+    ++i;                                                                                              \
+  }
+  MFG_STATE_FIELDS(F)
+#undef F
+  return L;
 }
 
 inline void bind_state(const MfgSpec& sp, int64_t N, void* base, State& st) {
-  std::vector<FieldInfo> fields;
-  compute_layout(sp, N, fields);
+  Layout L = compute_layout(sp, N);
   st.N = N;
-  st.S = env_stride(N);
+  st.blk_i = L.blk_i;
+  st.blk_f = L.blk_f;
   size_t i = 0;
   char* b = static_cast<char*>(base);
-#define F(type, name, rows_expr) st.name = reinterpret_cast<type*>(b + fields[i++].offset);
+#define F(type, name, rows_expr) st.name = reinterpret_cast<type*>(b + L.fields[i++].offset);
   MFG_STATE_FIELDS(F)
 #undef F
 }

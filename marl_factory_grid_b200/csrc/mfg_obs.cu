@@ -66,15 +66,14 @@ enum { SK_INT = 0, SK_STORE = 1, SK_DOOR = 2, SK_DIRT = 3 };
 struct Sprite { uint32_t w; float val; };          // w = index | kind << 16 | aux << 24
 
 __device__ __forceinline__ uint16_t load_slot(const State& st, const ObsSlots& sl, int s, int64_t e) {
-  const size_t N = (size_t)st.S;
-  if (s < sl.item0) return st.dirt_pos[(size_t)(s - sl.dirt0) * N + e];
-  if (s < sl.pod0) return st.item_pos[(size_t)(s - sl.item0) * N + e];
-  if (s < sl.dest0) return st.pod_pos[(size_t)(s - sl.pod0) * N + e];
-  if (s < sl.drop0) return st.dest_pos[(size_t)(s - sl.dest0) * N + e];
-  if (s < sl.mach0) return st.drop_pos[(size_t)(s - sl.drop0) * N + e];
-  if (s < sl.maint0) return st.mach_pos[(size_t)(s - sl.mach0) * N + e];
-  if (s < sl.agent0) return st.maint_pos[(size_t)(s - sl.maint0) * N + e];
-  return st.apos[(size_t)(s - sl.agent0) * N + e];
+  if (s < sl.item0) return field_at(st, st.dirt_pos, s - sl.dirt0, e);
+  if (s < sl.pod0) return field_at(st, st.item_pos, s - sl.item0, e);
+  if (s < sl.dest0) return field_at(st, st.pod_pos, s - sl.pod0, e);
+  if (s < sl.drop0) return field_at(st, st.dest_pos, s - sl.dest0, e);
+  if (s < sl.mach0) return field_at(st, st.drop_pos, s - sl.drop0, e);
+  if (s < sl.maint0) return field_at(st, st.mach_pos, s - sl.mach0, e);
+  if (s < sl.agent0) return field_at(st, st.maint_pos, s - sl.maint0, e);
+  return field_at(st, st.apos, s - sl.agent0, e);
 }
 
 __device__ __forceinline__ void bulk_store_tile(float* dst, const float* src_smem, uint32_t bytes) {
@@ -143,7 +142,7 @@ __device__ void slow_fill_env(const MfgSpec* __restrict__ sp, const Tables& tb, 
       if (q == NO_POS) continue;
       const int dx = px(q) - ax, dy = py(q) - ay;
       if (dx < 0 || dy < 0 || dx >= D || dy >= D) continue;
-      if ((vis_a[a] >> (dx * D + dy)) & 1) add_frac(m, sp->ch_offset[a], dx * D + dy, st.dirt_amt[(size_t)k * st.S + e]);
+      if ((vis_a[a] >> (dx * D + dy)) & 1) add_frac(m, sp->ch_offset[a], dx * D + dy, field_at(st, st.dirt_amt, (int)(k), e));
     }
   }
   __syncwarp();
@@ -151,7 +150,7 @@ __device__ void slow_fill_env(const MfgSpec* __restrict__ sp, const Tables& tb, 
     const int C = sp->n_channels[a], coff = sp->ch_offset[a];
     for (int c = 0; c < C; ++c) {
       const int kind = sp->ch_kind[a][c];
-      if (kind == MFG_CH_BATTERY) te[(coff + c) * DD] = (float)st.bat[(size_t)a * st.S + e];
+      if (kind == MFG_CH_BATTERY) te[(coff + c) * DD] = (float)field_at(st, st.bat, a, e);
       else if (kind == MFG_CH_GLOBALPOS) {
         const uint16_t ap = pos[sl.agent0 + a];
         te[(coff + c) * DD] = (float)((double)px(ap) / (double)sp->H);
@@ -189,8 +188,8 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
     // stage the dynamic entity positions: warp w copies slots w, w+NW, ... (coalesced over the env lanes)
     for (int s = warp; s < sl.total; s += NW) s_pos[lane * sl.stride + s] = live ? load_slot(st, sl, s, e) : NO_POS;
     if (warp == 0) {
-      s_dopen[lane] = (live && sp->n_doors) ? st.door_open[e] : 0ull;
-      s_reached[lane] = (live && sp->n_dest) ? st.dest_reached[e] : 0u;
+      s_dopen[lane] = (live && sp->n_doors) ? field_at(st, st.door_open, 0, e) : 0ull;
+      s_reached[lane] = (live && sp->n_dest) ? field_at(st, st.dest_reached, 0, e) : 0u;
       s_cnt[lane] = 0;
     }
     __syncthreads();
@@ -279,7 +278,7 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
         for (int c = 0; c < C; ++c) {
           const int kind = sp->ch_kind[a][c];
           if (kind == MFG_CH_BATTERY) {
-            put((uint32_t)((coff + c) * DD) | (SK_STORE << 16), (float)st.bat[(size_t)a * st.S + e]);
+            put((uint32_t)((coff + c) * DD) | (SK_STORE << 16), (float)field_at(st, st.bat, a, e));
           } else if (kind == MFG_CH_GLOBALPOS) {
             put((uint32_t)((coff + c) * DD) | (SK_STORE << 16), (float)((double)ax / (double)sp->H));
             put((uint32_t)((coff + c) * DD + 1) | (SK_STORE << 16), (float)((double)ay / (double)sp->W));
@@ -332,12 +331,12 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
       if (lane < cnt) {
         s0 = s_spr[(size_t)el * cap + lane];
         k0 = (s0.w >> 16) & 0xFF;
-        if (k0 == SK_DIRT) d0 = st.dirt_amt[(size_t)(s0.w >> 24) * st.S + e];
+        if (k0 == SK_DIRT) d0 = field_at(st, st.dirt_amt, (int)((s0.w >> 24)), e);
       }
       if (lane + 32 < cnt) {
         s1 = s_spr[(size_t)el * cap + lane + 32];
         k1 = (s1.w >> 16) & 0xFF;
-        if (k1 == SK_DIRT) d1 = st.dirt_amt[(size_t)(s1.w >> 24) * st.S + e];
+        if (k1 == SK_DIRT) d1 = field_at(st, st.dirt_amt, (int)((s1.w >> 24)), e);
       }
       // wall planes: 1.0 where a visible wall is.  Nothing else can be on a wall cell, so the (predicated) store has a
       // unique writer and needs no ordering against the sprite adds below.
@@ -376,7 +375,7 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
         if (k1 == SK_DIRT) { float* f = &te[s1.w & 0xFFFF]; *f = (float)((double)*f + d1); }
         for (int i = lane + 64; i < cnt; i += 32) {
           const Sprite s = s_spr[(size_t)el * cap + i];
-          if (((s.w >> 16) & 0xFF) == SK_DIRT) { float* f = &te[s.w & 0xFFFF]; *f = (float)((double)*f + st.dirt_amt[(size_t)(s.w >> 24) * st.S + e]); }
+          if (((s.w >> 16) & 0xFF) == SK_DIRT) { float* f = &te[s.w & 0xFFFF]; *f = (float)((double)*f + field_at(st, st.dirt_amt, (int)((s.w >> 24)), e)); }
         }
       }
     }

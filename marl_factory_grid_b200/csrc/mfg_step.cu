@@ -15,16 +15,16 @@ __global__ void __launch_bounds__(128) k_reset(const MfgSpec* __restrict__ sp, T
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= st.N) return;
   if (mask && !mask[e]) return;
-  uint32_t episode = mask ? st.episode[e] + 1 : 0;
+  uint32_t episode = mask ? field_at(st, st.episode, 0, e) + 1 : 0;
   env_reset<AMAX>(*sp, tb, st, e, episode);
 }
 
-// k_step: CTA = 128 envs.  The integer / byte fields of the CTA's 128 envs are moved from the field-major global
-// buffer into shared memory by TMA bulk copies (one cp.async.bulk per field row, completion on an mbarrier: every
-// copy is in flight at once), the whole step runs against that copy (tile look-ups, slot scans and rule hooks hit
-// shared memory instead of dependent HBM round trips), then the rows are written back with bulk stores.
-// f64 fields (dirt amounts, battery, returns) stay in HBM: few actions / rules touch them.
-constexpr int STEP_ENVS = 128;      // == ENV_PAD: every staged row is a whole, 16-byte aligned 128-env slice
+// k_step: CTA = one 128-env state block.  The block's integer / byte fields are ONE contiguous slab in HBM (blocked
+// layout, see State): a single TMA bulk copy (cp.async.bulk, completion on an mbarrier) stages it in shared memory,
+// the whole step runs against that copy (tile look-ups, slot scans and rule hooks hit shared memory instead of
+// dependent HBM round trips), and a single bulk store writes it back.  f64 fields (dirt amounts, battery, returns)
+// stay in HBM: few actions / rules touch them.
+constexpr int STEP_ENVS = ENV_BLOCK;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
@@ -57,67 +57,39 @@ template <int AMAX>
 __global__ void __launch_bounds__(STEP_ENVS) k_step(const MfgSpec* __restrict__ spp, Tables tb, State st, StepIO io) {
   extern __shared__ __align__(128) unsigned char stage[];
   __shared__ __align__(8) unsigned long long bar;
-  static_assert(STEP_ENVS == ENV_PAD, "staged rows must be whole padded slices");
   const MfgSpec& sp = *spp;
-  const int el = threadIdx.x, warp = el >> 5;
-  const bool issuer = (el & 31) == 0;                     // one elected lane per warp issues a quarter of the bulk copies
+  const int el = threadIdx.x;
   const int64_t e0 = (int64_t)blockIdx.x * STEP_ENVS, eg = e0 + el;
-  const size_t S = (size_t)st.S;
+  char* gblock = reinterpret_cast<char*>(st.step) + (size_t)blockIdx.x * st.blk_i;     // `step` is the first field
+  const uint32_t bytes = (uint32_t)st.blk_i;
 
+  if (el == 0) {
+    mbar_init(&bar, 1);
+    mbar_expect_tx(&bar, bytes);
+    // a bulk copy moves at most 2^20 - 16 bytes per instruction; blocks are tens of KB
+    bulk_g2s(stage, gblock, bytes, &bar);
+  }
+  // staged view of the state: same field offsets, block 0 == the shared-memory copy
   State ss = st;
   ss.N = STEP_ENVS;
-  ss.S = STEP_ENVS;
-  if (el == 0) mbar_init(&bar, STEP_ENVS / 32);
-  __syncthreads();
-
-  // ---- global -> shared: every row slice of every non-f64 field
-  uint32_t off = 0, mine = 0;
-  int ri = 0;
-#define F(type, name, rows_expr)                                                                    \
-  if constexpr (!std::is_same<type, double>::value) {                                               \
-    const int rows = (int)(rows_expr);                                                              \
-    ss.name = reinterpret_cast<type*>(stage + off);                                                 \
-    if (issuer) for (int r = 0; r < rows; ++r) if (((ri + r) & 3) == warp) mine += STEP_ENVS * sizeof(type); \
-    ri += rows;                                                                                     \
-    off += (uint32_t)rows * STEP_ENVS * sizeof(type);                                               \
-  }
-  MFG_STATE_FIELDS(F)
-#undef F
-  if (issuer) {
-    mbar_expect_tx(&bar, mine);
-    ri = 0;
-#define F(type, name, rows_expr)                                                                    \
-  if constexpr (!std::is_same<type, double>::value) {                                               \
-    const int rows = (int)(rows_expr);                                                              \
-    for (int r = 0; r < rows; ++r)                                                                  \
-      if (((ri + r) & 3) == warp)                                                                   \
-        bulk_g2s(ss.name + (size_t)r * STEP_ENVS, st.name + (size_t)r * S + e0, STEP_ENVS * sizeof(type), &bar); \
-    ri += rows;                                                                                     \
-  }
+  {
+    const char* g0 = reinterpret_cast<const char*>(st.step);
+#define F(type, name, rows_expr) \
+  if constexpr (!std::is_same<type, double>::value) ss.name = reinterpret_cast<type*>(stage + (reinterpret_cast<const char*>(st.name) - g0));
     MFG_STATE_FIELDS(F)
 #undef F
   }
+  __syncthreads();                  // the barrier init must be visible before anybody polls it
   mbar_wait(&bar, 0);
 
-  if (eg < st.N) env_step<AMAX>(sp, tb, ss, el, io, eg, (int64_t)S);
+  if (eg < st.N) env_step<AMAX>(sp, tb, ss, el, io, eg);
 
-  // ---- shared -> global
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   __syncthreads();
-  if (issuer) {
-    ri = 0;
-#define F(type, name, rows_expr)                                                                    \
-  if constexpr (!std::is_same<type, double>::value) {                                               \
-    const int rows = (int)(rows_expr);                                                              \
-    for (int r = 0; r < rows; ++r)                                                                  \
-      if (((ri + r) & 3) == warp)                                                                   \
-        bulk_s2g(st.name + (size_t)r * S + e0, ss.name + (size_t)r * STEP_ENVS, STEP_ENVS * sizeof(type)); \
-    ri += rows;                                                                                     \
-  }
-    MFG_STATE_FIELDS(F)
-#undef F
+  if (el == 0) {
+    bulk_s2g(gblock, stage, bytes);
     asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");     // shared memory must outlive the copies
+    asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");     // shared memory must outlive the copy
   }
 }
 
@@ -151,18 +123,9 @@ cudaError_t launch_reset(MfgHandle* h, const uint8_t* d_mask, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-size_t step_stage_bytes(const MfgSpec& sp) {
-  size_t off = 0;
-#define F(type, name, rows_expr) \
-  if (!std::is_same<type, double>::value) off += (size_t)(rows_expr) * STEP_ENVS * sizeof(type);
-  MFG_STATE_FIELDS(F)
-#undef F
-  return off;
-}
-
 cudaError_t launch_step(MfgHandle* h, const StepIO& io, cudaStream_t s) {
   const unsigned blocks = (unsigned)((h->N + STEP_ENVS - 1) / STEP_ENVS);
-  const size_t smem = step_stage_bytes(h->sp);
+  const size_t smem = h->st.blk_i;
   cudaError_t err = cudaSuccess;
   dispatch_amax(h->sp.n_agents, [&](auto amax) {
     auto kern = k_step<decltype(amax)::value>;

@@ -13,7 +13,8 @@ from typing import Dict, Optional
 
 import numpy as np
 
-from .abi import (FIELD_DTYPES, FIELD_VIEW, N_STATS, RESPAWN_TAPE_W, STATE_FIELD_NAMES, MfgField, MfgTape, PackedSpec)
+from .abi import (ENV_BLOCK, FIELD_DTYPES, FIELD_VIEW, N_STATS, RESPAWN_TAPE_W, STATE_FIELD_NAMES, MfgField, MfgTape,
+                  PackedSpec)
 from .spec import EnvSpec
 from .state_io import columns_to_snapshot, snapshot_to_columns
 
@@ -99,15 +100,17 @@ class Engine:
             nbytes = self.lib.mfg_state_bytes(self.h)
             self.state = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
             self._check(self.lib.mfg_bind_state(self.h, self.state.data_ptr()))
-        self.fields: Dict[str, 'torch.Tensor'] = {}
+        self.fields: Dict[str, 'torch.Tensor'] = {}       # name -> strided VIEW [n_blocks, rows, 128] of the state buffer
         for name in STATE_FIELD_NAMES:
             f = MfgField()
             self._check(self.lib.mfg_state_field(self.h, name.encode(), C.byref(f)))
             if f.rows == 0:
                 continue
-            dt = FIELD_VIEW.get(name, FIELD_DTYPES[f.elem_size])
-            raw = self.state[f.offset:f.offset + f.rows * f.stride * f.elem_size]
-            self.fields[name] = raw.view(_torch_dtype(dt)).view(f.rows, f.stride)[:, :self.N]   # rows are padded to 128 envs
+            # blocked layout: element (row r, env e) = offset + (e // 128) * block_bytes + (r * 128 + e % 128) * elem_size
+            dt = _torch_dtype(FIELD_VIEW.get(name, FIELD_DTYPES[f.elem_size]))
+            n_blocks = (self.N + ENV_BLOCK - 1) // ENV_BLOCK
+            self.fields[name] = torch.as_strided(self.state.view(dt), (n_blocks, f.rows, ENV_BLOCK),
+                                                 (f.block_bytes // f.elem_size, ENV_BLOCK, 1), f.offset // f.elem_size)
         A = es.n_agents
         self.n_rew = A if es.individual_rewards else 1
         self.obs = torch.zeros((self.N, es.total_channels, es.obs_d, es.obs_d), dtype=torch.float32, device=self.device)
@@ -217,12 +220,17 @@ class Engine:
         for name, col in snapshot_to_columns(self.es, snap).items():
             src = col.view(np.int16) if col.dtype == np.uint16 else col.view(np.int32) if col.dtype == np.uint32 \
                 else col.view(np.int64) if col.dtype == np.uint64 else col
-            self.fields[name][:, env] = t.as_tensor(src).to(self.device)
+            self.fields[name][env // ENV_BLOCK, :, env % ENV_BLOCK] = t.as_tensor(src).to(self.device)
+
+    def field(self, name: str):
+        """Copy of one state field as a [rows, N] tensor (signed dtype of the field's width; same bit patterns)."""
+        v = self.fields[name]
+        return v.permute(1, 0, 2).reshape(v.shape[1], -1)[:, :self.N]
 
     def fields_numpy(self) -> Dict[str, np.ndarray]:
         out = {}
-        for name, dst in self.fields.items():
-            arr = dst.cpu().numpy()
+        for name in self.fields:
+            arr = self.field(name).cpu().numpy()
             np_dt = FIELD_VIEW.get(name)
             if np_dt is None:
                 np_dt = {1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[arr.dtype.itemsize]

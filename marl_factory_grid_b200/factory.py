@@ -113,7 +113,7 @@ class Factory:
         if self.unbatched:
             r = reward[0].cpu().numpy().astype(np.float64)
             rew = [float(x) for x in r] if self.spec.individual_rewards else float(r[0])
-            step = int(self.engine.fields['step'][0, 0].item()) & 0xFFFF
+            step = int(self.engine.fields['step'][0, 0, 0].item()) & 0xFFFF
             info = dict(step_reward=float(np.sum(r)), step=step)
             return None, [o[0].cpu().numpy() for o in per_agent], rew, bool(done[0].item()), info
         return None, per_agent, reward, done.bool(), {}

@@ -42,7 +42,11 @@ const char* hs_create(const MfgSpec* spec, int64_t n_envs, int64_t env_id_offset
   err = build_tables(*spec, h->ht);
   if (!err.empty()) { delete h; return err.c_str(); }
   h->N = n_envs;
-  h->bytes = compute_layout(h->sp, n_envs, h->fields);
+  {
+    Layout L = compute_layout(h->sp, n_envs);
+    h->fields = L.fields;
+    h->bytes = L.total;
+  }
   h->stats.assign(MFG_N_STATS, 0);
   h->tb.wall = h->ht.wall.data(); h->tb.door_map = h->ht.door_map.data(); h->tb.floor_pos = h->ht.floor_pos.data();
   h->tb.floor_index = h->ht.floor_index.data(); h->tb.wall_uid = h->ht.wall_uid.data(); h->tb.wall_pos = h->ht.wall_pos.data();
@@ -57,7 +61,7 @@ void hs_destroy(HsHandle* h) { delete h; }
 size_t hs_state_bytes(const HsHandle* h) { return h->bytes; }
 int hs_state_field(const HsHandle* h, const char* name, MfgField* out) {
   for (const auto& f : h->fields)
-    if (std::string(f.name) == name) { out->offset = f.offset; out->rows = f.rows; out->elem_size = f.elem_size; out->stride = env_stride(h->N); return 0; }
+    if (std::string(f.name) == name) { out->offset = f.offset; out->rows = f.rows; out->elem_size = f.elem_size; out->block_bytes = f.block_bytes; return 0; }
   return -1;
 }
 void hs_bind_state(HsHandle* h, void* base) { bind_state(h->sp, h->N, base, h->st); }
@@ -65,7 +69,7 @@ void hs_bind_state(HsHandle* h, void* base) { bind_state(h->sp, h->N, base, h->s
 void hs_reset(HsHandle* h, const uint8_t* mask) {
   dispatch(h->sp.n_agents, [&](auto amax) {
     for (int64_t e = 0; e < h->N; ++e)
-      if (!mask || mask[e]) env_reset<decltype(amax)::value>(h->sp, h->tb, h->st, e, mask ? h->st.episode[e] + 1 : 0);
+      if (!mask || mask[e]) env_reset<decltype(amax)::value>(h->sp, h->tb, h->st, e, mask ? field_at(h->st, h->st.episode, 0, e) + 1 : 0);
   });
 }
 void hs_step(HsHandle* h, const int32_t* actions, const uint8_t* maint_act, const int8_t* respawn_n,

@@ -9,8 +9,8 @@ from pathlib import Path
 
 import numpy as np
 
-from marl_factory_grid_b200.abi import (FIELD_DTYPES, FIELD_VIEW, N_STATS, RESPAWN_TAPE_W, STATE_FIELD_NAMES, MfgField,
-                                        PackedSpec, pos16)
+from marl_factory_grid_b200.abi import (ENV_BLOCK, FIELD_DTYPES, FIELD_VIEW, N_STATS, RESPAWN_TAPE_W, STATE_FIELD_NAMES,
+                                        MfgField, PackedSpec, pos16)
 from marl_factory_grid_b200.state_io import columns_to_snapshot, snapshot_to_columns
 
 HERE = Path(__file__).resolve().parent / 'hostsim'
@@ -60,14 +60,19 @@ class HostSim:
             raise RuntimeError(err.decode())
         self.buf = np.zeros(lib().hs_state_bytes(self.h), np.uint8)
         lib().hs_bind_state(self.h, self.buf.ctypes.data)
-        self.fields = {}
+        self._views = {}
         for name in STATE_FIELD_NAMES:
             f = MfgField()
             assert lib().hs_state_field(self.h, name.encode(), C.byref(f)) == 0, name
             if f.rows == 0:
                 continue
             dt = FIELD_VIEW.get(name, FIELD_DTYPES[f.elem_size])
-            self.fields[name] = self.buf[f.offset:f.offset + f.rows * f.stride * f.elem_size].view(dt).reshape(f.rows, f.stride)[:, :n_envs]
+            n_blocks = (n_envs + ENV_BLOCK - 1) // ENV_BLOCK
+            typed = self.buf[f.offset:].view(dt) if (len(self.buf) - f.offset) % f.elem_size == 0 else \
+                self.buf[f.offset:f.offset + (len(self.buf) - f.offset) // f.elem_size * f.elem_size].view(dt)
+            # blocked layout: strided VIEW [n_blocks, rows, 128]
+            self._views[name] = np.lib.stride_tricks.as_strided(
+                typed, shape=(n_blocks, f.rows, ENV_BLOCK), strides=(f.block_bytes, ENV_BLOCK * f.elem_size, f.elem_size))
         A = es.n_agents
         self.n_rew = A if es.individual_rewards else 1
         self.reward = np.zeros((n_envs, self.n_rew), np.float32)
@@ -79,12 +84,17 @@ class HostSim:
             lib().hs_destroy(self.h)
             self.h = None
 
+    @property
+    def fields(self):
+        """name -> [rows, N] COPY of the field (same convention as Engine.fields_numpy())."""
+        return {k: v.transpose(1, 0, 2).reshape(v.shape[1], -1)[:, :self.N].copy() for k, v in self._views.items()}
+
     def load_snapshot(self, env, snap):
         for name, colv in snapshot_to_columns(self.es, snap).items():
-            self.fields[name][:, env] = colv
+            self._views[name][env // ENV_BLOCK, :, env % ENV_BLOCK] = colv
 
     def snapshot(self, env):
-        return columns_to_snapshot(self.es, {k: v[:, env] for k, v in self.fields.items()})
+        return columns_to_snapshot(self.es, {k: v[env // ENV_BLOCK, :, env % ENV_BLOCK] for k, v in self._views.items()})
 
     def reset(self, mask=None):
         m = None if mask is None else np.ascontiguousarray(mask, np.uint8)

@@ -103,7 +103,7 @@ def test_freerun_matches_host_build_of_device_code(cfg, faithful):
         obs, rew, done = eng.step_observe(acts, auto_reset=True)
         r2, d2 = sim.step(a, auto_reset=True)
         f = eng.fields_numpy()
-        for name, arr in sim.fields.items():
+        for name, arr in sim.fields.items():          # both are [rows, N] copies
             if name == 'ep_ret':
                 np.testing.assert_allclose(f[name], arr, rtol=1e-12, atol=1e-12)
             else:
@@ -141,13 +141,13 @@ def test_tiled_observation_kernel_equals_direct_kernel_at_scale(cfg):
             eng.set_option('obs_cap', 3)                 # tiny sprite lists: most envs take the overflow path
             assert torch.equal(o1, eng.observe()), f'{cfg} t={t}: tiled (overflow path) != direct'
             eng.set_option('obs_cap', eng.info('obs_cap_max'))
-            apos = eng.fields['apos'].to(torch.int64) & 0xFFFF
+            apos = eng.field('apos').to(torch.int64) & 0xFFFF
             assert not walls[apos >> 8, apos & 255].any()
             if es.n_doors:
-                assert int(eng.fields['door_timer'].max()) <= 10
+                assert int(eng.field('door_timer').max()) <= 10
             if es.has_dirt:
-                live = (eng.fields['dirt_pos'].to(torch.int64) & 0xFFFF) != 0xFFFF
-                amt = eng.fields['dirt_amt'][live]
+                live = (eng.field('dirt_pos').to(torch.int64) & 0xFFFF) != 0xFFFF
+                amt = eng.field('dirt_amt')[live]
                 assert float(amt.min()) > 0 and float(amt.max()) <= 5.0
     eng.close()
 

@@ -33,7 +33,7 @@ def test_ctypes_spec_mirror_has_the_c_struct_size():
     """sizeof(MfgSpec) seen by ctypes == sizeof seen by the C++ compiler (checked through the host build)."""
     from hostsim_util import HostSim
     sim = HostSim(spec_for('cfg4'), 2)     # hs_create would read garbage (and fail validation) on a layout mismatch
-    assert sim.fields['apos'].shape == (4, 2)
+    assert sim.fields['apos'].shape == (4, 2) and sim._views['apos'].shape == (1, 4, 128)
 
 
 def test_engine_fails_loudly_without_cuda():
