@@ -156,6 +156,7 @@ def run_engine(args):
                  env_id_offset=rank * n_local)
     if args.obs_kernel:
         eng.set_option('obs_kernel', args.obs_kernel)
+    eng.set_option('obs_store', args.obs_store)
     acts = torch.zeros((n_local, A), dtype=torch.int32, device=dev)
     eng.reset()
 
@@ -296,6 +297,7 @@ def main():
     ap.add_argument('--envs-per-gpu', type=int, default=1 << 20)
     ap.add_argument('--parity', default='identity', choices=['identity', 'faithful'])
     ap.add_argument('--obs-kernel', type=int, default=0, help='0 auto, 1 direct, 2 tiled')
+    ap.add_argument('--obs-store', type=int, default=1, help='1 TMA bulk store of the tile, 0 LDS/STG loop')
     ap.add_argument('--e2e-steps', type=int, default=5)
     ap.add_argument('--cpu-steps', type=int, default=3000, help='env-steps per CPU worker for the baseline sample')
     ap.add_argument('--no-e2e', action='store_true')

@@ -42,19 +42,29 @@ enum { C_DOOR = 0, C_DIRT, C_ITEM, C_POD, C_DEST, C_DROP, C_MACH, C_MAINT, C_NON
 // ------------------------------------------------------------------------------------------------
 // state layout: every field is a [rows][N] array inside one caller-owned buffer
 // ------------------------------------------------------------------------------------------------
+// NOTE the order: the positional fields the observation kernel needs come FIRST and in its slot order (dirt piles,
+// items, pods, destinations, drop-offs, machines, maintainers, agents, then the door / destination bit masks), so that
+// they form one contiguous prefix of every block and can be staged with a single bulk copy.
 #define MFG_STATE_FIELDS(F)                                                        \
+  F(uint16_t, dirt_pos, sp.has_dirt ? sp.dirt_slots : 0)                           \
+  F(uint16_t, item_pos, sp.n_items)                                                \
+  F(uint16_t, pod_pos, sp.n_pods)                                                  \
+  F(uint16_t, dest_pos, sp.n_dest)                                                 \
+  F(uint16_t, drop_pos, sp.n_dropoff)                                              \
+  F(uint16_t, mach_pos, sp.n_machines)                                             \
+  F(uint16_t, maint_pos, sp.n_maint)                                               \
+  F(uint16_t, apos, sp.n_agents)                                                   \
+  F(uint64_t, door_open, sp.n_doors ? 1 : 0)                                       \
+  F(uint32_t, dest_reached, sp.n_dest ? 1 : 0)                                     \
   F(uint16_t, step, 1)                                                             \
   F(uint32_t, episode, 1)                                                          \
   F(uint32_t, clock, 1)                                                            \
-  F(uint16_t, apos, sp.n_agents)                                                   \
   F(uint32_t, astamp, sp.n_agents)                                                 \
   F(uint8_t, aflag, sp.n_agents)                                                   \
   F(double, bat, sp.has_batteries ? sp.n_agents : 0)                               \
   F(double, ep_ret, sp.n_agents)                                                   \
-  F(uint64_t, door_open, sp.n_doors ? 1 : 0)                                       \
   F(uint64_t, door_listed, sp.n_doors ? 1 : 0)                                     \
   F(uint8_t, door_timer, sp.n_doors)                                               \
-  F(uint16_t, dirt_pos, sp.has_dirt ? sp.dirt_slots : 0)                           \
   F(double, dirt_amt, sp.has_dirt ? sp.dirt_slots : 0)                             \
   F(uint16_t, dirt_uid, sp.has_dirt ? sp.dirt_slots : 0)                           \
   F(uint64_t, dirt_listed, sp.has_dirt ? 1 : 0)                                    \
@@ -62,19 +72,12 @@ enum { C_DOOR = 0, C_DIRT, C_ITEM, C_POD, C_DEST, C_DROP, C_MACH, C_MAINT, C_NON
   F(uint8_t, dirt_n, sp.has_dirt ? 1 : 0)                                          \
   F(uint16_t, dirt_next_uid, sp.has_dirt ? 1 : 0)                                  \
   F(int16_t, dirt_next_spawn, sp.has_dirt ? 1 : 0)                                 \
-  F(uint16_t, item_pos, sp.n_items)                                                \
-  F(uint16_t, pod_pos, sp.n_pods)                                                  \
-  F(uint16_t, dest_pos, sp.n_dest)                                                 \
-  F(uint16_t, drop_pos, sp.n_dropoff)                                              \
-  F(uint16_t, mach_pos, sp.n_machines)                                             \
-  F(uint16_t, maint_pos, sp.n_maint)                                               \
   F(uint32_t, item_listed, sp.n_items ? 1 : 0)                                     \
   F(uint32_t, pod_listed, sp.n_pods ? 1 : 0)                                       \
   F(uint32_t, dest_listed, sp.n_dest ? 1 : 0)                                      \
   F(uint32_t, drop_listed, sp.n_dropoff ? 1 : 0)                                   \
   F(uint32_t, mach_listed, sp.n_machines ? 1 : 0)                                  \
   F(uint32_t, maint_listed, sp.n_maint ? 1 : 0)                                    \
-  F(uint32_t, dest_reached, sp.n_dest ? 1 : 0)                                     \
   F(uint16_t, maint_target, sp.n_maint)                                            \
   F(uint16_t, maint_rand, sp.n_maint)                                              \
   F(uint32_t, maint_remaining, sp.n_maint)                                         \
@@ -88,6 +91,7 @@ struct State {
   int64_t N;       // live environments
   size_t blk_i;    // bytes per 128-env block of the integer region
   size_t blk_f;    // bytes per 128-env block of the f64 region
+  char* base_i;    // start of block 0 of the integer region
 #define F(type, name, rows) type* name;
   MFG_STATE_FIELDS(F)
 #undef F

@@ -62,6 +62,7 @@ inline void bind_state(const MfgSpec& sp, int64_t N, void* base, State& st) {
   st.N = N;
   st.blk_i = L.blk_i;
   st.blk_f = L.blk_f;
+  st.base_i = static_cast<char*>(base);
   size_t i = 0;
   char* b = static_cast<char*>(base);
 #define F(type, name, rows_expr) st.name = reinterpret_cast<type*>(b + L.fields[i++].offset);

@@ -22,7 +22,8 @@ struct WindowRays {
 
 // dynamic-position entity slots staged per env in shared memory by the observation kernel
 struct ObsSlots {
-  int dirt0, item0, pod0, dest0, drop0, mach0, maint0, agent0, total, stride;
+  int dirt0, item0, pod0, dest0, drop0, mach0, maint0, agent0, total;
+  int off_dopen, off_reached, prefix_bytes;    // layout of the staged block prefix (bytes)
 };
 
 constexpr int MAX_WALL_PLANES = 48;

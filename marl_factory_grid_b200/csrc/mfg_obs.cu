@@ -65,26 +65,22 @@ __device__ __forceinline__ unsigned long long march(const unsigned long long B) 
 enum { SK_INT = 0, SK_STORE = 1, SK_DOOR = 2, SK_DIRT = 3 };
 struct Sprite { uint32_t w; float val; };          // w = index | kind << 16 | aux << 24
 
-__device__ __forceinline__ uint16_t load_slot(const State& st, const ObsSlots& sl, int s, int64_t e) {
-  if (s < sl.item0) return field_at(st, st.dirt_pos, s - sl.dirt0, e);
-  if (s < sl.pod0) return field_at(st, st.item_pos, s - sl.item0, e);
-  if (s < sl.dest0) return field_at(st, st.pod_pos, s - sl.pod0, e);
-  if (s < sl.drop0) return field_at(st, st.dest_pos, s - sl.dest0, e);
-  if (s < sl.mach0) return field_at(st, st.drop_pos, s - sl.drop0, e);
-  if (s < sl.maint0) return field_at(st, st.mach_pos, s - sl.mach0, e);
-  if (s < sl.agent0) return field_at(st, st.maint_pos, s - sl.maint0, e);
-  return field_at(st, st.apos, s - sl.agent0, e);
-}
+// positions of one env inside the staged block prefix: slot-major slabs of 128 envs (see MFG_STATE_FIELDS order)
+struct BlkPos {
+  const uint16_t* base;
+  int eb;                                   // env index inside the 128-env block
+  __device__ __forceinline__ uint16_t operator[](int s) const { return base[s * ENV_BLOCK + eb]; }
+};
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bulk_store_tile(float* dst, const float* src_smem, uint32_t bytes) {
-  const uint32_t s = (uint32_t)__cvta_generic_to_shared(src_smem);
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst), "r"(s), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
   asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
 }
 
-// generic (slow) fill of one env's tile: lanes over entity slots, used when an agent's sprite list overflowed
+// generic (slow) fill of one env's tile: lanes over entity slots, used when the env's sprite list overflowed
 __device__ void slow_fill_env(const MfgSpec* __restrict__ sp, const Tables& tb, const State& st, const ObsSlots& sl,
-                              const uint16_t* pos, const unsigned long long* vis_a, unsigned long long dopen,
+                              const BlkPos pos, const unsigned long long* vis_a, unsigned long long dopen,
                               uint32_t reached, float* te, int64_t e, int lane) {
   const int A = sp->n_agents, r = sp->pomdp_r, D = 2 * r + 1, DD = D * D;
   auto add_int = [&](uint32_t m, int coff, int cell, float v) {
@@ -142,7 +138,7 @@ __device__ void slow_fill_env(const MfgSpec* __restrict__ sp, const Tables& tb, 
       if (q == NO_POS) continue;
       const int dx = px(q) - ax, dy = py(q) - ay;
       if (dx < 0 || dy < 0 || dx >= D || dy >= D) continue;
-      if ((vis_a[a] >> (dx * D + dy)) & 1) add_frac(m, sp->ch_offset[a], dx * D + dy, field_at(st, st.dirt_amt, (int)(k), e));
+      if ((vis_a[a] >> (dx * D + dy)) & 1) add_frac(m, sp->ch_offset[a], dx * D + dy, field_at(st, st.dirt_amt, k, e));
     }
   }
   __syncwarp();
@@ -160,245 +156,276 @@ __device__ void slow_fill_env(const MfgSpec* __restrict__ sp, const Tables& tb, 
   }
 }
 
+__device__ __forceinline__ void mbar_init1(unsigned long long* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(bar)) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait0(unsigned long long* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MFG_OWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+      "@p bra MFG_ODONE_%=;\n"
+      "bra MFG_OWAIT_%=;\n"
+      "MFG_ODONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// CTA = one 128-env state block, processed as four groups of 32 envs.
 template <int R, int GE, int NBUF, bool BULK>
 __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st, ObsSlots sl, WallPlanes wp,
                             float* __restrict__ obs, int total_channels, int cap) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long bar;
   constexpr int D = 2 * R + 1, DD = D * D;
   const int A = sp->n_agents;
   const int NW = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t env0 = (int64_t)blockIdx.x * OBS_ENVS;
+  const int64_t blk0 = (int64_t)blockIdx.x * ENV_BLOCK;
   const int tile_floats = GE * total_channels * DD;
 
   // shared memory carve-up (every region start stays 16-byte aligned)
-  float* tiles = reinterpret_cast<float*>(smem_raw);                                        // [NW][NBUF][tile_floats]
+  unsigned char* s_blk = smem_raw;                                                          // staged block prefix
+  float* tiles = reinterpret_cast<float*>(smem_raw + sl.prefix_bytes);                      // [NW][NBUF][tile_floats]
   unsigned long long* s_vis = reinterpret_cast<unsigned long long*>(tiles + (size_t)NW * NBUF * tile_floats);  // [32][A]
   unsigned long long* s_wv = s_vis + OBS_ENVS * A;                                          // [32][A]
-  unsigned long long* s_dopen = s_wv + OBS_ENVS * A;                                        // [32]
-  Sprite* s_spr = reinterpret_cast<Sprite*>(s_dopen + OBS_ENVS);                            // [32][cap]  one list per env
-  uint32_t* s_reached = reinterpret_cast<uint32_t*>(s_spr + (size_t)OBS_ENVS * cap);        // [32]
-  int* s_cnt = reinterpret_cast<int*>(s_reached + OBS_ENVS);                                // [32] sprites emitted per env
-  uint16_t* s_pos = reinterpret_cast<uint16_t*>(s_cnt + OBS_ENVS);                          // [32][stride]
+  Sprite* s_spr = reinterpret_cast<Sprite*>(s_wv + OBS_ENVS * A);                           // [32][cap]  one list per env
+  int* s_cnt = reinterpret_cast<int*>(s_spr + (size_t)OBS_ENVS * cap);                      // [32] sprites emitted per env
 
-  // ---------------- phase 1 ------------------------------------------------------------------------------------
-  {
-    const int64_t e = env0 + lane;
-    const bool live = e < st.N;
-    // stage the dynamic entity positions: warp w copies slots w, w+NW, ... (coalesced over the env lanes)
-    for (int s = warp; s < sl.total; s += NW) s_pos[lane * sl.stride + s] = live ? load_slot(st, sl, s, e) : NO_POS;
-    if (warp == 0) {
-      s_dopen[lane] = (live && sp->n_doors) ? field_at(st, st.door_open, 0, e) : 0ull;
-      s_reached[lane] = (live && sp->n_dest) ? field_at(st, st.dest_reached, 0, e) : 0u;
-      s_cnt[lane] = 0;
-    }
-    __syncthreads();
-    const uint16_t* pos = s_pos + lane * sl.stride;
-    const unsigned long long dopen = s_dopen[lane];
-    const uint32_t reached = s_reached[lane];
-    for (int a = warp; a < A; a += NW) {
-      unsigned long long vis = 0ull, wv = 0ull;
-      if (live) {
-        const uint16_t p = pos[sl.agent0 + a];
-        const int ax = px(p), ay = py(p);
-        const unsigned long long W49 = tb.wall_win[ax * sp->W + ay];
-        unsigned long long B = W49;
-        for (int d = 0; d < sp->n_doors; ++d) {
-          const uint16_t q = tb.door_pos[d];
-          const int dx = px(q) - ax + R, dy = py(q) - ay + R;
-          if (!((dopen >> d) & 1) && (unsigned)dx < (unsigned)D && (unsigned)dy < (unsigned)D) B |= 1ull << (dx * D + dy);
-        }
-        vis = march<R>(B);
-        wv = W49 & vis;
+  // ---- stage the positional prefix of this block: one TMA bulk copy (dirt/item/.../agent positions, door + dest masks)
+  if (threadIdx.x == 0) {
+    mbar_init1(&bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(&bar)), "r"((uint32_t)sl.prefix_bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(s_blk)),
+                 "l"(st.base_i + (size_t)blockIdx.x * st.blk_i), "r"((uint32_t)sl.prefix_bytes), "r"(smem_u32(&bar)) : "memory");
+  }
+  __syncthreads();
+  mbar_wait0(&bar);
+  const uint16_t* blk16 = reinterpret_cast<const uint16_t*>(s_blk);
+  const unsigned long long* blk_dopen = reinterpret_cast<const unsigned long long*>(s_blk + sl.off_dopen);
+  const uint32_t* blk_reached = reinterpret_cast<const uint32_t*>(s_blk + sl.off_reached);
 
-        const uint32_t* chm = sp->term_chmask[a];
-        const int coff = sp->ch_offset[a];
-        Sprite* spr = s_spr + (size_t)lane * cap;
-        int* cnt = s_cnt + lane;
-        auto put = [&](uint32_t w, float val) {      // the A agent-threads of an env append to one list
-          const int slot = atomicAdd(cnt, 1);
-          if (slot < cap) spr[slot] = Sprite{w, val};
-        };
-        auto emit = [&](uint32_t m, int cell, uint32_t kind, uint32_t aux, float val) {
-          while (m) {
-            const int c = __ffs(m) - 1;
-            m &= m - 1;
-            put((uint32_t)((coff + c) * DD + cell) | (kind << 16) | (aux << 24), val);
+  int buf = 0;
+  for (int grp = 0; grp < ENV_BLOCK / OBS_ENVS; ++grp) {
+    const int64_t env0 = blk0 + (int64_t)grp * OBS_ENVS;
+    if (env0 >= st.N) break;
+    if (warp == 0) s_cnt[lane] = 0;
+    __syncthreads();            // also fences the previous group's phase 2 against the reuse of s_spr / s_vis / s_wv
+
+    // ---------------- phase 1: one thread per (env = lane, agent = warp, warp + NW, ..) -------------------------
+    {
+      const int64_t e = env0 + lane;
+      const bool live = e < st.N;
+      const int eb = grp * OBS_ENVS + lane;
+      const BlkPos pos{blk16, eb};
+      const unsigned long long dopen = sp->n_doors ? blk_dopen[eb] : 0ull;
+      const uint32_t reached = sp->n_dest ? blk_reached[eb] : 0u;
+      for (int a = warp; a < A; a += NW) {
+        unsigned long long vis = 0ull, wv = 0ull;
+        if (live) {
+          const uint16_t p = pos[sl.agent0 + a];
+          const int ax = px(p), ay = py(p);
+          const unsigned long long W49 = tb.wall_win[ax * sp->W + ay];
+          unsigned long long B = W49;
+          for (int d = 0; d < sp->n_doors; ++d) {
+            const uint16_t q = tb.door_pos[d];
+            const int dx = px(q) - ax + R, dy = py(q) - ay + R;
+            if (!((dopen >> d) & 1) && (unsigned)dx < (unsigned)D && (unsigned)dy < (unsigned)D) B |= 1ull << (dx * D + dy);
           }
-        };
-        auto cell_of = [&](uint16_t q) -> int {        // window cell if inside the window and visible, else -1
-          const int dx = px(q) - ax + R, dy = py(q) - ay + R;
-          if ((unsigned)dx >= (unsigned)D || (unsigned)dy >= (unsigned)D) return -1;
-          const int cell = dx * D + dy;
-          return ((vis >> cell) & 1) ? cell : -1;
-        };
-        // agents (each agent plane is 1.0 at the agent's cell; stacks add up in Combined planes)
-        for (int j = 0; j < A; ++j) {
-          const uint32_t m = chm[MFG_G_AGENT0 + j];
-          if (!m) continue;
-          const int cell = cell_of(pos[sl.agent0 + j]);
-          if (cell >= 0) emit(m, cell, SK_INT, 0, 1.0f);
-        }
-        // small groups
-        {
-          const int lo[6] = {sl.item0, sl.pod0, sl.dest0, sl.drop0, sl.mach0, sl.maint0};
-          const int hi[6] = {sl.pod0, sl.dest0, sl.drop0, sl.mach0, sl.maint0, sl.agent0};
-          const int term[6] = {MFG_G_ITEMS, MFG_G_PODS, MFG_G_DEST, MFG_G_DROPOFF, MFG_G_MACHINES, MFG_G_MAINT};
-#pragma unroll
-          for (int g = 0; g < 6; ++g) {
-            const uint32_t m = chm[term[g]];
+          vis = march<R>(B);
+          wv = W49 & vis;
+
+          const uint32_t* chm = sp->term_chmask[a];
+          const int coff = sp->ch_offset[a];
+          Sprite* spr = s_spr + (size_t)lane * cap;
+          int* cnt = s_cnt + lane;
+          auto put = [&](uint32_t w, float val) {      // the A agent-threads of an env append to one list
+            const int slot = atomicAdd(cnt, 1);
+            if (slot < cap) spr[slot] = Sprite{w, val};
+          };
+          auto emit = [&](uint32_t m, int cell, uint32_t kind, uint32_t aux, float val) {
+            while (m) {
+              const int c = __ffs(m) - 1;
+              m &= m - 1;
+              put((uint32_t)((coff + c) * DD + cell) | (kind << 16) | (aux << 24), val);
+            }
+          };
+          auto cell_of = [&](uint16_t q) -> int {        // window cell if inside the window and visible, else -1
+            const int dx = px(q) - ax + R, dy = py(q) - ay + R;
+            if ((unsigned)dx >= (unsigned)D || (unsigned)dy >= (unsigned)D) return -1;
+            const int cell = dx * D + dy;
+            return ((vis >> cell) & 1) ? cell : -1;
+          };
+          // agents (each agent plane is 1.0 at the agent's cell; stacks add up in Combined planes)
+          for (int j = 0; j < A; ++j) {
+            const uint32_t m = chm[MFG_G_AGENT0 + j];
             if (!m) continue;
-            for (int s = lo[g]; s < hi[g]; ++s) {
-              const uint16_t q = pos[s];
+            const int cell = cell_of(pos[sl.agent0 + j]);
+            if (cell >= 0) emit(m, cell, SK_INT, 0, 1.0f);
+          }
+          // small groups
+          {
+            const int lo[6] = {sl.item0, sl.pod0, sl.dest0, sl.drop0, sl.mach0, sl.maint0};
+            const int hi[6] = {sl.pod0, sl.dest0, sl.drop0, sl.mach0, sl.maint0, sl.agent0};
+            const int term[6] = {MFG_G_ITEMS, MFG_G_PODS, MFG_G_DEST, MFG_G_DROPOFF, MFG_G_MACHINES, MFG_G_MAINT};
+#pragma unroll
+            for (int g = 0; g < 6; ++g) {
+              const uint32_t m = chm[term[g]];
+              if (!m) continue;
+              for (int s = lo[g]; s < hi[g]; ++s) {
+                const uint16_t q = pos[s];
+                if (q == NO_POS) continue;
+                if (g == 2 && ((reached >> (s - lo[g])) & 1)) continue;      // a reached destination encodes as 0
+                const int cell = cell_of(q);
+                if (cell >= 0) emit(m, cell, SK_INT, 0, g == 4 ? (float)ENC_MACHINE : 1.0f);
+              }
+            }
+          }
+          // doors
+          if (chm[MFG_G_DOORS]) {
+            for (int d = 0; d < sp->n_doors; ++d) {
+              const int cell = cell_of(tb.door_pos[d]);
+              if (cell >= 0) emit(chm[MFG_G_DOORS], cell, SK_DOOR, (uint32_t)((dopen >> d) & 1), 0.f);
+            }
+          }
+          // dirt piles
+          if (chm[MFG_G_DIRT]) {
+            for (int k = 0; k < sl.item0; ++k) {
+              const uint16_t q = pos[k];
               if (q == NO_POS) continue;
-              if (g == 2 && ((reached >> (s - lo[g])) & 1)) continue;      // a reached destination encodes as 0
               const int cell = cell_of(q);
-              if (cell >= 0) emit(m, cell, SK_INT, 0, g == 4 ? (float)ENC_MACHINE : 1.0f);
+              if (cell >= 0) emit(chm[MFG_G_DIRT], cell, SK_DIRT, (uint32_t)k, 0.f);
+            }
+          }
+          // scalar channels
+          const int C = sp->n_channels[a];
+          for (int c = 0; c < C; ++c) {
+            const int kind = sp->ch_kind[a][c];
+            if (kind == MFG_CH_BATTERY) {
+              put((uint32_t)((coff + c) * DD) | (SK_STORE << 16), (float)field_at(st, st.bat, a, e));
+            } else if (kind == MFG_CH_GLOBALPOS) {
+              put((uint32_t)((coff + c) * DD) | (SK_STORE << 16), (float)((double)ax / (double)sp->H));
+              put((uint32_t)((coff + c) * DD + 1) | (SK_STORE << 16), (float)((double)ay / (double)sp->W));
             }
           }
         }
-        // doors
-        if (chm[MFG_G_DOORS]) {
-          for (int d = 0; d < sp->n_doors; ++d) {
-            const int cell = cell_of(tb.door_pos[d]);
-            if (cell >= 0) emit(chm[MFG_G_DOORS], cell, SK_DOOR, (uint32_t)((dopen >> d) & 1), 0.f);
-          }
-        }
-        // dirt piles
-        if (chm[MFG_G_DIRT]) {
-          for (int k = 0; k < sl.item0; ++k) {
-            const uint16_t q = pos[k];
-            if (q == NO_POS) continue;
-            const int cell = cell_of(q);
-            if (cell >= 0) emit(chm[MFG_G_DIRT], cell, SK_DIRT, (uint32_t)k, 0.f);
-          }
-        }
-        // scalar channels
-        const int C = sp->n_channels[a];
-        for (int c = 0; c < C; ++c) {
-          const int kind = sp->ch_kind[a][c];
-          if (kind == MFG_CH_BATTERY) {
-            put((uint32_t)((coff + c) * DD) | (SK_STORE << 16), (float)field_at(st, st.bat, a, e));
-          } else if (kind == MFG_CH_GLOBALPOS) {
-            put((uint32_t)((coff + c) * DD) | (SK_STORE << 16), (float)((double)ax / (double)sp->H));
-            put((uint32_t)((coff + c) * DD + 1) | (SK_STORE << 16), (float)((double)ay / (double)sp->W));
-          }
-        }
+        s_vis[lane * A + a] = vis;
+        s_wv[lane * A + a] = wv;
       }
-      s_vis[lane * A + a] = vis;
-      s_wv[lane * A + a] = wv;
     }
-  }
-  __syncthreads();
+    __syncthreads();
 
-  // ---------------- phase 2: one warp per group of GE envs -----------------------------------------------------
-  const int n_groups = OBS_ENVS / GE;
-  int buf = 0;
-  for (int g = warp; g < n_groups; g += NW) {
-    const int64_t eg = env0 + (int64_t)g * GE;
-    if (eg >= st.N) break;
-    float* tile = tiles + ((size_t)warp * NBUF + buf) * tile_floats;
-    if (BULK) {
-      // the bulk store that last read this buffer must have finished reading shared memory
-      if (lane == 0) {
-        if (NBUF == 1) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
-        else asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
+    // ---------------- phase 2: one warp per tile of GE envs ------------------------------------------------------
+    const int n_tiles = OBS_ENVS / GE;
+    for (int g = warp; g < n_tiles; g += NW) {
+      const int64_t eg = env0 + (int64_t)g * GE;
+      if (eg >= st.N) break;
+      float* tile = tiles + ((size_t)warp * NBUF + buf) * tile_floats;
+      if (BULK) {
+        // the bulk store that last read this buffer must have finished reading shared memory
+        if (lane == 0) {
+          if (NBUF == 1) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
+        }
+        __syncwarp();
+      }
+      {
+        float4* t4 = reinterpret_cast<float4*>(tile);
+        const int n4 = tile_floats >> 2;
+        for (int i = lane; i < n4; i += 32) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       __syncwarp();
-    }
-    {
-      float4* t4 = reinterpret_cast<float4*>(tile);
-      const int n4 = tile_floats >> 2;
-      for (int i = lane; i < n4; i += 32) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    __syncwarp();
-    // Each lane keeps (up to) two sprites of the env in registers across the three passes; a third round (more than
-    // 64 sprites) only exists on the overflow path.  Dirt amounts (f64, uncoalesced) are requested as soon as the sprite
-    // is decoded so that their latency overlaps the integer pass.
-    for (int ge = 0; ge < GE; ++ge) {
-      const int el = g * GE + ge;
-      const int64_t e = env0 + el;
-      if (e >= st.N) break;
-      float* te = tile + (size_t)ge * total_channels * DD;
-      const int cnt = s_cnt[el];
-      if (cnt > cap) {                      // sprite list overflowed: generic lanes-over-slots fill of the whole env
-        slow_fill_env(sp, tb, st, sl, s_pos + el * sl.stride, s_vis + el * A, s_dopen[el], s_reached[el], te, e, lane);
-        continue;
-      }
-      Sprite s0{0u, 0.f}, s1{0u, 0.f};
-      uint32_t k0 = 0xFF, k1 = 0xFF;
-      double d0 = 0.0, d1 = 0.0;
-      if (lane < cnt) {
-        s0 = s_spr[(size_t)el * cap + lane];
-        k0 = (s0.w >> 16) & 0xFF;
-        if (k0 == SK_DIRT) d0 = field_at(st, st.dirt_amt, (int)((s0.w >> 24)), e);
-      }
-      if (lane + 32 < cnt) {
-        s1 = s_spr[(size_t)el * cap + lane + 32];
-        k1 = (s1.w >> 16) & 0xFF;
-        if (k1 == SK_DIRT) d1 = field_at(st, st.dirt_amt, (int)((s1.w >> 24)), e);
-      }
-      // wall planes: 1.0 where a visible wall is.  Nothing else can be on a wall cell, so the (predicated) store has a
-      // unique writer and needs no ordering against the sprite adds below.
-      for (int w = 0; w < wp.n; ++w) {
-        const uint32_t* wv32 = reinterpret_cast<const uint32_t*>(s_wv + el * A + wp.agent[w]);
-        float* plane = te + (int)wp.plane[w] * DD;
-        if ((wv32[0] >> lane) & 1u) plane[lane] = 1.0f;
-        if (lane + 32 < DD && ((wv32[1] >> lane) & 1u)) plane[lane + 32] = 1.0f;
-      }
-      // pass A: integer-valued sprites (stacks add up exactly) and direct stores
-      if (k0 == SK_INT) atomicAdd(&te[s0.w & 0xFFFF], s0.val);
-      else if (k0 == SK_STORE) te[s0.w & 0xFFFF] = s0.val;
-      if (k1 == SK_INT) atomicAdd(&te[s1.w & 0xFFFF], s1.val);
-      else if (k1 == SK_STORE) te[s1.w & 0xFFFF] = s1.val;
-      for (int i = lane + 64; i < cnt; i += 32) {          // only reachable with a raised sprite capacity
-        const Sprite s = s_spr[(size_t)el * cap + i];
-        const uint32_t kind = (s.w >> 16) & 0xFF;
-        if (kind == SK_INT) atomicAdd(&te[s.w & 0xFFFF], s.val);
-        else if (kind == SK_STORE) te[s.w & 0xFFFF] = s.val;
-      }
-      // fractional encodings last: value = (float)((double)integer_stack + encoding), one rounding like the reference
-      const bool door_here = k0 == SK_DOOR || k1 == SK_DOOR || cnt > 64;
-      const bool dirt_here = k0 == SK_DIRT || k1 == SK_DIRT || cnt > 64;
-      if (__any_sync(0xffffffffu, door_here)) {
-        __syncwarp();
-        if (k0 == SK_DOOR) { float* f = &te[s0.w & 0xFFFF]; *f = (float)((double)*f + ((s0.w >> 24) ? ENC_DOOR_OPEN : ENC_DOOR_CLOSED)); }
-        if (k1 == SK_DOOR) { float* f = &te[s1.w & 0xFFFF]; *f = (float)((double)*f + ((s1.w >> 24) ? ENC_DOOR_OPEN : ENC_DOOR_CLOSED)); }
+      // Each lane keeps (up to) two sprites of the env in registers across the three passes; further rounds only exist
+      // with a raised sprite capacity.  Dirt amounts (f64, uncoalesced) are requested as soon as the sprite is decoded
+      // so that their latency overlaps the integer pass.
+      for (int ge = 0; ge < GE; ++ge) {
+        const int el = g * GE + ge;
+        const int64_t e = env0 + el;
+        if (e >= st.N) break;
+        float* te = tile + (size_t)ge * total_channels * DD;
+        const int cnt = s_cnt[el];
+        if (cnt > cap) {                      // sprite list overflowed: generic lanes-over-slots fill of the whole env
+          const int eb = grp * OBS_ENVS + el;
+          slow_fill_env(sp, tb, st, sl, BlkPos{blk16, eb}, s_vis + el * A, sp->n_doors ? blk_dopen[eb] : 0ull,
+                        sp->n_dest ? blk_reached[eb] : 0u, te, e, lane);
+          continue;
+        }
+        Sprite s0{0u, 0.f}, s1{0u, 0.f};
+        uint32_t k0 = 0xFF, k1 = 0xFF;
+        double d0 = 0.0, d1 = 0.0;
+        if (lane < cnt) {
+          s0 = s_spr[(size_t)el * cap + lane];
+          k0 = (s0.w >> 16) & 0xFF;
+          if (k0 == SK_DIRT) d0 = field_at(st, st.dirt_amt, (int)(s0.w >> 24), e);
+        }
+        if (lane + 32 < cnt) {
+          s1 = s_spr[(size_t)el * cap + lane + 32];
+          k1 = (s1.w >> 16) & 0xFF;
+          if (k1 == SK_DIRT) d1 = field_at(st, st.dirt_amt, (int)(s1.w >> 24), e);
+        }
+        // wall planes: 1.0 where a visible wall is.  Nothing else can be on a wall cell, so the (predicated) store has
+        // a unique writer and needs no ordering against the sprite adds below.
+        for (int w = 0; w < wp.n; ++w) {
+          const uint32_t* wv32 = reinterpret_cast<const uint32_t*>(s_wv + el * A + wp.agent[w]);
+          float* plane = te + (int)wp.plane[w] * DD;
+          if ((wv32[0] >> lane) & 1u) plane[lane] = 1.0f;
+          if (lane + 32 < DD && ((wv32[1] >> lane) & 1u)) plane[lane + 32] = 1.0f;
+        }
+        // pass A: integer-valued sprites (stacks add up exactly) and direct stores
+        if (k0 == SK_INT) atomicAdd(&te[s0.w & 0xFFFF], s0.val);
+        else if (k0 == SK_STORE) te[s0.w & 0xFFFF] = s0.val;
+        if (k1 == SK_INT) atomicAdd(&te[s1.w & 0xFFFF], s1.val);
+        else if (k1 == SK_STORE) te[s1.w & 0xFFFF] = s1.val;
         for (int i = lane + 64; i < cnt; i += 32) {
           const Sprite s = s_spr[(size_t)el * cap + i];
-          if (((s.w >> 16) & 0xFF) == SK_DOOR) { float* f = &te[s.w & 0xFFFF]; *f = (float)((double)*f + ((s.w >> 24) ? ENC_DOOR_OPEN : ENC_DOOR_CLOSED)); }
+          const uint32_t kind = (s.w >> 16) & 0xFF;
+          if (kind == SK_INT) atomicAdd(&te[s.w & 0xFFFF], s.val);
+          else if (kind == SK_STORE) te[s.w & 0xFFFF] = s.val;
+        }
+        // fractional encodings last: value = (float)((double)integer_stack + encoding), one rounding like the reference
+        const bool door_here = k0 == SK_DOOR || k1 == SK_DOOR || cnt > 64;
+        const bool dirt_here = k0 == SK_DIRT || k1 == SK_DIRT || cnt > 64;
+        if (__any_sync(0xffffffffu, door_here)) {
+          __syncwarp();
+          if (k0 == SK_DOOR) { float* f = &te[s0.w & 0xFFFF]; *f = (float)((double)*f + ((s0.w >> 24) ? ENC_DOOR_OPEN : ENC_DOOR_CLOSED)); }
+          if (k1 == SK_DOOR) { float* f = &te[s1.w & 0xFFFF]; *f = (float)((double)*f + ((s1.w >> 24) ? ENC_DOOR_OPEN : ENC_DOOR_CLOSED)); }
+          for (int i = lane + 64; i < cnt; i += 32) {
+            const Sprite s = s_spr[(size_t)el * cap + i];
+            if (((s.w >> 16) & 0xFF) == SK_DOOR) { float* f = &te[s.w & 0xFFFF]; *f = (float)((double)*f + ((s.w >> 24) ? ENC_DOOR_OPEN : ENC_DOOR_CLOSED)); }
+          }
+        }
+        if (__any_sync(0xffffffffu, dirt_here)) {
+          __syncwarp();
+          if (k0 == SK_DIRT) { float* f = &te[s0.w & 0xFFFF]; *f = (float)((double)*f + d0); }
+          if (k1 == SK_DIRT) { float* f = &te[s1.w & 0xFFFF]; *f = (float)((double)*f + d1); }
+          for (int i = lane + 64; i < cnt; i += 32) {
+            const Sprite s = s_spr[(size_t)el * cap + i];
+            if (((s.w >> 16) & 0xFF) == SK_DIRT) { float* f = &te[s.w & 0xFFFF]; *f = (float)((double)*f + field_at(st, st.dirt_amt, (int)(s.w >> 24), e)); }
+          }
         }
       }
-      if (__any_sync(0xffffffffu, dirt_here)) {
+      // ---- stream the tile out
+      const int ne = (int)((st.N - eg) < GE ? (st.N - eg) : GE);
+      float* dst = obs + (size_t)eg * total_channels * DD;
+      if (BULK && ne == GE) {
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> visible to the async proxy
         __syncwarp();
-        if (k0 == SK_DIRT) { float* f = &te[s0.w & 0xFFFF]; *f = (float)((double)*f + d0); }
-        if (k1 == SK_DIRT) { float* f = &te[s1.w & 0xFFFF]; *f = (float)((double)*f + d1); }
-        for (int i = lane + 64; i < cnt; i += 32) {
-          const Sprite s = s_spr[(size_t)el * cap + i];
-          if (((s.w >> 16) & 0xFF) == SK_DIRT) { float* f = &te[s.w & 0xFFFF]; *f = (float)((double)*f + field_at(st, st.dirt_amt, (int)((s.w >> 24)), e)); }
-        }
-      }
-    }
-    // ---- stream the tile out
-    const int ne = (int)((st.N - eg) < GE ? (st.N - eg) : GE);
-    float* dst = obs + (size_t)eg * total_channels * DD;
-    if (BULK && ne == GE) {
-      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> visible to the async proxy
-      __syncwarp();
-      if (lane == 0) bulk_store_tile(dst, tile, (uint32_t)(tile_floats * sizeof(float)));
-      buf = (buf + 1) % NBUF;
-    } else {
-      __syncwarp();
-      const int nfl = ne * total_channels * DD;
-      if (ne == GE) {
-        const float4* t4 = reinterpret_cast<const float4*>(tile);
-        float4* d4 = reinterpret_cast<float4*>(dst);
-        const int n4 = nfl >> 2;
-        for (int i = lane; i < n4; i += 32) __stcs(&d4[i], t4[i]);
+        if (lane == 0) bulk_store_tile(dst, tile, (uint32_t)(tile_floats * sizeof(float)));
+        buf = (buf + 1) % NBUF;
       } else {
-        for (int i = lane; i < nfl; i += 32) dst[i] = tile[i];
+        __syncwarp();
+        const int nfl = ne * total_channels * DD;
+        if (ne == GE) {
+          const float4* t4 = reinterpret_cast<const float4*>(tile);
+          float4* d4 = reinterpret_cast<float4*>(dst);
+          const int n4 = nfl >> 2;
+          for (int i = lane; i < n4; i += 32) __stcs(&d4[i], t4[i]);
+        } else {
+          for (int i = lane; i < nfl; i += 32) dst[i] = tile[i];
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   }
   if (BULK && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // smem must outlive the copies
@@ -486,19 +513,28 @@ void plan_obs(MfgHandle* h) {
   sl.maint0 = sl.mach0 + sp.n_machines;
   sl.agent0 = sl.maint0 + sp.n_maint;
   sl.total = sl.agent0 + sp.n_agents;
-  sl.stride = sl.total + (sl.total & 1);                 // in uint16; make the 32-bit word stride odd => conflict-free
-  if (((sl.stride / 2) & 1) == 0) sl.stride += 2;
+  // the slots are exactly the first rows of every state block (MFG_STATE_FIELDS order), followed by the two bit masks
+  sl.off_dopen = sl.total * ENV_BLOCK * (int)sizeof(uint16_t);
+  sl.off_reached = sl.off_dopen + (sp.n_doors ? ENV_BLOCK * 8 : 0);
+  sl.prefix_bytes = sl.off_reached + (sp.n_dest ? ENV_BLOCK * 4 : 0);
+  {
+    Layout L = compute_layout(sp, h->N);
+    auto off_of = [&](const char* name) { for (auto& f : L.fields) if (!strcmp(f.name, name)) return (long long)f.offset; return -1ll; };
+    bool order_ok = off_of("dirt_pos") == 0 && off_of("apos") == (long long)sl.agent0 * ENV_BLOCK * 2 &&
+                    (!sp.n_doors || off_of("door_open") == sl.off_dopen) && (!sp.n_dest || off_of("dest_reached") == sl.off_reached);
+    if (!order_ok) { p.ok = false; return; }
+  }
   const int tcdd = h->total_channels * h->DD;
   p.ge = (tcdd % 4 == 0) ? 1 : (tcdd % 2 == 0) ? 2 : 4;
   p.nw = sp.n_agents < 2 ? 2 : (sp.n_agents > 8 ? 8 : sp.n_agents);
-  p.cap = 12 * sp.n_agents < 16 ? 16 : 12 * sp.n_agents;      // sprite slots per env
+  p.cap = 8 * sp.n_agents < 16 ? 16 : 8 * sp.n_agents;        // sprite slots per env (overflow => generic slow path)
   p.cap_max = p.cap;
   auto smem_for = [&](int nbuf) {
     size_t b = (size_t)p.nw * nbuf * p.ge * tcdd * sizeof(float);
-    b += (size_t)OBS_ENVS * sp.n_agents * 8 * 2 + OBS_ENVS * 8;            // vis, wv, dopen
+    b += (size_t)OBS_ENVS * sp.n_agents * 8 * 2;                           // vis, wv
     b += (size_t)OBS_ENVS * p.cap * 8;                                     // sprites (one list per env)
-    b += OBS_ENVS * 4 * 2;                                                 // reached, cnt
-    b += (size_t)OBS_ENVS * sl.stride * 2 + 32;
+    b += OBS_ENVS * 4;                                                     // cnt
+    b += (size_t)sl.prefix_bytes + 32;                                     // staged block prefix
     return b;
   };
   p.nbuf = smem_for(2) <= 56 * 1024 ? 2 : 1;
@@ -529,7 +565,7 @@ static cudaError_t launch_tiled_t(MfgHandle* h, float* d_obs, cudaStream_t s) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return e;
   }
-  const unsigned blocks = (unsigned)((h->N + OBS_ENVS - 1) / OBS_ENVS);
+  const unsigned blocks = (unsigned)((h->N + ENV_BLOCK - 1) / ENV_BLOCK);
   kern<<<blocks, p.nw * 32, p.smem, s>>>(h->d_sp, h->tb, h->st, p.slots, p.walls, d_obs, h->total_channels, p.cap);
   return cudaGetLastError();
 }

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(STEP_ENVS) k_step(const MfgSpec* __restrict__ 
   const MfgSpec& sp = *spp;
   const int el = threadIdx.x;
   const int64_t e0 = (int64_t)blockIdx.x * STEP_ENVS, eg = e0 + el;
-  char* gblock = reinterpret_cast<char*>(st.step) + (size_t)blockIdx.x * st.blk_i;     // `step` is the first field
+  char* gblock = st.base_i + (size_t)blockIdx.x * st.blk_i;
   const uint32_t bytes = (uint32_t)st.blk_i;
 
   if (el == 0) {
@@ -72,8 +72,9 @@ __global__ void __launch_bounds__(STEP_ENVS) k_step(const MfgSpec* __restrict__ 
   // staged view of the state: same field offsets, block 0 == the shared-memory copy
   State ss = st;
   ss.N = STEP_ENVS;
+  ss.base_i = reinterpret_cast<char*>(stage);
   {
-    const char* g0 = reinterpret_cast<const char*>(st.step);
+    const char* g0 = st.base_i;
 #define F(type, name, rows_expr) \
   if constexpr (!std::is_same<type, double>::value) ss.name = reinterpret_cast<type*>(stage + (reinterpret_cast<const char*>(st.name) - g0));
     MFG_STATE_FIELDS(F)
