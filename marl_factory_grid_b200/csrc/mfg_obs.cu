@@ -206,12 +206,13 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
   const unsigned long long* blk_dopen = reinterpret_cast<const unsigned long long*>(s_blk + sl.off_dopen);
   const uint32_t* blk_reached = reinterpret_cast<const uint32_t*>(s_blk + sl.off_reached);
 
+  if (warp == 0) s_cnt[lane] = 0;
   int buf = 0;
   for (int grp = 0; grp < ENV_BLOCK / OBS_ENVS; ++grp) {
     const int64_t env0 = blk0 + (int64_t)grp * OBS_ENVS;
     if (env0 >= st.N) break;
-    if (warp == 0) s_cnt[lane] = 0;
-    __syncthreads();            // also fences the previous group's phase 2 against the reuse of s_spr / s_vis / s_wv
+    // s_cnt is zero here: initialised before the loop, and re-zeroed by the phase-2 warp that consumed each list
+    __syncthreads();            // fences the previous group's phase 2 against the reuse of s_spr / s_vis / s_wv / s_cnt
 
     // ---------------- phase 1: one thread per (env = lane, agent = warp, warp + NW, ..) -------------------------
     {
@@ -345,6 +346,8 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
         if (e >= st.N) break;
         float* te = tile + (size_t)ge * total_channels * DD;
         const int cnt = s_cnt[el];
+        __syncwarp();
+        if (lane == 0) s_cnt[el] = 0;         // every lane holds `cnt`; the list counter is ready for the next group
         if (cnt > cap) {                      // sprite list overflowed: generic lanes-over-slots fill of the whole env
           const int eb = grp * OBS_ENVS + el;
           slow_fill_env(sp, tb, st, sl, BlkPos{blk16, eb}, s_vis + el * A, sp->n_doors ? blk_dopen[eb] : 0ull,
