@@ -198,12 +198,10 @@ def run_engine(args):
     launches = eng.info('launches') - launches0
 
     # episode statistics: the only cross-GPU exchange of the path (one small all-reduce over NVLink)
-    stats = torch.as_tensor(eng.stats()[:11].copy(), device=dev)
-    t_el = torch.tensor([elapsed_ms, obs_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
-        dist.all_reduce(t_el, op=dist.ReduceOp.MAX)
-    elapsed_ms, obs_ms = float(t_el[0]), float(t_el[1])
+    from marl_factory_grid_b200.distributed import allreduce_max, allreduce_stats
+    stats = allreduce_stats(eng.stats(), device=dev)
+    elapsed_ms, obs_ms = allreduce_max(elapsed_ms, dev), allreduce_max(obs_ms, dev)
+    step_ms, rand_ms = allreduce_max(step_ms, dev), allreduce_max(rand_ms, dev)
 
     # ---- e2e: host buffers through the C-ABI host entry point (H2D actions, D2H reward + done + obs inside the timed region)
     e2e = None
