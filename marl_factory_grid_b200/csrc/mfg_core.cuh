@@ -171,9 +171,55 @@ struct Philox {
 // ------------------------------------------------------------------------------------------------
 // per-environment context: hot fields live in registers, the rest is touched in the SoA buffers
 // ------------------------------------------------------------------------------------------------
+// Compact copy of the spec fields the step path reads, small enough to be passed BY VALUE as a kernel parameter
+// (constant bank: uniform reads are broadcast, no L1/L2 round trip).  Member names equal MfgSpec's so that the same
+// templated code runs against either.
 template <int AMAX>
+struct HotSpec {
+  int32_t H, W, pomdp_r, n_agents, individual_rewards, faithful, n_floor, n_doors, n_walls, has_dirt, dirt_slots,
+      dirt_quantity, has_batteries, has_globalpos, n_items, n_dropoff, n_pods, n_dest, n_machines, n_maint, n_rules, n_groups;
+  double dirt_initial_amount, dirt_clean_amount, dirt_max_global, dirt_n_var, dirt_amount_var, battery_initial;
+  uint64_t seed;
+  int32_t n_actions[AMAX];
+  int32_t agent_blocking[AMAX];
+  int8_t act_opcode[AMAX][MFG_MAX_ACTIONS];
+  int8_t act_dir[AMAX][MFG_MAX_ACTIONS];
+  double act_valid[AMAX][MFG_MAX_ACTIONS];
+  double act_fail[AMAX][MFG_MAX_ACTIONS];
+  double act_aux[AMAX][MFG_MAX_ACTIONS];
+  int32_t rule_op[MFG_MAX_RULES];
+  double rule_param[MFG_MAX_RULES][MFG_RULE_NPARAM];
+};
+
+template <int AMAX>
+inline void fill_hot_spec(const MfgSpec& s, HotSpec<AMAX>& h) {
+#define CP(x) h.x = s.x;
+  CP(H) CP(W) CP(pomdp_r) CP(n_agents) CP(individual_rewards) CP(faithful) CP(n_floor) CP(n_doors) CP(n_walls) CP(has_dirt)
+  CP(dirt_slots) CP(dirt_quantity) CP(has_batteries) CP(has_globalpos) CP(n_items) CP(n_dropoff) CP(n_pods) CP(n_dest)
+  CP(n_machines) CP(n_maint) CP(n_rules) CP(n_groups) CP(dirt_initial_amount) CP(dirt_clean_amount) CP(dirt_max_global)
+  CP(dirt_n_var) CP(dirt_amount_var) CP(battery_initial) CP(seed)
+#undef CP
+  for (int i = 0; i < AMAX; ++i) {
+    const bool in = i < s.n_agents && i < MFG_MAX_AGENTS;
+    h.n_actions[i] = in ? s.n_actions[i] : 0;
+    h.agent_blocking[i] = in ? s.agent_blocking[i] : 0;
+    for (int a = 0; a < MFG_MAX_ACTIONS; ++a) {
+      h.act_opcode[i][a] = in ? (int8_t)s.act_opcode[i][a] : 0;
+      h.act_dir[i][a] = in ? (int8_t)s.act_dir[i][a] : 0;
+      h.act_valid[i][a] = in ? s.act_valid[i][a] : 0.0;
+      h.act_fail[i][a] = in ? s.act_fail[i][a] : 0.0;
+      h.act_aux[i][a] = in ? s.act_aux[i][a] : 0.0;
+    }
+  }
+  for (int r = 0; r < MFG_MAX_RULES; ++r) {
+    h.rule_op[r] = s.rule_op[r];
+    for (int k = 0; k < MFG_RULE_NPARAM; ++k) h.rule_param[r][k] = s.rule_param[r][k];
+  }
+}
+
+template <int AMAX, typename SpecT = MfgSpec>
 struct Env {
-  const MfgSpec& sp;
+  const SpecT& sp;
   const Tables& tb;
   const State& st;
   int64_t e;        // env index inside `st`'s integer region (== eg unless that region was staged into a per-CTA copy)
@@ -183,7 +229,7 @@ struct Env {
   uint64_t dopen, dlisted, dirt_listed;
   int dirt_end, dirt_n;
 
-  MFG_HD Env(const MfgSpec& sp_, const Tables& tb_, const State& st_, int64_t e_, int64_t eg_ = -1)
+  MFG_HD Env(const SpecT& sp_, const Tables& tb_, const State& st_, int64_t e_, int64_t eg_ = -1)
       : sp(sp_), tb(tb_), st(st_), e(e_), eg(eg_ < 0 ? e_ : eg_) {
     A = sp.n_agents;
     dopen = dlisted = dirt_listed = 0;
@@ -518,9 +564,9 @@ struct StepIO {
 };
 
 // maintainer policy when no tape is given (maintenance/entities.py:37-136), next hop from the BFS table
-template <int AMAX>
-MFG_HD int maint_policy(Env<AMAX>& v, int k, uint32_t step) {
-  const MfgSpec& sp = v.sp; const State& st = v.st; const Tables& tb = v.tb;
+template <int AMAX, typename SpecT>
+MFG_HD int maint_policy(Env<AMAX, SpecT>& v, int k, uint32_t step) {
+  const SpecT& sp = v.sp; const State& st = v.st; const Tables& tb = v.tb;
   uint16_t p = v.at(st.maint_pos, k);
   int here = -1;
   for (int m = 0; m < sp.n_machines && here < 0; ++m) if (v.at(st.mach_pos, m) == p) here = m;
@@ -557,10 +603,11 @@ MFG_HD int maint_policy(Env<AMAX>& v, int k, uint32_t step) {
   return d;
 }
 
-template <int AMAX>
-MFG_HDN void env_step(const MfgSpec& sp, const Tables& tb, const State& st, int64_t e_local, const StepIO& io,
-                      int64_t eg = -1) {
-  Env<AMAX> v(sp, tb, st, e_local, eg);
+// `sp` may be the full MfgSpec or its compact HotSpec copy; `full` (the MfgSpec) is only read by the in-kernel reset
+template <int AMAX, typename SpecT>
+MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, const State& st, int64_t e_local,
+                      const StepIO& io, int64_t eg = -1) {
+  Env<AMAX, SpecT> v(sp, tb, st, e_local, eg);
   const int64_t e = v.eg;            // index into the caller's actions / tape / reward / done buffers
   v.load();
   const int A = v.A;
@@ -670,7 +717,7 @@ MFG_HDN void env_step(const MfgSpec& sp, const Tables& tb, const State& st, int6
       }
     } else if (op == MFG_R_MOVE_MAINTAINERS) {
       for (int k = 0; k < sp.n_maint; ++k) {
-        int code = io.maint_act ? (int)io.maint_act[(size_t)e * sp.n_maint + k] : maint_policy<AMAX>(v, k, (uint32_t)step);
+        int code = io.maint_act ? (int)io.maint_act[(size_t)e * sp.n_maint + k] : maint_policy<AMAX, SpecT>(v, k, (uint32_t)step);
         uint16_t p = v.at(st.maint_pos, k);
         if (code < 8) {
           uint16_t t;
@@ -869,7 +916,7 @@ MFG_HDN void env_step(const MfgSpec& sp, const Tables& tb, const State& st, int6
     const int nr = sp.individual_rewards ? A : 1;
     for (int i = 0; i < nr; ++i) { double x = v.at(st.ep_ret, i); tot += x; stat_add_f64(tb, MFG_ST_RETURN_AGENT0 + i, x); }
     stat_add_f64(tb, MFG_ST_RETURN_SUM, tot);
-    if (io.auto_reset) env_reset<AMAX>(sp, tb, st, v.e, v.at(st.episode, 0) + 1, v.eg);
+    if (io.auto_reset) env_reset<AMAX>(full, tb, st, v.e, v.at(st.episode, 0) + 1, v.eg);
   }
 }
 

@@ -54,10 +54,10 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, uint32
 }
 
 template <int AMAX>
-__global__ void __launch_bounds__(STEP_ENVS) k_step(const MfgSpec* __restrict__ spp, Tables tb, State st, StepIO io) {
+__global__ void __launch_bounds__(STEP_ENVS) k_step(const __grid_constant__ HotSpec<AMAX> hs, const MfgSpec* __restrict__ full,
+                                                    Tables tb, State st, StepIO io) {
   extern __shared__ __align__(128) unsigned char stage[];
   __shared__ __align__(8) unsigned long long bar;
-  const MfgSpec& sp = *spp;
   const int el = threadIdx.x;
   const int64_t e0 = (int64_t)blockIdx.x * STEP_ENVS, eg = e0 + el;
   char* gblock = st.base_i + (size_t)blockIdx.x * st.blk_i;
@@ -66,9 +66,24 @@ __global__ void __launch_bounds__(STEP_ENVS) k_step(const MfgSpec* __restrict__ 
   if (el == 0) {
     mbar_init(&bar, 1);
     mbar_expect_tx(&bar, bytes);
-    // a bulk copy moves at most 2^20 - 16 bytes per instruction; blocks are tens of KB
     bulk_g2s(stage, gblock, bytes, &bar);
   }
+  // level tables the step touches with divergent indices: wall map, tile -> door map, door positions.  With most of
+  // the SM's unified cache carved out as shared memory they would otherwise be L2 round trips.
+  const int HW = hs.H * hs.W, HW4 = (HW + 3) >> 2;
+  uint32_t* s_wall = reinterpret_cast<uint32_t*>(stage + bytes);
+  uint32_t* s_dmap = s_wall + HW4;
+  uint16_t* s_dpos = reinterpret_cast<uint16_t*>(s_dmap + HW4);
+  for (int i = el; i < HW; i += STEP_ENVS) {
+    reinterpret_cast<uint8_t*>(s_wall)[i] = tb.wall[i];
+    reinterpret_cast<uint8_t*>(s_dmap)[i] = tb.door_map[i];
+  }
+  if (el < hs.n_doors) s_dpos[el] = tb.door_pos[el];
+  Tables tbs = tb;
+  tbs.wall = reinterpret_cast<const uint8_t*>(s_wall);
+  tbs.door_map = reinterpret_cast<const uint8_t*>(s_dmap);
+  tbs.door_pos = s_dpos;
+
   // staged view of the state: same field offsets, block 0 == the shared-memory copy
   State ss = st;
   ss.N = STEP_ENVS;
@@ -80,10 +95,10 @@ __global__ void __launch_bounds__(STEP_ENVS) k_step(const MfgSpec* __restrict__ 
     MFG_STATE_FIELDS(F)
 #undef F
   }
-  __syncthreads();                  // the barrier init must be visible before anybody polls it
+  __syncthreads();                  // barrier init + table copies visible
   mbar_wait(&bar, 0);
 
-  if (eg < st.N) env_step<AMAX>(sp, tb, ss, el, io, eg);
+  if (eg < st.N) env_step<AMAX, HotSpec<AMAX>>(hs, *full, tbs, ss, el, io, eg);
 
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   __syncthreads();
@@ -126,12 +141,16 @@ cudaError_t launch_reset(MfgHandle* h, const uint8_t* d_mask, cudaStream_t s) {
 
 cudaError_t launch_step(MfgHandle* h, const StepIO& io, cudaStream_t s) {
   const unsigned blocks = (unsigned)((h->N + STEP_ENVS - 1) / STEP_ENVS);
-  const size_t smem = h->st.blk_i;
+  const size_t hw4 = ((size_t)h->sp.H * h->sp.W + 3) / 4 * 4;
+  const size_t smem = h->st.blk_i + 2 * hw4 + 2 * MFG_MAX_DOORS + 16;
   cudaError_t err = cudaSuccess;
   dispatch_amax(h->sp.n_agents, [&](auto amax) {
-    auto kern = k_step<decltype(amax)::value>;
+    constexpr int AMAX = decltype(amax)::value;
+    auto kern = k_step<AMAX>;
+    HotSpec<AMAX> hs;
+    fill_hot_spec<AMAX>(h->sp, hs);
     if (smem > 48 * 1024) err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err == cudaSuccess) kern<<<blocks, STEP_ENVS, smem, s>>>(h->d_sp, h->tb, h->st, io);
+    if (err == cudaSuccess) kern<<<blocks, STEP_ENVS, smem, s>>>(hs, h->d_sp, h->tb, h->st, io);
   });
   return err != cudaSuccess ? err : cudaGetLastError();
 }

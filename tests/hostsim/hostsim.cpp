@@ -76,7 +76,7 @@ void hs_step(HsHandle* h, const int32_t* actions, const uint8_t* maint_act, cons
              const uint16_t* respawn_pos, float* reward, uint8_t* done, int auto_reset) {
   StepIO io{actions, maint_act, respawn_n, respawn_pos, reward, done, auto_reset};
   dispatch(h->sp.n_agents, [&](auto amax) {
-    for (int64_t e = 0; e < h->N; ++e) env_step<decltype(amax)::value>(h->sp, h->tb, h->st, e, io);
+    for (int64_t e = 0; e < h->N; ++e) env_step<decltype(amax)::value, MfgSpec>(h->sp, h->sp, h->tb, h->st, e, io);
   });
 }
 void hs_observe(HsHandle* h, float* obs) {
