@@ -618,13 +618,23 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
 #pragma unroll
   for (int i = 0; i < AMAX; ++i) rew[i] = 0.0;
   double glob = 0.0, other = 0.0;
+  // The f64 fields live in HBM (never staged): fetch every battery level, episode return and action of this env up
+  // front with independent loads (one round trip instead of a dependent one per use) and keep them in registers.
+  double bat[AMAX], epr[AMAX];
+  int act[AMAX];
+#pragma unroll
+  for (int i = 0; i < AMAX; ++i) {
+    bat[i] = (i < A && sp.has_batteries) ? v.at(st.bat, i) : 1.0;
+    epr[i] = (i < A && (sp.individual_rewards || i == 0)) ? v.at(st.ep_ret, i) : 0.0;
+    act[i] = i < A ? io.actions[(size_t)e * A + i] : 0;
+  }
 
   // ---- agents act sequentially against the live state (states.py:189-198)
 #pragma unroll
   for (int i = 0; i < AMAX; ++i) {
     if (i >= A) break;
     if (v.at(st.aflag, i) & 1) continue;                       // paralysed: skipped entirely
-    int a = io.actions[(size_t)e * A + i];
+    int a = act[i];
     if (a < 0 || a >= sp.n_actions[i]) a = 0;
     const int op = sp.act_opcode[i][a];
     const uint16_t p = v.apos[i];
@@ -666,8 +676,8 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
       bool on_pod = false;
       for (int k = 0; k < sp.n_pods; ++k) on_pod |= v.at(st.pod_pos, k) == p;
       if (on_pod) {
-        double b = v.at(st.bat, i);
-        if (!(b >= 1.0) && !(v.agents_at(p) > 1)) { v.at(st.bat, i) = fmin(1.0, CHARGE_RATE + b); ok = true; }
+        double b = bat[i];
+        if (!(b >= 1.0) && !(v.agents_at(p) > 1)) { bat[i] = fmin(1.0, CHARGE_RATE + b); ok = true; }
       }
     } else if (op == MFG_OP_DEST) {                            // destinations/actions.py:17-24 (reference raises on a dest)
       ok = false;
@@ -762,9 +772,9 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
         v.at(st.dirt_next_spawn, 0) = (int16_t)(next - 1);
       }
     } else if (op == MFG_R_BATTERY_DECHARGE || op == MFG_R_DONE_BATTERY) {   // batteries/rules.py:50-63
-      for (int i = 0; i < A; ++i) {
-        double b = v.at(st.bat, i);
-        if (b != 0) v.at(st.bat, i) = fmax(0.0, P[0] + b);
+#pragma unroll
+      for (int i = 0; i < AMAX; ++i) {
+        if (i < A && bat[i] != 0) bat[i] = fmax(0.0, P[0] + bat[i]);
       }
     } else if (op == MFG_R_DEST_REACH_REWARD || op == MFG_R_DONE_DEST) {     // destinations/rules.py:34-54
       uint32_t reached = v.at(st.dest_reached, 0);
@@ -821,8 +831,10 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
         other += P[0] * n_other;
       }
     } else if (op == MFG_R_BATTERY_DECHARGE || op == MFG_R_DONE_BATTERY) {   // batteries/rules.py:66-87
-      for (int i = 0; i < A; ++i) {
-        bool discharged = v.at(st.bat, i) == 0;
+#pragma unroll
+      for (int i = 0; i < AMAX; ++i) {
+        if (i >= A) continue;
+        bool discharged = bat[i] == 0;
         uint8_t f = v.at(st.aflag, i);
         if (discharged) {
 #pragma unroll
@@ -850,7 +862,8 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
       if (fired) { glob += P[0]; if (reason < 0) reason = MFG_ST_DONE_ALL_DIRT; }
     } else if (op == MFG_R_DONE_BATTERY) {
       bool any = false;
-      for (int i = 0; i < A; ++i) any |= v.at(st.bat, i) == 0;
+#pragma unroll
+      for (int i = 0; i < AMAX; ++i) any |= i < A && bat[i] == 0;
       fired = P[4] != 0 && any;
       if (fired) { glob += P[3]; if (reason < 0) reason = MFG_ST_DONE_BATTERY; }
     } else if (op == MFG_R_DONE_DEST) {
@@ -891,7 +904,8 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
       if (i < A) {
         double r = rew[i] + glob;
         io.reward[(size_t)e * A + i] = (float)r;
-        v.at(st.ep_ret, i) += r;
+        epr[i] += r;
+        v.at(st.ep_ret, i) = epr[i];
       }
     }
   } else {
@@ -901,9 +915,14 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
     s += other;
     s += glob;
     io.reward[e] = (float)s;
-    v.at(st.ep_ret, 0) += s;
+    epr[0] += s;
+    v.at(st.ep_ret, 0) = epr[0];
   }
   io.done[e] = done ? 1 : 0;
+  if (sp.has_batteries) {
+#pragma unroll
+    for (int i = 0; i < AMAX; ++i) if (i < A) v.at(st.bat, i) = bat[i];
+  }
   v.store();
 
   // ---- episode statistics + optional in-kernel auto reset
@@ -914,7 +933,8 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
     if (reason >= 0) stat_add(tb, reason, 1);
     double tot = 0.0;
     const int nr = sp.individual_rewards ? A : 1;
-    for (int i = 0; i < nr; ++i) { double x = v.at(st.ep_ret, i); tot += x; stat_add_f64(tb, MFG_ST_RETURN_AGENT0 + i, x); }
+#pragma unroll
+    for (int i = 0; i < AMAX; ++i) if (i < nr) { double x = epr[i]; tot += x; stat_add_f64(tb, MFG_ST_RETURN_AGENT0 + i, x); }
     stat_add_f64(tb, MFG_ST_RETURN_SUM, tot);
     if (io.auto_reset) env_reset<AMAX>(full, tb, st, v.e, v.at(st.episode, 0) + 1, v.eg);
   }

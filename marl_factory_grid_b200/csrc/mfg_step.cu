@@ -74,9 +74,10 @@ __global__ void __launch_bounds__(STEP_ENVS) k_step(const __grid_constant__ HotS
   uint32_t* s_wall = reinterpret_cast<uint32_t*>(stage + bytes);
   uint32_t* s_dmap = s_wall + HW4;
   uint16_t* s_dpos = reinterpret_cast<uint16_t*>(s_dmap + HW4);
-  for (int i = el; i < HW; i += STEP_ENVS) {
-    reinterpret_cast<uint8_t*>(s_wall)[i] = tb.wall[i];
-    reinterpret_cast<uint8_t*>(s_dmap)[i] = tb.door_map[i];
+  {   // 32-bit copies (the device tables are allocated in 256-byte granules, reading the pad word is safe)
+    const uint32_t* gw = reinterpret_cast<const uint32_t*>(tb.wall);
+    const uint32_t* gd = reinterpret_cast<const uint32_t*>(tb.door_map);
+    for (int i = el; i < HW4; i += STEP_ENVS) { s_wall[i] = gw[i]; s_dmap[i] = gd[i]; }
   }
   if (el < hs.n_doors) s_dpos[el] = tb.door_pos[el];
   Tables tbs = tb;
