@@ -82,6 +82,8 @@ void mfg_destroy(MfgHandle* h) {
   if (h->d_reward) cudaFree(h->d_reward);
   if (h->d_done) cudaFree(h->d_done);
   if (h->d_obs) cudaFree(h->d_obs);
+  if (h->d_reset_list) cudaFree(h->d_reset_list);
+  if (h->d_reset_count) cudaFree(h->d_reset_count);
   delete h;
 }
 
@@ -116,14 +118,20 @@ int mfg_step(MfgHandle* h, const int32_t* d_actions, const MfgTape* tape, float*
   NEED_BOUND(h);
   if (!d_actions || !d_reward || !d_done) return fail(MFG_E_INVALID, "mfg_step: NULL buffer");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (auto_reset && h->defer_reset && !h->d_reset_list) {
+    CUDA_TRY(cudaMalloc(&h->d_reset_list, (size_t)h->N * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&h->d_reset_count, sizeof(uint32_t)));
+  }
+  const bool defer = auto_reset && h->defer_reset;
   StepIO io{d_actions, tape ? tape->d_maint_action : nullptr, tape ? tape->d_respawn_n : nullptr,
-            tape ? tape->d_respawn_pos : nullptr, d_reward, d_done, auto_reset};
+            tape ? tape->d_respawn_pos : nullptr, d_reward, d_done, auto_reset,
+            defer ? h->d_reset_list : nullptr, defer ? h->d_reset_count : nullptr};
   bool need_policy = false;
   for (int r = 0; r < h->sp.n_rules; ++r) need_policy |= h->sp.rule_op[r] == MFG_R_MOVE_MAINTAINERS;
   if (need_policy && !io.maint_act && !h->tb.nexthop)
     return fail(MFG_E_INVALID, "mfg_step: MoveMaintainers without a tape needs the next-hop table (MfgSpec.nexthop)");
   CUDA_TRY(launch_step(h, io, s));
-  h->launches++;
+  h->launches += defer ? 2 : 1;
   return MFG_OK;
 }
 
@@ -190,6 +198,10 @@ int mfg_set_option(MfgHandle* h, const char* name, int64_t value) {
     if (value < 0 || value > 2) return fail(MFG_E_INVALID, "obs_kernel must be 0 (auto), 1 (direct) or 2 (tiled)");
     if (value == 2 && !h->plan.ok) return fail(MFG_E_UNSUPPORTED, "tiled observation kernel not available for this spec");
     h->obs_kernel = (int)value;
+    return MFG_OK;
+  }
+  if (strcmp(name, "defer_reset") == 0) {       // 1 = packed reset kernel after the step (default), 0 = in-line reset
+    h->defer_reset = value != 0;
     return MFG_OK;
   }
   if (strcmp(name, "obs_cap") == 0) {          // sprite slots per (env, agent); small values force the overflow path (tests)

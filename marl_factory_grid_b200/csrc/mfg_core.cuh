@@ -560,7 +560,9 @@ struct StepIO {
   const uint16_t* respawn_pos;// [N][8] or null
   float* reward;              // [N][A] (or [N][1])
   uint8_t* done;              // [N]
-  int auto_reset;
+  int auto_reset;             // 0 = never, 1 = re-spawn finished envs (inline, or deferred when reset_list is set)
+  uint32_t* reset_list;       // deferred reset: finished env ids are appended here and re-spawned by k_reset_list, packed
+  uint32_t* reset_count;      //                 (an in-line reset makes almost every warp run the long spawn path for 1-2 lanes)
 };
 
 // maintainer policy when no tape is given (maintenance/entities.py:37-136), next hop from the BFS table
@@ -936,7 +938,13 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
 #pragma unroll
     for (int i = 0; i < AMAX; ++i) if (i < nr) { double x = epr[i]; tot += x; stat_add_f64(tb, MFG_ST_RETURN_AGENT0 + i, x); }
     stat_add_f64(tb, MFG_ST_RETURN_SUM, tot);
-    if (io.auto_reset) env_reset<AMAX>(full, tb, st, v.e, v.at(st.episode, 0) + 1, v.eg);
+    if (io.auto_reset) {
+#if defined(__CUDA_ARCH__)
+      if (io.reset_list) io.reset_list[atomicAdd(io.reset_count, 1u)] = (uint32_t)v.eg;
+      else
+#endif
+        env_reset<AMAX>(full, tb, st, v.e, v.at(st.episode, 0) + 1, v.eg);
+    }
   }
 }
 

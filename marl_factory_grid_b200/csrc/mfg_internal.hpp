@@ -64,6 +64,9 @@ struct MfgHandle {
   // host-buffer path staging
   int32_t* d_actions = nullptr; float* d_reward = nullptr; uint8_t* d_done = nullptr; float* d_obs = nullptr;
   int64_t launches = 0;
+  uint32_t* d_reset_list = nullptr;   // [N] ids of envs that finished in the current step
+  uint32_t* d_reset_count = nullptr;
+  int defer_reset = 1;
 };
 
 namespace mfg {

@@ -19,6 +19,18 @@ __global__ void __launch_bounds__(128) k_reset(const MfgSpec* __restrict__ sp, T
   env_reset<AMAX>(*sp, tb, st, e, episode);
 }
 
+// deferred auto-reset: one thread per FINISHED env (ids appended by k_step), so the long Philox spawn path runs in
+// fully packed warps instead of dragging 1-2 lanes of almost every step warp through it
+template <int AMAX>
+__global__ void __launch_bounds__(128) k_reset_list(const MfgSpec* __restrict__ sp, Tables tb, State st,
+                                                    const uint32_t* __restrict__ list, const uint32_t* __restrict__ count) {
+  const uint32_t n = *count;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int64_t e = list[i];
+    env_reset<AMAX>(*sp, tb, st, e, field_at(st, st.episode, 0, e) + 1);
+  }
+}
+
 // k_step: CTA = one 128-env state block.  The block's integer / byte fields are ONE contiguous slab in HBM (blocked
 // layout, see State): a single TMA bulk copy (cp.async.bulk, completion on an mbarrier) stages it in shared memory,
 // the whole step runs against that copy (tile look-ups, slot scans and rule hooks hit shared memory instead of
@@ -151,7 +163,12 @@ cudaError_t launch_step(MfgHandle* h, const StepIO& io, cudaStream_t s) {
     HotSpec<AMAX> hs;
     fill_hot_spec<AMAX>(h->sp, hs);
     if (smem > 48 * 1024) err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err == cudaSuccess && io.auto_reset && io.reset_list) err = cudaMemsetAsync(io.reset_count, 0, sizeof(uint32_t), s);
     if (err == cudaSuccess) kern<<<blocks, STEP_ENVS, smem, s>>>(hs, h->d_sp, h->tb, h->st, io);
+    if (err == cudaSuccess && io.auto_reset && io.reset_list) {
+      const unsigned rblocks = blocks < 1024 ? blocks : 1024;
+      k_reset_list<AMAX><<<rblocks, 128, 0, s>>>(h->d_sp, h->tb, h->st, io.reset_list, io.reset_count);
+    }
   });
   return err != cudaSuccess ? err : cudaGetLastError();
 }

@@ -74,7 +74,7 @@ void hs_reset(HsHandle* h, const uint8_t* mask) {
 }
 void hs_step(HsHandle* h, const int32_t* actions, const uint8_t* maint_act, const int8_t* respawn_n,
              const uint16_t* respawn_pos, float* reward, uint8_t* done, int auto_reset) {
-  StepIO io{actions, maint_act, respawn_n, respawn_pos, reward, done, auto_reset};
+  StepIO io{actions, maint_act, respawn_n, respawn_pos, reward, done, auto_reset, nullptr, nullptr};
   dispatch(h->sp.n_agents, [&](auto amax) {
     for (int64_t e = 0; e < h->N; ++e) env_step<decltype(amax)::value, MfgSpec>(h->sp, h->sp, h->tb, h->st, e, io);
   });

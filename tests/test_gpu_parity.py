@@ -152,6 +152,25 @@ def test_tiled_observation_kernel_equals_direct_kernel_at_scale(cfg):
     eng.close()
 
 
+def test_inline_and_deferred_auto_reset_agree():
+    """The packed reset kernel (default) and the in-line reset inside k_step re-spawn finished envs identically."""
+    es = spec_for('cfg4')
+    a, b = _engine(es, 640, faithful=True, seed=9), _engine(es, 640, faithful=True, seed=9)
+    b.set_option('defer_reset', 0)
+    a.reset()
+    b.reset()
+    acts = torch.zeros((640, es.n_agents), dtype=torch.int32, device='cuda:0')
+    for t in range(60):
+        a.random_actions(acts, seed=2, step_index=t)
+        o1, r1, d1 = a.step_observe(acts, auto_reset=True)
+        o2, r2, d2 = b.step_observe(acts, auto_reset=True)
+        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2), t
+    np.testing.assert_array_equal(a.stats()[:11], b.stats()[:11])
+    assert a.stats()[0] > 0
+    a.close()
+    b.close()
+
+
 def test_env_shards_are_independent_of_the_partition():
     """Multi-GPU property on one device: envs [0, 256) as one engine == two engines of 128 with env_id_offset 0 / 128."""
     es = spec_for('cfg4')
