@@ -401,13 +401,16 @@ struct Env {
   // trigger_spawn body after the random draws: tiles/amounts zipped
   template <typename TileFn, typename AmtFn>
   MFG_HD void dirt_spawn(int n, TileFn tile, AmtFn amount) {
+    // global_amount (clean_up/groups.py:27-32) is a left-to-right f64 sum over the piles in creation order; a new pile
+    // is appended at the end, so `sum + a` IS the recomputed sum bit for bit; only a top-up forces a re-scan
+    double total = n > 0 ? dirt_sum() : 0.0;
     for (int j = 0; j < n; ++j) {
-      if (dirt_sum() > sp.dirt_max_global) return;
+      if (total > sp.dirt_max_global) return;
       uint16_t p = tile(j);
       double a = amount(j);
       int k = dirt_at(p);
-      if (k >= 0) at(st.dirt_amt, k) = fmin(at(st.dirt_amt, k) + a, DIRT_PILE_MAX);
-      else dirt_create(p, a);
+      if (k >= 0) { at(st.dirt_amt, k) = fmin(at(st.dirt_amt, k) + a, DIRT_PILE_MAX); total = dirt_sum(); }
+      else { const int before = dirt_n; dirt_create(p, a); if (dirt_n > before) total += a; }
     }
   }
 

@@ -19,15 +19,50 @@ __global__ void __launch_bounds__(128) k_reset(const MfgSpec* __restrict__ sp, T
   env_reset<AMAX>(*sp, tb, st, e, episode);
 }
 
+constexpr int STEP_ENVS = ENV_BLOCK;
+constexpr int STEP_ENVS_R = ENV_BLOCK;   // threads (= private columns) per CTA of the packed reset kernel
+
 // deferred auto-reset: one thread per FINISHED env (ids appended by k_step), so the long Philox spawn path runs in
-// fully packed warps instead of dragging 1-2 lanes of almost every step warp through it
+// fully packed warps instead of dragging 1-2 lanes of almost every step warp through it.  Each thread gathers its
+// env's integer column into a private column of a shared-memory block image (independent loads), re-spawns against
+// that copy (hundreds of dependent look-ups stay on chip) and scatters the column back.
 template <int AMAX>
-__global__ void __launch_bounds__(128) k_reset_list(const MfgSpec* __restrict__ sp, Tables tb, State st,
-                                                    const uint32_t* __restrict__ list, const uint32_t* __restrict__ count) {
+__global__ void __launch_bounds__(STEP_ENVS_R) k_reset_list(const MfgSpec* __restrict__ sp, Tables tb, State st,
+                                                            const uint32_t* __restrict__ list, const uint32_t* __restrict__ count) {
+  extern __shared__ __align__(128) unsigned char stage[];
   const uint32_t n = *count;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  const int t = threadIdx.x;
+  State ss = st;
+  ss.N = STEP_ENVS_R;
+  ss.base_i = reinterpret_cast<char*>(stage);
+  {
+    const char* g0 = st.base_i;
+#define F(type, name, rows_expr) \
+  if constexpr (!std::is_same<type, double>::value) ss.name = reinterpret_cast<type*>(stage + (reinterpret_cast<const char*>(st.name) - g0));
+    MFG_STATE_FIELDS(F)
+#undef F
+  }
+  const MfgSpec& spr = *sp;
+  for (uint32_t i = blockIdx.x * blockDim.x + t; i < n; i += gridDim.x * blockDim.x) {
     const int64_t e = list[i];
-    env_reset<AMAX>(*sp, tb, st, e, field_at(st, st.episode, 0, e) + 1);
+    const uint32_t episode = field_at(st, st.episode, 0, e) + 1;
+#define F(type, name, rows_expr)                                                                       \
+  if constexpr (!std::is_same<type, double>::value) {                                                  \
+    const MfgSpec& sp = spr; (void)sp;                                                                 \
+    const int rows = (int)(rows_expr);                                                                 \
+    for (int r = 0; r < rows; ++r) ss.name[r * ENV_BLOCK + t] = field_at(st, st.name, r, e);           \
+  }
+    MFG_STATE_FIELDS(F)
+#undef F
+    env_reset<AMAX>(spr, tb, ss, t, episode, e);
+#define F(type, name, rows_expr)                                                                       \
+  if constexpr (!std::is_same<type, double>::value) {                                                  \
+    const MfgSpec& sp = spr; (void)sp;                                                                 \
+    const int rows = (int)(rows_expr);                                                                 \
+    for (int r = 0; r < rows; ++r) field_at(st, st.name, r, e) = ss.name[r * ENV_BLOCK + t];           \
+  }
+    MFG_STATE_FIELDS(F)
+#undef F
   }
 }
 
@@ -36,8 +71,6 @@ __global__ void __launch_bounds__(128) k_reset_list(const MfgSpec* __restrict__ 
 // the whole step runs against that copy (tile look-ups, slot scans and rule hooks hit shared memory instead of
 // dependent HBM round trips), and a single bulk store writes it back.  f64 fields (dirt amounts, battery, returns)
 // stay in HBM: few actions / rules touch them.
-constexpr int STEP_ENVS = ENV_BLOCK;
-
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -166,8 +199,10 @@ cudaError_t launch_step(MfgHandle* h, const StepIO& io, cudaStream_t s) {
     if (err == cudaSuccess && io.auto_reset && io.reset_list) err = cudaMemsetAsync(io.reset_count, 0, sizeof(uint32_t), s);
     if (err == cudaSuccess) kern<<<blocks, STEP_ENVS, smem, s>>>(hs, h->d_sp, h->tb, h->st, io);
     if (err == cudaSuccess && io.auto_reset && io.reset_list) {
-      const unsigned rblocks = blocks < 1024 ? blocks : 1024;
-      k_reset_list<AMAX><<<rblocks, 128, 0, s>>>(h->d_sp, h->tb, h->st, io.reset_list, io.reset_count);
+      const unsigned rblocks = blocks < 592 ? blocks : 592;
+      auto rk = k_reset_list<AMAX>;
+      if (h->st.blk_i > 48 * 1024) err = cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->st.blk_i);
+      if (err == cudaSuccess) rk<<<rblocks, STEP_ENVS_R, h->st.blk_i, s>>>(h->d_sp, h->tb, h->st, io.reset_list, io.reset_count);
     }
   });
   return err != cudaSuccess ? err : cudaGetLastError();
