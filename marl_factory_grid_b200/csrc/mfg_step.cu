@@ -99,7 +99,7 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, uint32
 }
 
 template <int AMAX>
-__global__ void __launch_bounds__(STEP_ENVS) k_step(const __grid_constant__ HotSpec<AMAX> hs, const MfgSpec* __restrict__ full,
+__global__ void __launch_bounds__(STEP_ENVS, 5) k_step(const __grid_constant__ HotSpec<AMAX> hs, const MfgSpec* __restrict__ full,
                                                     Tables tb, State st, StepIO io) {
   extern __shared__ __align__(128) unsigned char stage[];
   __shared__ __align__(8) unsigned long long bar;
