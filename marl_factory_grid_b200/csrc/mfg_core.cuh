@@ -56,6 +56,17 @@ enum { C_DOOR = 0, C_DIRT, C_ITEM, C_POD, C_DEST, C_DROP, C_MACH, C_MAINT, C_NON
   F(uint16_t, apos, sp.n_agents)                                                   \
   F(uint64_t, door_open, sp.n_doors ? 1 : 0)                                       \
   F(uint32_t, dest_reached, sp.n_dest ? 1 : 0)                                     \
+  /* ---- end of the identity-mode observation prefix; the faithful mode also needs listing bits and dirt uids */ \
+  F(uint64_t, door_listed, sp.n_doors ? 1 : 0)                                     \
+  F(uint64_t, dirt_listed, sp.has_dirt ? 1 : 0)                                    \
+  F(uint32_t, item_listed, sp.n_items ? 1 : 0)                                     \
+  F(uint32_t, pod_listed, sp.n_pods ? 1 : 0)                                       \
+  F(uint32_t, dest_listed, sp.n_dest ? 1 : 0)                                      \
+  F(uint32_t, drop_listed, sp.n_dropoff ? 1 : 0)                                   \
+  F(uint32_t, mach_listed, sp.n_machines ? 1 : 0)                                  \
+  F(uint32_t, maint_listed, sp.n_maint ? 1 : 0)                                    \
+  F(uint16_t, dirt_uid, sp.has_dirt ? sp.dirt_slots : 0)                           \
+  /* ---- end of the faithful-mode observation prefix */                           \
   F(uint16_t, step, 1)                                                             \
   F(uint32_t, episode, 1)                                                          \
   F(uint32_t, clock, 1)                                                            \
@@ -63,21 +74,12 @@ enum { C_DOOR = 0, C_DIRT, C_ITEM, C_POD, C_DEST, C_DROP, C_MACH, C_MAINT, C_NON
   F(uint8_t, aflag, sp.n_agents)                                                   \
   F(double, bat, sp.has_batteries ? sp.n_agents : 0)                               \
   F(double, ep_ret, sp.n_agents)                                                   \
-  F(uint64_t, door_listed, sp.n_doors ? 1 : 0)                                     \
   F(uint8_t, door_timer, sp.n_doors)                                               \
   F(double, dirt_amt, sp.has_dirt ? sp.dirt_slots : 0)                             \
-  F(uint16_t, dirt_uid, sp.has_dirt ? sp.dirt_slots : 0)                           \
-  F(uint64_t, dirt_listed, sp.has_dirt ? 1 : 0)                                    \
   F(uint8_t, dirt_end, sp.has_dirt ? 1 : 0)                                        \
   F(uint8_t, dirt_n, sp.has_dirt ? 1 : 0)                                          \
   F(uint16_t, dirt_next_uid, sp.has_dirt ? 1 : 0)                                  \
   F(int16_t, dirt_next_spawn, sp.has_dirt ? 1 : 0)                                 \
-  F(uint32_t, item_listed, sp.n_items ? 1 : 0)                                     \
-  F(uint32_t, pod_listed, sp.n_pods ? 1 : 0)                                       \
-  F(uint32_t, dest_listed, sp.n_dest ? 1 : 0)                                      \
-  F(uint32_t, drop_listed, sp.n_dropoff ? 1 : 0)                                   \
-  F(uint32_t, mach_listed, sp.n_machines ? 1 : 0)                                  \
-  F(uint32_t, maint_listed, sp.n_maint ? 1 : 0)                                    \
   F(uint16_t, maint_target, sp.n_maint)                                            \
   F(uint16_t, maint_rand, sp.n_maint)                                              \
   F(uint32_t, maint_remaining, sp.n_maint)                                         \
@@ -954,14 +956,15 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
 // ================================================================================================
 // observation, one (env, agent) per thread, all parity modes (the tiled fast path lives in mfg_kernels.cu)
 // ================================================================================================
-constexpr int RANK_INF = 0xFFFF;
+constexpr int RANK_INF = 0xFF;            // first-visit ranks: at most (2*7+1)^2 = 225 distinct cells are ever visited
+constexpr int RANK_CELLS = (2 * 7 + 1) * (2 * 7 + 1);
 
 template <int AMAX>
 struct ObsCtx {
   Env<AMAX>& v;
   int a, ax, ay, r, D, R, BW;
-  uint16_t rank[(2 * 2 * 3 + 3) * (2 * 2 * 3 + 3)];      // (2*radius+1)^2 with radius = D = 7 for pomdp_r = 3
-  MFG_HD ObsCtx(Env<AMAX>& v_) : v(v_) {}
+  uint8_t* rank;                          // [(2R+1)^2] first-visit order of every cell of the radius box, RANK_INF = unseen
+  MFG_HD ObsCtx(Env<AMAX>& v_, uint8_t* rank_) : v(v_), rank(rank_) {}
   MFG_HD bool blocks_light(int x, int y) const {
     if (!v.in_grid(x, y)) return false;
     return v.tb.wall[x * v.sp.W + y] || v.closed_listed_door(x, y);
@@ -994,19 +997,27 @@ MFG_HD bool uid_shadowed(const ObsCtx<AMAX>& o, int cls, int idx, int uid, int m
   return false;
 }
 
-// out points at this agent's first channel: [C_a][D*D] floats, contiguous
-template <int AMAX>
-MFG_HDN void obs_agent_direct(const MfgSpec& sp, const Tables& tb, const State& st, int64_t e, int a, float* out) {
+// What an entity contributes: an integer-valued encoding (stacks add up exactly), a door (open / closed encoding),
+// a dirt pile (f64 amount of slot `aux`), or a directly stored scalar.
+enum { OK_INT = 0, OK_STORE = 1, OK_DOOR = 2, OK_DIRT = 3 };
+
+// Exact observation of one agent in every parity mode (observation_builder.py:138-220 + ray_caster.py:66-104):
+// full radius rays in the reference's order, first-visit rank per cell, uid shadowing when spec.faithful.
+// The result goes to a Sink:  sink.wall(cell)                       visible, unshadowed wall on a window cell
+//                             sink.ent(chmask, cell, kind, aux, v)  entity contribution to every channel in chmask
+//                             sink.scalar(channel, flat_index, v)   Battery / GlobalPosition values
+// Call order: walls, agents, integer-valued groups, doors, dirt, scalars (fractional encodings last).
+template <int AMAX, typename Sink>
+MFG_HDN void obs_agent_exact(const MfgSpec& sp, const Tables& tb, const State& st, int64_t e, int a, uint8_t* rank,
+                             Sink& sink) {
   Env<AMAX> v(sp, tb, st, e);
   v.load();
-  ObsCtx<AMAX> o(v);
-  const int r = sp.pomdp_r, D = 2 * r + 1, R = D, BW = 2 * R + 1, DD = D * D;
+  ObsCtx<AMAX> o(v, rank);
+  const int r = sp.pomdp_r, D = 2 * r + 1, R = D, BW = 2 * R + 1;
   o.a = a; o.ax = px(v.apos[a]); o.ay = py(v.apos[a]); o.r = r; o.D = D; o.R = R; o.BW = BW;
-  const int C = sp.n_channels[a];
-  for (int i = 0; i < C * DD; ++i) out[i] = 0.0f;
-  for (int i = 0; i < BW * BW; ++i) o.rank[i] = RANK_INF;
+  for (int i = 0; i < BW * BW; ++i) rank[i] = RANK_INF;
 
-  // ---- ray walk (ray_caster.py:66-104): first-visit rank per cell of the radius box
+  // ---- ray walk: first-visit order of the cells of the radius box
   int visit = 0;
   for (int ray = 0; ray < sp.n_rays; ++ray) {
     int pxr = o.ax, pyr = o.ay;
@@ -1017,10 +1028,9 @@ MFG_HDN void obs_agent_direct(const MfgSpec& sp, const Tables& tb, const State& 
       bool hits = o.blocks_light(x, y);
       bool diag = (cx != 0 && cy != 0) && o.blocks_light(x, y - cy) && o.blocks_light(x - cx, y);
       if (!diag) {
-        uint16_t& rk = o.rank[(dx + R) * BW + (dy + R)];
-        if (rk == RANK_INF) rk = (uint16_t)visit;
+        uint8_t& rk = rank[(dx + R) * BW + (dy + R)];
+        if (rk == RANK_INF) rk = (uint8_t)visit++;
       }
-      ++visit;
       if (hits || diag) break;
       pxr = x; pyr = y;
     }
@@ -1033,22 +1043,13 @@ MFG_HDN void obs_agent_direct(const MfgSpec& sp, const Tables& tb, const State& 
     cell = dx * D + dy;
     return true;
   };
-  auto add = [&](uint32_t mask, int cell, double val) {
-    while (mask) {
-      int c = 0;
-      while (!((mask >> c) & 1)) ++c;
-      mask &= mask - 1;
-      float& f = out[c * DD + cell];
-      f = (float)((double)f + val);
-    }
-  };
 
   // ---- walls (uid = row-major wall index)
   if (chm[MFG_G_WALLS]) {
     for (int dx = -r; dx <= r; ++dx) for (int dy = -r; dy <= r; ++dy) {
       int x = o.ax + dx, y = o.ay + dy;
       if (!v.in_grid(x, y) || !tb.wall[x * sp.W + y]) continue;
-      int rk = o.rank[(dx + R) * BW + (dy + R)];
+      int rk = rank[(dx + R) * BW + (dy + R)];
       if (rk == RANK_INF) continue;
       if (sp.faithful) {
         // walls are never shadowed by other walls; only a dynamic entity with the same uid seen earlier hides it
@@ -1062,7 +1063,7 @@ MFG_HDN void obs_agent_direct(const MfgSpec& sp, const Tables& tb, const State& 
           sh = uid < v.cls_count(c) && ((v.at(v.cls_listed(c), 0) >> uid) & 1) && o.rank_of(v.at(v.cls_pos(c), uid)) < rk;
         if (sh) continue;
       }
-      add(chm[MFG_G_WALLS], (dx + r) * D + (dy + r), 1.0);
+      sink.wall((dx + r) * D + (dy + r));
     }
   }
   // ---- agents (string identifiers: never shadowed)
@@ -1070,7 +1071,7 @@ MFG_HDN void obs_agent_direct(const MfgSpec& sp, const Tables& tb, const State& 
     int cell;
     if (!chm[MFG_G_AGENT0 + j] || !in_window(v.apos[j], cell)) continue;
     if (o.rank_of(v.apos[j]) == RANK_INF) continue;
-    add(chm[MFG_G_AGENT0 + j], cell, 1.0);
+    sink.ent(chm[MFG_G_AGENT0 + j], cell, OK_INT, 0, 1.0);
   }
   // ---- small groups with constant encodings
   const int term_of[8] = {MFG_G_DOORS, MFG_G_DIRT, MFG_G_ITEMS, MFG_G_PODS, MFG_G_DEST, MFG_G_DROPOFF, MFG_G_MACHINES, MFG_G_MAINT};
@@ -1086,8 +1087,8 @@ MFG_HDN void obs_agent_direct(const MfgSpec& sp, const Tables& tb, const State& 
       int rk = o.rank_of(p);
       if (rk == RANK_INF) continue;
       if (sp.faithful && uid_shadowed(o, c, k, k, rk)) continue;
-      double enc = c == C_MACH ? ENC_MACHINE : (c == C_DEST && ((v.at(st.dest_reached, 0) >> k) & 1)) ? 0.0 : 1.0;
-      add(m, cell, enc);
+      if (c == C_DEST && ((v.at(st.dest_reached, 0) >> k) & 1)) continue;         // a reached destination encodes as 0
+      sink.ent(m, cell, OK_INT, 0, c == C_MACH ? ENC_MACHINE : 1.0);
     }
   }
   // ---- doors, then dirt (fractional encodings go last so that integer stacks are summed exactly first)
@@ -1099,7 +1100,8 @@ MFG_HDN void obs_agent_direct(const MfgSpec& sp, const Tables& tb, const State& 
       int rk = o.rank_of(p);
       if (rk == RANK_INF) continue;
       if (sp.faithful && uid_shadowed(o, C_DOOR, d, d, rk)) continue;
-      add(chm[MFG_G_DOORS], cell, ((v.dopen >> d) & 1) ? ENC_DOOR_OPEN : ENC_DOOR_CLOSED);
+      const bool open = (v.dopen >> d) & 1;
+      sink.ent(chm[MFG_G_DOORS], cell, OK_DOOR, open ? 1 : 0, open ? ENC_DOOR_OPEN : ENC_DOOR_CLOSED);
     }
   }
   if (sp.has_dirt && chm[MFG_G_DIRT]) {
@@ -1110,18 +1112,48 @@ MFG_HDN void obs_agent_direct(const MfgSpec& sp, const Tables& tb, const State& 
       int rk = o.rank_of(p);
       if (rk == RANK_INF) continue;
       if (sp.faithful && uid_shadowed(o, C_DIRT, k, v.at(st.dirt_uid, k), rk)) continue;
-      add(chm[MFG_G_DIRT], cell, v.at(st.dirt_amt, k));
+      sink.ent(chm[MFG_G_DIRT], cell, OK_DIRT, k, v.at(st.dirt_amt, k));
     }
   }
   // ---- scalar channels (observation_builder.py:205-218, entity/util.py:56-66)
+  const int C = sp.n_channels[a];
   for (int c = 0; c < C; ++c) {
     int kind = sp.ch_kind[a][c];
-    if (kind == MFG_CH_BATTERY) out[c * DD] = (float)v.at(st.bat, a);
+    if (kind == MFG_CH_BATTERY) sink.scalar(c, 0, (float)v.at(st.bat, a));
     else if (kind == MFG_CH_GLOBALPOS) {
-      out[c * DD] = (float)((double)o.ax / (double)sp.H);
-      out[c * DD + 1] = (float)((double)o.ay / (double)sp.W);
+      sink.scalar(c, 0, (float)((double)o.ax / (double)sp.H));
+      sink.scalar(c, 1, (float)((double)o.ay / (double)sp.W));
     }
   }
+}
+
+// Sink that writes the agent's planes directly: out = [C_a][D*D] floats, contiguous
+struct FloatSink {
+  float* out;
+  int DD;
+  uint32_t wall_mask;
+  MFG_HD void add(uint32_t mask, int cell, double val) {
+    while (mask) {
+      int c = 0;
+      while (!((mask >> c) & 1)) ++c;
+      mask &= mask - 1;
+      float& f = out[c * DD + cell];
+      f = (float)((double)f + val);
+    }
+  }
+  MFG_HD void wall(int cell) { add(wall_mask, cell, 1.0); }
+  MFG_HD void ent(uint32_t mask, int cell, int, int, double val) { add(mask, cell, val); }
+  MFG_HD void scalar(int c, int flat, float v) { out[c * DD + flat] = v; }
+};
+
+template <int AMAX>
+MFG_HDN void obs_agent_direct(const MfgSpec& sp, const Tables& tb, const State& st, int64_t e, int a, float* out) {
+  const int D = 2 * sp.pomdp_r + 1, DD = D * D;
+  const int C = sp.n_channels[a];
+  for (int i = 0; i < C * DD; ++i) out[i] = 0.0f;
+  uint8_t rank[RANK_CELLS];
+  FloatSink sink{out, DD, sp.term_chmask[a][MFG_G_WALLS]};
+  obs_agent_exact<AMAX>(sp, tb, st, e, a, rank, sink);
 }
 
 }  // namespace mfg

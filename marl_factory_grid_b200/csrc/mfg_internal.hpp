@@ -24,6 +24,7 @@ struct WindowRays {
 struct ObsSlots {
   int dirt0, item0, pod0, dest0, drop0, mach0, maint0, agent0, total;
   int off_dopen, off_reached, prefix_bytes;    // layout of the staged block prefix (bytes)
+  int off_door_listed, off_dirt_listed, off_dirt_uid, off_listed[6];   // faithful mode only (-1 / 0 = absent)
 };
 
 constexpr int MAX_WALL_PLANES = 48;

@@ -65,6 +65,9 @@ __device__ __forceinline__ unsigned long long march(const unsigned long long B) 
 enum { SK_INT = 0, SK_STORE = 1, SK_DOOR = 2, SK_DIRT = 3 };
 struct Sprite { uint32_t w; float val; };          // w = index | kind << 16 | aux << 24
 
+constexpr int RANK_BUFS = 16;            // conflicted pairs resolved per round (one first-visit rank table each)
+constexpr int RANK_STRIDE = 232;
+
 // positions of one env inside the staged block prefix: slot-major slabs of 128 envs (see MFG_STATE_FIELDS order)
 struct BlkPos {
   const uint16_t* base;
@@ -78,82 +81,43 @@ __device__ __forceinline__ void bulk_store_tile(float* dst, const float* src_sme
   asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
 }
 
-// generic (slow) fill of one env's tile: lanes over entity slots, used when the env's sprite list overflowed
-__device__ void slow_fill_env(const MfgSpec* __restrict__ sp, const Tables& tb, const State& st, const ObsSlots& sl,
-                              const BlkPos pos, const unsigned long long* vis_a, unsigned long long dopen,
-                              uint32_t reached, float* te, int64_t e, int lane) {
-  const int A = sp->n_agents, r = sp->pomdp_r, D = 2 * r + 1, DD = D * D;
-  auto add_int = [&](uint32_t m, int coff, int cell, float v) {
-    while (m) { int c = __ffs(m) - 1; m &= m - 1; atomicAdd(&te[(coff + c) * DD + cell], v); }
-  };
-  auto add_frac = [&](uint32_t m, int coff, int cell, double v) {
-    while (m) { int c = __ffs(m) - 1; m &= m - 1; float* f = &te[(coff + c) * DD + cell]; *f = (float)((double)*f + v); }
-  };
-  for (int a = 0; a < A; ++a) {
-    const uint32_t* chm = sp->term_chmask[a];
-    const int coff = sp->ch_offset[a];
-    const unsigned long long vis = vis_a[a];
-    const uint16_t ap = pos[sl.agent0 + a];
-    const int ax = px(ap) - r, ay = py(ap) - r;
-    if (chm[MFG_G_WALLS]) {
-      const unsigned long long wv = tb.wall_win[px(ap) * sp->W + py(ap)] & vis;
-      for (int cell = lane; cell < DD; cell += 32) if ((wv >> cell) & 1) add_int(chm[MFG_G_WALLS], coff, cell, 1.0f);
-    }
-    for (int s = sl.item0 + lane; s < sl.total; s += 32) {
-      const uint16_t q = pos[s];
-      if (q == NO_POS) continue;
-      int term; float enc = 1.0f;
-      if (s < sl.pod0) term = MFG_G_ITEMS;
-      else if (s < sl.dest0) term = MFG_G_PODS;
-      else if (s < sl.drop0) { term = MFG_G_DEST; if ((reached >> (s - sl.dest0)) & 1) continue; }
-      else if (s < sl.mach0) term = MFG_G_DROPOFF;
-      else if (s < sl.maint0) { term = MFG_G_MACHINES; enc = (float)ENC_MACHINE; }
-      else if (s < sl.agent0) term = MFG_G_MAINT;
-      else term = MFG_G_AGENT0 + (s - sl.agent0);
-      const int dx = px(q) - ax, dy = py(q) - ay;
-      if (!chm[term] || dx < 0 || dy < 0 || dx >= D || dy >= D) continue;
-      if ((vis >> (dx * D + dy)) & 1) add_int(chm[term], coff, dx * D + dy, enc);
+// ---------------------------------------------------------------------------------------------------------------
+// exact per-agent path (mfg_core.cuh obs_agent_exact) used by the tiled kernel for the rare cases its fast path
+// does not cover: sprite-list overflow (any mode) and possible uid conflicts (faithful mode)
+// ---------------------------------------------------------------------------------------------------------------
+struct SpriteSink {
+  Sprite* spr;
+  int* cnt;
+  int cap, coff, DD;
+  unsigned long long wv;
+  __device__ __forceinline__ void put(uint32_t w, float val) {
+    const int slot = atomicAdd(cnt, 1);
+    if (slot < cap) spr[slot] = Sprite{w, val};
+  }
+  __device__ __forceinline__ void wall(int cell) { wv |= 1ull << cell; }
+  __device__ __forceinline__ void ent(uint32_t mask, int cell, int kind, int aux, double val) {
+    while (mask) {
+      const int c = __ffs(mask) - 1;
+      mask &= mask - 1;
+      put((uint32_t)((coff + c) * DD + cell) | ((uint32_t)kind << 16) | ((uint32_t)aux << 24), (float)val);
     }
   }
-  __syncwarp();
-  for (int a = 0; a < A && sp->n_doors; ++a) {
-    const uint32_t m = sp->term_chmask[a][MFG_G_DOORS];
-    const uint16_t ap = pos[sl.agent0 + a];
-    const int ax = px(ap) - r, ay = py(ap) - r;
-    for (int d = lane; d < sp->n_doors && m; d += 32) {
-      const uint16_t q = tb.door_pos[d];
-      const int dx = px(q) - ax, dy = py(q) - ay;
-      if (dx < 0 || dy < 0 || dx >= D || dy >= D) continue;
-      if ((vis_a[a] >> (dx * D + dy)) & 1)
-        add_frac(m, sp->ch_offset[a], dx * D + dy, ((dopen >> d) & 1) ? ENC_DOOR_OPEN : ENC_DOOR_CLOSED);
-    }
-  }
-  __syncwarp();
-  for (int a = 0; a < A && sp->has_dirt; ++a) {
-    const uint32_t m = sp->term_chmask[a][MFG_G_DIRT];
-    const uint16_t ap = pos[sl.agent0 + a];
-    const int ax = px(ap) - r, ay = py(ap) - r;
-    for (int k = lane; k < sl.item0 && m; k += 32) {
-      const uint16_t q = pos[k];
-      if (q == NO_POS) continue;
-      const int dx = px(q) - ax, dy = py(q) - ay;
-      if (dx < 0 || dy < 0 || dx >= D || dy >= D) continue;
-      if ((vis_a[a] >> (dx * D + dy)) & 1) add_frac(m, sp->ch_offset[a], dx * D + dy, field_at(st, st.dirt_amt, k, e));
-    }
-  }
-  __syncwarp();
-  for (int a = lane; a < A; a += 32) {
-    const int C = sp->n_channels[a], coff = sp->ch_offset[a];
-    for (int c = 0; c < C; ++c) {
-      const int kind = sp->ch_kind[a][c];
-      if (kind == MFG_CH_BATTERY) te[(coff + c) * DD] = (float)field_at(st, st.bat, a, e);
-      else if (kind == MFG_CH_GLOBALPOS) {
-        const uint16_t ap = pos[sl.agent0 + a];
-        te[(coff + c) * DD] = (float)((double)px(ap) / (double)sp->H);
-        te[(coff + c) * DD + 1] = (float)((double)py(ap) / (double)sp->W);
-      }
-    }
-  }
+  __device__ __forceinline__ void scalar(int c, int flat, float v) { put((uint32_t)((coff + c) * DD + flat) | (SK_STORE << 16), v); }
+};
+static_assert(SK_INT == OK_INT && SK_STORE == OK_STORE && SK_DOOR == OK_DOOR && SK_DIRT == OK_DIRT, "sprite kinds");
+
+__device__ __noinline__ void exact_agent_sprites(const MfgSpec* __restrict__ sp, const Tables& tb, const State& st, int64_t e,
+                                                 int a, uint8_t* rank, SpriteSink& sink) {
+  if (sp->n_agents <= 4) obs_agent_exact<4>(*sp, tb, st, e, a, rank, sink);
+  else obs_agent_exact<16>(*sp, tb, st, e, a, rank, sink);
+}
+// writes the agent's planes (already zeroed) straight into `out`; rank table on the thread's stack
+__device__ __noinline__ void exact_agent_floats(const MfgSpec* __restrict__ sp, const Tables& tb, const State& st, int64_t e,
+                                                int a, float* out, int DD) {
+  uint8_t rank[RANK_CELLS];
+  FloatSink sink{out, DD, sp->term_chmask[a][MFG_G_WALLS]};
+  if (sp->n_agents <= 4) obs_agent_exact<4>(*sp, tb, st, e, a, rank, sink);
+  else obs_agent_exact<16>(*sp, tb, st, e, a, rank, sink);
 }
 
 __device__ __forceinline__ void mbar_init1(unsigned long long* bar) {
@@ -173,7 +137,7 @@ __device__ __forceinline__ void mbar_wait0(unsigned long long* bar) {
 }
 
 // CTA = one 128-env state block, processed as four groups of 32 envs.
-template <int R, int GE, int NBUF, bool BULK>
+template <int R, int GE, int NBUF, bool BULK, bool FAITHFUL>
 __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st, ObsSlots sl, WallPlanes wp,
                             float* __restrict__ obs, int total_channels, int cap) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -192,6 +156,10 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
   unsigned long long* s_wv = s_vis + OBS_ENVS * A;                                          // [32][A]
   Sprite* s_spr = reinterpret_cast<Sprite*>(s_wv + OBS_ENVS * A);                           // [32][cap]  one list per env
   int* s_cnt = reinterpret_cast<int*>(s_spr + (size_t)OBS_ENVS * cap);                      // [32] sprites emitted per env
+  // faithful mode only: (env, agent) pairs with a possible uid conflict -> exact path, packed
+  int* s_nconf = s_cnt + OBS_ENVS;                                                          // [1] (+ pad)
+  uint16_t* s_conf = reinterpret_cast<uint16_t*>(s_nconf + 4);                              // [32 * A]
+  uint8_t* s_rank = reinterpret_cast<uint8_t*>(s_conf + ((OBS_ENVS * A + 7) & ~7));         // [RANK_BUFS][RANK_STRIDE]
 
   // ---- stage the positional prefix of this block: one TMA bulk copy (dirt/item/.../agent positions, door + dest masks)
   if (threadIdx.x == 0) {
@@ -205,8 +173,12 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
   const uint16_t* blk16 = reinterpret_cast<const uint16_t*>(s_blk);
   const unsigned long long* blk_dopen = reinterpret_cast<const unsigned long long*>(s_blk + sl.off_dopen);
   const uint32_t* blk_reached = reinterpret_cast<const uint32_t*>(s_blk + sl.off_reached);
+  const unsigned long long* blk_dlisted = reinterpret_cast<const unsigned long long*>(s_blk + sl.off_door_listed);
+  const unsigned long long* blk_dirtlisted = reinterpret_cast<const unsigned long long*>(s_blk + sl.off_dirt_listed);
+  const uint16_t* blk_dirt_uid = reinterpret_cast<const uint16_t*>(s_blk + sl.off_dirt_uid);
 
   if (warp == 0) s_cnt[lane] = 0;
+  if (threadIdx.x == 0) s_nconf[0] = 0;
   int buf = 0;
   for (int grp = 0; grp < ENV_BLOCK / OBS_ENVS; ++grp) {
     const int64_t env0 = blk0 + (int64_t)grp * OBS_ENVS;
@@ -222,6 +194,15 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
       const BlkPos pos{blk16, eb};
       const unsigned long long dopen = sp->n_doors ? blk_dopen[eb] : 0ull;
       const uint32_t reached = sp->n_dest ? blk_reached[eb] : 0u;
+      // listing bits (uid-equality artefact): everything is listed in identity mode
+      const unsigned long long dlisted = (FAITHFUL && sp->n_doors) ? blk_dlisted[eb] : ~0ull;
+      const unsigned long long dirtlisted = (FAITHFUL && sp->has_dirt) ? blk_dirtlisted[eb] : ~0ull;
+      uint32_t glisted[6] = {~0u, ~0u, ~0u, ~0u, ~0u, ~0u};
+      if (FAITHFUL) {
+#pragma unroll
+        for (int g = 0; g < 6; ++g)
+          if (sl.off_listed[g] >= 0) glisted[g] = reinterpret_cast<const uint32_t*>(s_blk + sl.off_listed[g])[eb];
+      }
       for (int a = warp; a < A; a += NW) {
         unsigned long long vis = 0ull, wv = 0ull;
         if (live) {
@@ -232,10 +213,51 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
           for (int d = 0; d < sp->n_doors; ++d) {
             const uint16_t q = tb.door_pos[d];
             const int dx = px(q) - ax + R, dy = py(q) - ay + R;
-            if (!((dopen >> d) & 1) && (unsigned)dx < (unsigned)D && (unsigned)dy < (unsigned)D) B |= 1ull << (dx * D + dy);
+            if (!((dopen >> d) & 1) && ((dlisted >> d) & 1) && (unsigned)dx < (unsigned)D && (unsigned)dy < (unsigned)D)
+              B |= 1ull << (dx * D + dy);
           }
           vis = march<R>(B);
           wv = W49 & vis;
+
+          if (FAITHFUL) {
+            // Conservative uid-conflict test: two LISTED entities with the same uid inside the
+            // radius-D box around the agent (a superset of everything a ray can reach).  Same-class entities never
+            // share a uid, so a repeated uid < 64 among the dynamic entities, or a wall with that uid inside the box,
+            // means "maybe".  Such (env, agent) pairs are resolved exactly afterwards, packed into one warp.
+            bool conflict = false;
+            unsigned long long seen = 0ull;
+            auto touch = [&](int uid, uint16_t q) {
+              const int dx = px(q) - ax, dy = py(q) - ay;
+              if (dx < -D || dx > D || dy < -D || dy > D) return;
+              if (uid < 64) { conflict |= ((seen >> uid) & 1ull) != 0; seen |= 1ull << uid; }
+              if (uid < sp->n_walls) {
+                const uint16_t w = tb.wall_pos[uid];
+                const int wx = px(w) - ax, wy = py(w) - ay;
+                conflict |= wx >= -D && wx <= D && wy >= -D && wy <= D;
+              }
+            };
+            for (int d = 0; d < sp->n_doors; ++d) if ((dlisted >> d) & 1) touch(d, tb.door_pos[d]);
+            for (int k = 0; k < sl.item0; ++k) {
+              const uint16_t q = pos[k];
+              if (q != NO_POS && ((dirtlisted >> k) & 1)) touch(blk_dirt_uid[k * ENV_BLOCK + eb], q);
+            }
+            {
+              const int lo[6] = {sl.item0, sl.pod0, sl.dest0, sl.drop0, sl.mach0, sl.maint0};
+              const int hi[6] = {sl.pod0, sl.dest0, sl.drop0, sl.mach0, sl.maint0, sl.agent0};
+#pragma unroll
+              for (int g = 0; g < 6; ++g)
+                for (int s = lo[g]; s < hi[g]; ++s) {
+                  const uint16_t q = pos[s];
+                  if (q != NO_POS && ((glisted[g] >> (s - lo[g])) & 1)) touch(s - lo[g], q);
+                }
+            }
+            if (conflict) {
+              s_conf[atomicAdd(s_nconf, 1)] = (uint16_t)(lane * A + a);
+              s_vis[lane * A + a] = vis;
+              s_wv[lane * A + a] = 0ull;            // filled in by the exact path
+              continue;
+            }
+          }
 
           const uint32_t* chm = sp->term_chmask[a];
           const int coff = sp->ch_offset[a];
@@ -276,7 +298,7 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
               if (!m) continue;
               for (int s = lo[g]; s < hi[g]; ++s) {
                 const uint16_t q = pos[s];
-                if (q == NO_POS) continue;
+                if (q == NO_POS || !((glisted[g] >> (s - lo[g])) & 1)) continue;
                 if (g == 2 && ((reached >> (s - lo[g])) & 1)) continue;      // a reached destination encodes as 0
                 const int cell = cell_of(q);
                 if (cell >= 0) emit(m, cell, SK_INT, 0, g == 4 ? (float)ENC_MACHINE : 1.0f);
@@ -286,6 +308,7 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
           // doors
           if (chm[MFG_G_DOORS]) {
             for (int d = 0; d < sp->n_doors; ++d) {
+              if (!((dlisted >> d) & 1)) continue;
               const int cell = cell_of(tb.door_pos[d]);
               if (cell >= 0) emit(chm[MFG_G_DOORS], cell, SK_DOOR, (uint32_t)((dopen >> d) & 1), 0.f);
             }
@@ -294,7 +317,7 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
           if (chm[MFG_G_DIRT]) {
             for (int k = 0; k < sl.item0; ++k) {
               const uint16_t q = pos[k];
-              if (q == NO_POS) continue;
+              if (q == NO_POS || !((dirtlisted >> k) & 1)) continue;
               const int cell = cell_of(q);
               if (cell >= 0) emit(chm[MFG_G_DIRT], cell, SK_DIRT, (uint32_t)k, 0.f);
             }
@@ -316,6 +339,22 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
       }
     }
     __syncthreads();
+
+    // ---------------- phase 1b (faithful): exact resolution of the conflicted pairs, packed into the first lanes ---
+    if (FAITHFUL) {
+      const int nconf = s_nconf[0];
+      for (int base = 0; base < nconf; base += RANK_BUFS) {
+        const int i = base + (int)threadIdx.x;
+        if ((int)threadIdx.x < RANK_BUFS && i < nconf) {
+          const int pair = s_conf[i], el = pair / A, a = pair - el * A;
+          SpriteSink sink{s_spr + (size_t)el * cap, s_cnt + el, cap, sp->ch_offset[a], DD, 0ull};
+          exact_agent_sprites(sp, tb, st, env0 + el, a, s_rank + threadIdx.x * RANK_STRIDE, sink);
+          s_wv[el * A + a] = sink.wv;
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) s_nconf[0] = 0;       // next group's phase 1 only starts after the loop-top barrier
+    }
 
     // ---------------- phase 2: one warp per tile of GE envs ------------------------------------------------------
     const int n_tiles = OBS_ENVS / GE;
@@ -348,10 +387,9 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
         const int cnt = s_cnt[el];
         __syncwarp();
         if (lane == 0) s_cnt[el] = 0;         // every lane holds `cnt`; the list counter is ready for the next group
-        if (cnt > cap) {                      // sprite list overflowed: generic lanes-over-slots fill of the whole env
-          const int eb = grp * OBS_ENVS + el;
-          slow_fill_env(sp, tb, st, sl, BlkPos{blk16, eb}, s_vis + el * A, sp->n_doors ? blk_dopen[eb] : 0ull,
-                        sp->n_dest ? blk_reached[eb] : 0u, te, e, lane);
+        if (cnt > cap) {                      // sprite list overflowed: exact per-agent path straight into the tile
+          for (int a = lane; a < A; a += 32) exact_agent_floats(sp, tb, st, e, a, te + sp->ch_offset[a] * DD, DD);
+          __syncwarp();
           continue;
         }
         Sprite s0{0u, 0.f}, s1{0u, 0.f};
@@ -516,16 +554,30 @@ void plan_obs(MfgHandle* h) {
   sl.maint0 = sl.mach0 + sp.n_machines;
   sl.agent0 = sl.maint0 + sp.n_maint;
   sl.total = sl.agent0 + sp.n_agents;
-  // the slots are exactly the first rows of every state block (MFG_STATE_FIELDS order), followed by the two bit masks
-  sl.off_dopen = sl.total * ENV_BLOCK * (int)sizeof(uint16_t);
-  sl.off_reached = sl.off_dopen + (sp.n_doors ? ENV_BLOCK * 8 : 0);
-  sl.prefix_bytes = sl.off_reached + (sp.n_dest ? ENV_BLOCK * 4 : 0);
+  // the slots are exactly the first rows of every state block (MFG_STATE_FIELDS order), followed by the bit masks
   {
     Layout L = compute_layout(sp, h->N);
-    auto off_of = [&](const char* name) { for (auto& f : L.fields) if (!strcmp(f.name, name)) return (long long)f.offset; return -1ll; };
-    bool order_ok = off_of("dirt_pos") == 0 && off_of("apos") == (long long)sl.agent0 * ENV_BLOCK * 2 &&
-                    (!sp.n_doors || off_of("door_open") == sl.off_dopen) && (!sp.n_dest || off_of("dest_reached") == sl.off_reached);
-    if (!order_ok) { p.ok = false; return; }
+    auto off_of = [&](const char* name) -> int {
+      for (auto& f : L.fields) if (!strcmp(f.name, name)) return f.rows ? (int)f.offset : -1;
+      return -1;
+    };
+    auto end_of = [&](const char* name) -> int {
+      for (auto& f : L.fields) if (!strcmp(f.name, name)) return (int)(f.offset + (size_t)f.rows * ENV_BLOCK * f.elem_size);
+      return 0;
+    };
+    sl.off_dopen = off_of("door_open");
+    sl.off_reached = off_of("dest_reached");
+    sl.off_door_listed = off_of("door_listed");
+    sl.off_dirt_listed = off_of("dirt_listed");
+    sl.off_dirt_uid = off_of("dirt_uid");
+    const char* ln[6] = {"item_listed", "pod_listed", "dest_listed", "drop_listed", "mach_listed", "maint_listed"};
+    for (int g = 0; g < 6; ++g) sl.off_listed[g] = off_of(ln[g]);
+    sl.prefix_bytes = sp.faithful ? end_of("dirt_uid") : end_of("dest_reached");
+    const bool order_ok = (!sp.has_dirt || off_of("dirt_pos") == 0) && off_of("apos") == sl.agent0 * ENV_BLOCK * 2 &&
+                          end_of("apos") <= sl.prefix_bytes && end_of("door_open") <= sl.prefix_bytes;
+    if (!order_ok || sl.prefix_bytes % 16) { p.ok = false; return; }
+    for (int* o : {&sl.off_dopen, &sl.off_reached, &sl.off_door_listed, &sl.off_dirt_listed, &sl.off_dirt_uid})
+      if (*o < 0) *o = 0;                       // absent fields are never dereferenced; keep the pointers in range
   }
   const int tcdd = h->total_channels * h->DD;
   p.ge = (tcdd % 4 == 0) ? 1 : (tcdd % 2 == 0) ? 2 : 4;
@@ -537,6 +589,7 @@ void plan_obs(MfgHandle* h) {
     b += (size_t)OBS_ENVS * sp.n_agents * 8 * 2;                           // vis, wv
     b += (size_t)OBS_ENVS * p.cap * 8;                                     // sprites (one list per env)
     b += OBS_ENVS * 4;                                                     // cnt
+    b += 16 + (size_t)((OBS_ENVS * sp.n_agents + 7) & ~7) * 2 + (size_t)RANK_BUFS * RANK_STRIDE;   // conflict list, rank tables
     b += (size_t)sl.prefix_bytes + 32;                                     // staged block prefix
     return b;
   };
@@ -557,12 +610,12 @@ void plan_obs(MfgHandle* h) {
         p.walls.plane[p.walls.n] = (uint16_t)(sp.ch_offset[a] + c);
         p.walls.n++;
       }
-  p.ok = !sp.faithful && trie_ok && walls_fit && p.smem <= 200 * 1024 && tcdd * p.ge <= 0xFFFF;
+  p.ok = trie_ok && walls_fit && p.smem <= 200 * 1024 && tcdd * p.ge <= 0xFFFF;
 }
 
-template <int R, int GE, int NBUF, bool BULK>
-static cudaError_t launch_tiled_t(MfgHandle* h, float* d_obs, cudaStream_t s) {
-  auto kern = k_obs_tiled<R, GE, NBUF, BULK>;
+template <int R, int GE, int NBUF, bool BULK, bool FAITHFUL>
+static cudaError_t launch_tiled_f(MfgHandle* h, float* d_obs, cudaStream_t s) {
+  auto kern = k_obs_tiled<R, GE, NBUF, BULK, FAITHFUL>;
   const ObsPlan& p = h->plan;
   if (p.smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
@@ -571,6 +624,11 @@ static cudaError_t launch_tiled_t(MfgHandle* h, float* d_obs, cudaStream_t s) {
   const unsigned blocks = (unsigned)((h->N + ENV_BLOCK - 1) / ENV_BLOCK);
   kern<<<blocks, p.nw * 32, p.smem, s>>>(h->d_sp, h->tb, h->st, p.slots, p.walls, d_obs, h->total_channels, p.cap);
   return cudaGetLastError();
+}
+
+template <int R, int GE, int NBUF, bool BULK>
+static cudaError_t launch_tiled_t(MfgHandle* h, float* d_obs, cudaStream_t s) {
+  return h->sp.faithful ? launch_tiled_f<R, GE, NBUF, BULK, true>(h, d_obs, s) : launch_tiled_f<R, GE, NBUF, BULK, false>(h, d_obs, s);
 }
 
 template <int R, int GE>

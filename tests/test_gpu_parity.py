@@ -75,8 +75,8 @@ def _replay_batch(cfg, mode, obs_kernels):
 
 @pytest.mark.parametrize('cfg', ALL_CFGS)
 def test_replay_untouched_reference(cfg):
-    """faithful mode == the unmodified reference (uid-equality artefact included); direct observation kernel."""
-    _replay_batch(cfg, 'U', obs_kernels=[1])
+    """faithful mode == the unmodified reference (uid-equality artefact included); BOTH observation kernels."""
+    _replay_batch(cfg, 'U', obs_kernels=[1, 2])
 
 
 @pytest.mark.parametrize('cfg', ALL_CFGS)
@@ -116,13 +116,14 @@ def test_freerun_matches_host_build_of_device_code(cfg, faithful):
     eng.close()
 
 
-@pytest.mark.parametrize('cfg', ['cfg2', 'cfg4'])
-def test_tiled_observation_kernel_equals_direct_kernel_at_scale(cfg):
+@pytest.mark.parametrize('faithful', [False, True])
+@pytest.mark.parametrize('cfg', ['cfg1', 'cfg2', 'cfg4', 'stress'])
+def test_tiled_observation_kernel_equals_direct_kernel_at_scale(cfg, faithful):
     """Size-independent property at a larger batch: both observation kernels produce identical tensors, agents never
     stand on walls, door timers stay within the auto-close interval, dirt amounts within (0, 5]."""
     es = spec_for(cfg)
     N = 8192 + 5                     # ragged: not a multiple of the 32-env CTA tile
-    eng = _engine(es, N, faithful=False, seed=7)
+    eng = _engine(es, N, faithful=faithful, seed=7)
     eng.reset()
     acts = torch.zeros((N, es.n_agents), dtype=torch.int32, device='cuda:0')
     walls = torch.as_tensor(es.walls, device='cuda:0')
