@@ -65,9 +65,6 @@ __device__ __forceinline__ unsigned long long march(const unsigned long long B) 
 enum { SK_INT = 0, SK_STORE = 1, SK_DOOR = 2, SK_DIRT = 3 };
 struct Sprite { uint32_t w; float val; };          // w = index | kind << 16 | aux << 24
 
-constexpr int RANK_BUFS = 16;            // conflicted pairs resolved per round (one first-visit rank table each)
-constexpr int RANK_STRIDE = 232;
-
 // positions of one env inside the staged block prefix: slot-major slabs of 128 envs (see MFG_STATE_FIELDS order)
 struct BlkPos {
   const uint16_t* base;
@@ -85,32 +82,6 @@ __device__ __forceinline__ void bulk_store_tile(float* dst, const float* src_sme
 // exact per-agent path (mfg_core.cuh obs_agent_exact) used by the tiled kernel for the rare cases its fast path
 // does not cover: sprite-list overflow (any mode) and possible uid conflicts (faithful mode)
 // ---------------------------------------------------------------------------------------------------------------
-struct SpriteSink {
-  Sprite* spr;
-  int* cnt;
-  int cap, coff, DD;
-  unsigned long long wv;
-  __device__ __forceinline__ void put(uint32_t w, float val) {
-    const int slot = atomicAdd(cnt, 1);
-    if (slot < cap) spr[slot] = Sprite{w, val};
-  }
-  __device__ __forceinline__ void wall(int cell) { wv |= 1ull << cell; }
-  __device__ __forceinline__ void ent(uint32_t mask, int cell, int kind, int aux, double val) {
-    while (mask) {
-      const int c = __ffs(mask) - 1;
-      mask &= mask - 1;
-      put((uint32_t)((coff + c) * DD + cell) | ((uint32_t)kind << 16) | ((uint32_t)aux << 24), (float)val);
-    }
-  }
-  __device__ __forceinline__ void scalar(int c, int flat, float v) { put((uint32_t)((coff + c) * DD + flat) | (SK_STORE << 16), v); }
-};
-static_assert(SK_INT == OK_INT && SK_STORE == OK_STORE && SK_DOOR == OK_DOOR && SK_DIRT == OK_DIRT, "sprite kinds");
-
-__device__ __noinline__ void exact_agent_sprites(const MfgSpec* __restrict__ sp, const Tables& tb, const State& st, int64_t e,
-                                                 int a, uint8_t* rank, SpriteSink& sink) {
-  if (sp->n_agents <= 4) obs_agent_exact<4>(*sp, tb, st, e, a, rank, sink);
-  else obs_agent_exact<16>(*sp, tb, st, e, a, rank, sink);
-}
 // writes the agent's planes (already zeroed) straight into `out`; rank table on the thread's stack
 __device__ __noinline__ void exact_agent_floats(const MfgSpec* __restrict__ sp, const Tables& tb, const State& st, int64_t e,
                                                 int a, float* out, int DD) {
@@ -139,7 +110,7 @@ __device__ __forceinline__ void mbar_wait0(unsigned long long* bar) {
 // CTA = one 128-env state block, processed as four groups of 32 envs.
 template <int R, int GE, int NBUF, bool BULK, bool FAITHFUL>
 __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st, ObsSlots sl, WallPlanes wp,
-                            float* __restrict__ obs, int total_channels, int cap) {
+                            const BoxRays* __restrict__ br, float* __restrict__ obs, int total_channels, int cap) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long bar;
   constexpr int D = 2 * R + 1, DD = D * D;
@@ -156,10 +127,9 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
   unsigned long long* s_wv = s_vis + OBS_ENVS * A;                                          // [32][A]
   Sprite* s_spr = reinterpret_cast<Sprite*>(s_wv + OBS_ENVS * A);                           // [32][cap]  one list per env
   int* s_cnt = reinterpret_cast<int*>(s_spr + (size_t)OBS_ENVS * cap);                      // [32] sprites emitted per env
-  // faithful mode only: (env, agent) pairs with a possible uid conflict -> exact path, packed
-  int* s_nconf = s_cnt + OBS_ENVS;                                                          // [1] (+ pad)
-  uint16_t* s_conf = reinterpret_cast<uint16_t*>(s_nconf + 4);                              // [32 * A]
-  uint8_t* s_rank = reinterpret_cast<uint8_t*>(s_conf + ((OBS_ENVS * A + 7) & ~7));         // [RANK_BUFS][RANK_STRIDE]
+  // faithful mode only: wall map and tile -> door map for the box-wide light-block tests of the rank computation
+  uint32_t* s_wall = reinterpret_cast<uint32_t*>(s_cnt + OBS_ENVS);
+  uint32_t* s_dmap = s_wall + ((sp->H * sp->W + 3) >> 2);
 
   // ---- stage the positional prefix of this block: one TMA bulk copy (dirt/item/.../agent positions, door + dest masks)
   if (threadIdx.x == 0) {
@@ -167,6 +137,12 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(&bar)), "r"((uint32_t)sl.prefix_bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(s_blk)),
                  "l"(st.base_i + (size_t)blockIdx.x * st.blk_i), "r"((uint32_t)sl.prefix_bytes), "r"(smem_u32(&bar)) : "memory");
+  }
+  if (FAITHFUL) {
+    const int HW4 = (sp->H * sp->W + 3) >> 2;
+    const uint32_t* gw = reinterpret_cast<const uint32_t*>(tb.wall);
+    const uint32_t* gd = reinterpret_cast<const uint32_t*>(tb.door_map);
+    for (int i = threadIdx.x; i < HW4; i += blockDim.x) { s_wall[i] = gw[i]; s_dmap[i] = gd[i]; }
   }
   __syncthreads();
   mbar_wait0(&bar);
@@ -178,7 +154,6 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
   const uint16_t* blk_dirt_uid = reinterpret_cast<const uint16_t*>(s_blk + sl.off_dirt_uid);
 
   if (warp == 0) s_cnt[lane] = 0;
-  if (threadIdx.x == 0) s_nconf[0] = 0;
   int buf = 0;
   for (int grp = 0; grp < ENV_BLOCK / OBS_ENVS; ++grp) {
     const int64_t env0 = blk0 + (int64_t)grp * OBS_ENVS;
@@ -219,21 +194,61 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
           vis = march<R>(B);
           wv = W49 & vis;
 
+          // ---- faithful mode: among the visible LISTED entities that share a uid only the one the
+          // rays visit first survives `set(visible_entities)`.  Conflicts need two listed entities with one uid inside the
+          // radius-D box; they are detected with a bitmap over uid < 64 (same-class entities never share a uid) plus a
+          // wall look-up, and only then the first-visit order of the cells involved is derived from the ray tables.
+          unsigned long long dup = 0ull;
+          const uint8_t* wall8 = reinterpret_cast<const uint8_t*>(s_wall);
+          const uint8_t* dmap8 = reinterpret_cast<const uint8_t*>(s_dmap);
+          auto blocks = [&](int dx, int dy) -> bool {              // blocks_light at an offset from the agent
+            const int x = ax + dx, y = ay + dy;
+            if (x < 0 || y < 0 || x >= sp->H || y >= sp->W) return false;
+            const int t = x * sp->W + y;
+            if (wall8[t]) return true;
+            const int d = dmap8[t];
+            return d != 0xFF && !((dopen >> d) & 1) && ((dlisted >> d) & 1);
+          };
+          // first-visit key of a box cell: (ray, step) of the first ray, in the reference's ray order, that reaches it
+          auto rank_of = [&](uint16_t q) -> int {
+            const int bx = px(q) - ax, by = py(q) - ay;
+            if (bx < -D || bx > D || by < -D || by > D) return 0x7FFF;
+            const int ci = (bx + D) * (2 * D + 1) + (by + D);
+            for (int v = br->cell_off[ci]; v < br->cell_off[ci + 1]; ++v) {
+              const int ray = br->cell_ray[v], stp = br->cell_step[v];
+              int pxo = 0, pyo = 0;
+              bool reached = false;
+              for (int t = 0; t <= stp; ++t) {
+                const int dx = br->dx[ray][t], dy = br->dy[ray][t];
+                const int cx = dx - pxo, cy = dy - pyo;
+                const bool diag = (cx != 0 && cy != 0) && blocks(dx, dy - cy) && blocks(dx - cx, dy);
+                if (t == stp) { reached = !diag; break; }
+                if (diag || blocks(dx, dy)) break;
+                pxo = dx; pyo = dy;
+              }
+              if (reached) return ray * 16 + stp;
+            }
+            return 0x7FFF;
+          };
+          auto wall_rival = [&](int uid) -> bool {                   // is the wall with this uid inside the box?
+            if (uid >= sp->n_walls) return false;
+            const uint16_t w = tb.wall_pos[uid];
+            const int wx = px(w) - ax, wy = py(w) - ay;
+            return wx >= -D && wx <= D && wy >= -D && wy <= D;
+          };
           if (FAITHFUL) {
-            // Conservative uid-conflict test: two LISTED entities with the same uid inside the
-            // radius-D box around the agent (a superset of everything a ray can reach).  Same-class entities never
-            // share a uid, so a repeated uid < 64 among the dynamic entities, or a wall with that uid inside the box,
-            // means "maybe".  Such (env, agent) pairs are resolved exactly afterwards, packed into one warp.
-            bool conflict = false;
             unsigned long long seen = 0ull;
             auto touch = [&](int uid, uint16_t q) {
               const int dx = px(q) - ax, dy = py(q) - ay;
               if (dx < -D || dx > D || dy < -D || dy > D) return;
-              if (uid < 64) { conflict |= ((seen >> uid) & 1ull) != 0; seen |= 1ull << uid; }
-              if (uid < sp->n_walls) {
+              if (uid < 64) { dup |= seen & (1ull << uid); seen |= 1ull << uid; }
+              if (wall_rival(uid)) {
+                // a visible wall inside the window loses its plane entry if this entity is visited before it
                 const uint16_t w = tb.wall_pos[uid];
-                const int wx = px(w) - ax, wy = py(w) - ay;
-                conflict |= wx >= -D && wx <= D && wy >= -D && wy <= D;
+                const int wx = px(w) - ax + R, wy = py(w) - ay + R;
+                if ((unsigned)wx < (unsigned)D && (unsigned)wy < (unsigned)D && ((wv >> (wx * D + wy)) & 1) &&
+                    rank_of(q) < rank_of(w))
+                  wv &= ~(1ull << (wx * D + wy));
               }
             };
             for (int d = 0; d < sp->n_doors; ++d) if ((dlisted >> d) & 1) touch(d, tb.door_pos[d]);
@@ -251,13 +266,31 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
                   if (q != NO_POS && ((glisted[g] >> (s - lo[g])) & 1)) touch(s - lo[g], q);
                 }
             }
-            if (conflict) {
-              s_conf[atomicAdd(s_nconf, 1)] = (uint16_t)(lane * A + a);
-              s_vis[lane * A + a] = vis;
-              s_wv[lane * A + a] = 0ull;            // filled in by the exact path
-              continue;
-            }
           }
+          // is the listed, visible entity (class code, index, uid) at q preceded by another visible listed entity of the
+          // same uid?  class codes: 0 door, 1 dirt, 2.. = small group g + 2
+          auto shadowed = [&](int cls, int idx, int uid, uint16_t q) -> bool {
+            if (!FAITHFUL) return false;
+            const bool maybe = (uid < 64 && ((dup >> uid) & 1)) || wall_rival(uid);
+            if (!maybe) return false;
+            const int my = rank_of(q);
+            if (wall_rival(uid) && rank_of(tb.wall_pos[uid]) < my) return true;
+            if (cls != 0 && uid < sp->n_doors && ((dlisted >> uid) & 1) && rank_of(tb.door_pos[uid]) < my) return true;
+            for (int k = 0; k < sl.item0; ++k) {
+              if (cls == 1 && k == idx) continue;
+              const uint16_t p2 = pos[k];
+              if (p2 != NO_POS && ((dirtlisted >> k) & 1) && blk_dirt_uid[k * ENV_BLOCK + eb] == uid && rank_of(p2) < my) return true;
+            }
+            const int lo[6] = {sl.item0, sl.pod0, sl.dest0, sl.drop0, sl.mach0, sl.maint0};
+            const int hi[6] = {sl.pod0, sl.dest0, sl.drop0, sl.mach0, sl.maint0, sl.agent0};
+#pragma unroll
+            for (int g = 0; g < 6; ++g) {
+              if (cls == g + 2 || uid >= hi[g] - lo[g] || !((glisted[g] >> uid) & 1)) continue;
+              const uint16_t p2 = pos[lo[g] + uid];
+              if (p2 != NO_POS && rank_of(p2) < my) return true;
+            }
+            return false;
+          };
 
           const uint32_t* chm = sp->term_chmask[a];
           const int coff = sp->ch_offset[a];
@@ -301,7 +334,7 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
                 if (q == NO_POS || !((glisted[g] >> (s - lo[g])) & 1)) continue;
                 if (g == 2 && ((reached >> (s - lo[g])) & 1)) continue;      // a reached destination encodes as 0
                 const int cell = cell_of(q);
-                if (cell >= 0) emit(m, cell, SK_INT, 0, g == 4 ? (float)ENC_MACHINE : 1.0f);
+                if (cell >= 0 && !shadowed(g + 2, s - lo[g], s - lo[g], q)) emit(m, cell, SK_INT, 0, g == 4 ? (float)ENC_MACHINE : 1.0f);
               }
             }
           }
@@ -310,7 +343,7 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
             for (int d = 0; d < sp->n_doors; ++d) {
               if (!((dlisted >> d) & 1)) continue;
               const int cell = cell_of(tb.door_pos[d]);
-              if (cell >= 0) emit(chm[MFG_G_DOORS], cell, SK_DOOR, (uint32_t)((dopen >> d) & 1), 0.f);
+              if (cell >= 0 && !shadowed(0, d, d, tb.door_pos[d])) emit(chm[MFG_G_DOORS], cell, SK_DOOR, (uint32_t)((dopen >> d) & 1), 0.f);
             }
           }
           // dirt piles
@@ -319,7 +352,7 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
               const uint16_t q = pos[k];
               if (q == NO_POS || !((dirtlisted >> k) & 1)) continue;
               const int cell = cell_of(q);
-              if (cell >= 0) emit(chm[MFG_G_DIRT], cell, SK_DIRT, (uint32_t)k, 0.f);
+              if (cell >= 0 && !shadowed(1, k, blk_dirt_uid[k * ENV_BLOCK + eb], q)) emit(chm[MFG_G_DIRT], cell, SK_DIRT, (uint32_t)k, 0.f);
             }
           }
           // scalar channels
@@ -339,22 +372,6 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
       }
     }
     __syncthreads();
-
-    // ---------------- phase 1b (faithful): exact resolution of the conflicted pairs, packed into the first lanes ---
-    if (FAITHFUL) {
-      const int nconf = s_nconf[0];
-      for (int base = 0; base < nconf; base += RANK_BUFS) {
-        const int i = base + (int)threadIdx.x;
-        if ((int)threadIdx.x < RANK_BUFS && i < nconf) {
-          const int pair = s_conf[i], el = pair / A, a = pair - el * A;
-          SpriteSink sink{s_spr + (size_t)el * cap, s_cnt + el, cap, sp->ch_offset[a], DD, 0ull};
-          exact_agent_sprites(sp, tb, st, env0 + el, a, s_rank + threadIdx.x * RANK_STRIDE, sink);
-          s_wv[el * A + a] = sink.wv;
-        }
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) s_nconf[0] = 0;       // next group's phase 1 only starts after the loop-top barrier
-    }
 
     // ---------------- phase 2: one warp per tile of GE envs ------------------------------------------------------
     const int n_tiles = OBS_ENVS / GE;
@@ -589,7 +606,7 @@ void plan_obs(MfgHandle* h) {
     b += (size_t)OBS_ENVS * sp.n_agents * 8 * 2;                           // vis, wv
     b += (size_t)OBS_ENVS * p.cap * 8;                                     // sprites (one list per env)
     b += OBS_ENVS * 4;                                                     // cnt
-    b += 16 + (size_t)((OBS_ENVS * sp.n_agents + 7) & ~7) * 2 + (size_t)RANK_BUFS * RANK_STRIDE;   // conflict list, rank tables
+    if (sp.faithful) b += 2 * (((size_t)sp.H * sp.W + 3) / 4 * 4) + 16;    // wall map + door map for the rank computation
     b += (size_t)sl.prefix_bytes + 32;                                     // staged block prefix
     return b;
   };
@@ -599,6 +616,39 @@ void plan_obs(MfgHandle* h) {
   build_window_rays(sp, wr);
   bool trie_ok = sp.pomdp_r == 1 ? trie_matches<1>(wr) : sp.pomdp_r == 2 ? trie_matches<2>(wr)
                : sp.pomdp_r == 3 ? trie_matches<3>(wr) : false;
+  // full rays per box cell, in visit order, for the faithful first-visit ranks
+  if (sp.faithful && !p.d_box_rays) {
+    BoxRays host{};
+    const int D = 2 * sp.pomdp_r + 1, BW = 2 * D + 1;
+    host.n_rays = sp.n_rays;
+    std::vector<std::vector<std::pair<int, int>>> per_cell(BW * BW);
+    bool fits = sp.n_rays <= 64;
+    for (int r = 0; r < sp.n_rays && fits; ++r) {
+      host.len[r] = (uint8_t)sp.ray_len[r];
+      if (sp.ray_len[r] > 16) { fits = false; break; }
+      for (int t = 0; t < sp.ray_len[r]; ++t) {
+        const int dx = sp.ray_dx[r][t], dy = sp.ray_dy[r][t];
+        host.dx[r][t] = (int8_t)dx; host.dy[r][t] = (int8_t)dy;
+        if (dx < -D || dx > D || dy < -D || dy > D) { fits = false; break; }
+        per_cell[(dx + D) * BW + (dy + D)].emplace_back(r, t);
+      }
+    }
+    int off = 0;
+    for (int c = 0; c < BW * BW && fits; ++c) {
+      host.cell_off[c] = (uint16_t)off;
+      for (auto& rt : per_cell[c]) {
+        if (off >= 512) { fits = false; break; }
+        host.cell_ray[off] = (uint8_t)rt.first; host.cell_step[off] = (uint8_t)rt.second; ++off;
+      }
+    }
+    host.cell_off[BW * BW] = (uint16_t)off;
+    void* d = nullptr;
+    if (fits && cudaMalloc(&d, sizeof(BoxRays)) == cudaSuccess) {
+      h->dev_allocs.push_back(d);
+      cudaMemcpy(d, &host, sizeof(BoxRays), cudaMemcpyHostToDevice);
+      p.d_box_rays = static_cast<BoxRays*>(d);
+    }
+  }
   // wall planes: (agent, packed channel) of every channel that contains Walls
   p.walls.n = 0;
   bool walls_fit = true;
@@ -610,19 +660,19 @@ void plan_obs(MfgHandle* h) {
         p.walls.plane[p.walls.n] = (uint16_t)(sp.ch_offset[a] + c);
         p.walls.n++;
       }
-  p.ok = trie_ok && walls_fit && p.smem <= 200 * 1024 && tcdd * p.ge <= 0xFFFF;
+  p.ok = trie_ok && walls_fit && p.smem <= 200 * 1024 && tcdd * p.ge <= 0xFFFF && (!sp.faithful || p.d_box_rays);
 }
 
 template <int R, int GE, int NBUF, bool BULK, bool FAITHFUL>
 static cudaError_t launch_tiled_f(MfgHandle* h, float* d_obs, cudaStream_t s) {
   auto kern = k_obs_tiled<R, GE, NBUF, BULK, FAITHFUL>;
   const ObsPlan& p = h->plan;
-  if (p.smem > 48 * 1024) {
+  if (p.smem > 40 * 1024) {         // (static shared memory counts against the 48 KB default limit too)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return e;
   }
   const unsigned blocks = (unsigned)((h->N + ENV_BLOCK - 1) / ENV_BLOCK);
-  kern<<<blocks, p.nw * 32, p.smem, s>>>(h->d_sp, h->tb, h->st, p.slots, p.walls, d_obs, h->total_channels, p.cap);
+  kern<<<blocks, p.nw * 32, p.smem, s>>>(h->d_sp, h->tb, h->st, p.slots, p.walls, p.d_box_rays, d_obs, h->total_channels, p.cap);
   return cudaGetLastError();
 }
 
