@@ -110,6 +110,7 @@ struct Tables {
   const uint16_t* door_pos;    // [ND] pos16
   const uint8_t* nexthop;      // [F*F] or null
   const uint64_t* wall_win;    // [H*W] (2r+1)^2-bit wall mask of the window centred on the tile (r <= 3)
+  const uint64_t* wall_box;    // [H*W][4] wall mask of the (2D+1)^2 box (D = 2r+1) centred on the tile, bit = (dx+D)*(2D+1)+(dy+D)
   int64_t env_id_offset;
   unsigned long long* stats;   // [MFG_N_STATS]
 };

@@ -74,7 +74,7 @@ inline void bind_state(const MfgSpec& sp, int64_t N, void* base, State& st) {
 struct HostTables {
   std::vector<uint8_t> wall, door_map, nexthop;
   std::vector<uint16_t> floor_pos, floor_index, wall_uid, wall_pos, door_pos;
-  std::vector<uint64_t> wall_win;
+  std::vector<uint64_t> wall_win, wall_box;
 };
 
 inline std::string build_tables(const MfgSpec& sp, HostTables& t) {
@@ -124,6 +124,21 @@ inline std::string build_tables(const MfgSpec& sp, HostTables& t) {
           }
         t.wall_win[(size_t)x * W + y] = m;
       }
+  }
+  // per-tile wall masks of the radius-D box (faithful observation mode: first-visit order over the full rays)
+  t.wall_box.assign((size_t)H * W * 4, 0);
+  if (r >= 1 && r <= 3) {
+    const int BW = 2 * D + 1;
+    for (int x = 0; x < H; ++x)
+      for (int y = 0; y < W; ++y)
+        for (int dx = -D; dx <= D; ++dx)
+          for (int dy = -D; dy <= D; ++dy) {
+            int xx = x + dx, yy = y + dy;
+            if (xx >= 0 && yy >= 0 && xx < H && yy < W && t.wall[(size_t)xx * W + yy]) {
+              const int b = (dx + D) * BW + (dy + D);
+              t.wall_box[((size_t)x * W + y) * 4 + (b >> 6)] |= 1ull << (b & 63);
+            }
+          }
   }
   return "";
 }

@@ -34,15 +34,6 @@ struct WallPlanes {               // channels that contain Walls, as (agent, pla
   uint8_t agent[MAX_WALL_PLANES];
 };
 
-// full radius rays and, per cell of the (2D+1)^2 box around the agent, the (ray, step) visits in ray order
-struct BoxRays {
-  int n_rays;
-  uint8_t len[64];
-  int8_t dx[64][16], dy[64][16];
-  uint16_t cell_off[15 * 15 + 1];
-  uint8_t cell_ray[512], cell_step[512];
-};
-
 struct ObsPlan {
   bool ok = false;        // tiled kernel usable for this spec
   int ge = 1;             // envs per output tile (tile = whole number of 16-byte vectors)
@@ -51,7 +42,6 @@ struct ObsPlan {
   int cap = 48;           // sprite slots per env (all agents share one list)
   int cap_max = 48;
   WallPlanes walls{};
-  BoxRays* d_box_rays = nullptr;
   size_t smem = 0;
   ObsSlots slots{};
 };

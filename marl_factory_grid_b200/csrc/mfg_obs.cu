@@ -59,6 +59,42 @@ __device__ __forceinline__ unsigned long long march(const unsigned long long B) 
   return vis;
 }
 
+// faithful mode: the same march over the FULL radius-D rays (box mask of up to 225 bits in four words).  Besides the
+// window visibility it yields `vn`: one bit per trie node that was visited and not diagonally occluded.  Node ids are
+// in the reference's visit order, so the first-visit rank of a box cell is the lowest set node id among its nodes.
+template <int R, int n>
+__device__ __forceinline__ void full_step(const unsigned long long (&B)[4], unsigned long long& vis,
+                                          unsigned long long (&cont)[4], unsigned long long (&vn)[4]) {
+  using T = FullTrie<R>;
+  constexpr int p = T::parent(n), c = T::cell(n), da = T::da(n), db = T::db(n), wc = T::wcell(n);
+  constexpr int pw = p < 0 ? 0 : (p >> 6), pb = p < 0 ? 0 : (p & 63);
+  const bool reach = p < 0 ? true : (((cont[pw] >> pb) & 1ull) != 0);
+  const bool hits = (B[c >> 6] & (1ull << (c & 63))) != 0;
+  bool diag = false;
+  if constexpr (da != 255) diag = ((B[da >> 6] & (1ull << (da & 63))) != 0) && ((B[db >> 6] & (1ull << (db & 63))) != 0);
+  if (reach && !diag) {
+    vn[n >> 6] |= 1ull << (n & 63);
+    if constexpr (wc >= 0) vis |= 1ull << wc;
+  }
+  if (reach && !hits && !diag) cont[n >> 6] |= 1ull << (n & 63);
+}
+template <int R, int... I>
+__device__ __forceinline__ void full_march_impl(const unsigned long long (&B)[4], unsigned long long& vis,
+                                                unsigned long long (&cont)[4], unsigned long long (&vn)[4],
+                                                std::integer_sequence<int, I...>) {
+  (full_step<R, I>(B, vis, cont, vn), ...);
+}
+template <int R>
+__device__ __forceinline__ unsigned long long march_full(const unsigned long long (&B)[4], unsigned long long (&vn)[4]) {
+  constexpr int D = 2 * R + 1, BW = 2 * D + 1, origin = D * BW + D, centre = R * D + R;
+  unsigned long long vis = 1ull << centre;
+  unsigned long long cont[4] = {0ull, 0ull, 0ull, 0ull};
+  vn[0] = vn[1] = vn[2] = vn[3] = 0ull;
+  if (B[origin >> 6] & (1ull << (origin & 63))) return vis;
+  full_march_impl<R>(B, vis, cont, vn, std::make_integer_sequence<int, FullTrie<R>::N>());
+  return vis;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // sprites
 // ---------------------------------------------------------------------------------------------------------------
@@ -110,7 +146,7 @@ __device__ __forceinline__ void mbar_wait0(unsigned long long* bar) {
 // CTA = one 128-env state block, processed as four groups of 32 envs.
 template <int R, int GE, int NBUF, bool BULK, bool FAITHFUL>
 __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st, ObsSlots sl, WallPlanes wp,
-                            const BoxRays* __restrict__ br, float* __restrict__ obs, int total_channels, int cap) {
+                            float* __restrict__ obs, int total_channels, int cap) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long bar;
   constexpr int D = 2 * R + 1, DD = D * D;
@@ -127,22 +163,12 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
   unsigned long long* s_wv = s_vis + OBS_ENVS * A;                                          // [32][A]
   Sprite* s_spr = reinterpret_cast<Sprite*>(s_wv + OBS_ENVS * A);                           // [32][cap]  one list per env
   int* s_cnt = reinterpret_cast<int*>(s_spr + (size_t)OBS_ENVS * cap);                      // [32] sprites emitted per env
-  // faithful mode only: wall map and tile -> door map for the box-wide light-block tests of the rank computation
-  uint32_t* s_wall = reinterpret_cast<uint32_t*>(s_cnt + OBS_ENVS);
-  uint32_t* s_dmap = s_wall + ((sp->H * sp->W + 3) >> 2);
-
   // ---- stage the positional prefix of this block: one TMA bulk copy (dirt/item/.../agent positions, door + dest masks)
   if (threadIdx.x == 0) {
     mbar_init1(&bar);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(&bar)), "r"((uint32_t)sl.prefix_bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(s_blk)),
                  "l"(st.base_i + (size_t)blockIdx.x * st.blk_i), "r"((uint32_t)sl.prefix_bytes), "r"(smem_u32(&bar)) : "memory");
-  }
-  if (FAITHFUL) {
-    const int HW4 = (sp->H * sp->W + 3) >> 2;
-    const uint32_t* gw = reinterpret_cast<const uint32_t*>(tb.wall);
-    const uint32_t* gd = reinterpret_cast<const uint32_t*>(tb.door_map);
-    for (int i = threadIdx.x; i < HW4; i += blockDim.x) { s_wall[i] = gw[i]; s_dmap[i] = gd[i]; }
   }
   __syncthreads();
   mbar_wait0(&bar);
@@ -191,7 +217,26 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
             if (!((dopen >> d) & 1) && ((dlisted >> d) & 1) && (unsigned)dx < (unsigned)D && (unsigned)dy < (unsigned)D)
               B |= 1ull << (dx * D + dy);
           }
-          vis = march<R>(B);
+          unsigned long long vn[4] = {0ull, 0ull, 0ull, 0ull};
+          if (FAITHFUL) {
+            // box-wide light-block mask: walls from the per-tile table, closed listed doors added
+            constexpr int BW = 2 * D + 1;
+            const unsigned long long* wb = reinterpret_cast<const unsigned long long*>(tb.wall_box) + (size_t)(ax * sp->W + ay) * 4;
+            unsigned long long b0 = wb[0], b1 = wb[1], b2 = wb[2], b3 = wb[3];
+            for (int d = 0; d < sp->n_doors; ++d) {
+              const uint16_t q = tb.door_pos[d];
+              const int dx = px(q) - ax + D, dy = py(q) - ay + D;
+              if (!((dopen >> d) & 1) && ((dlisted >> d) & 1) && (unsigned)dx < (unsigned)BW && (unsigned)dy < (unsigned)BW) {
+                const int bi = dx * BW + dy, w = bi >> 6;
+                const unsigned long long bit = 1ull << (bi & 63);
+                b0 |= w == 0 ? bit : 0ull; b1 |= w == 1 ? bit : 0ull; b2 |= w == 2 ? bit : 0ull; b3 |= w == 3 ? bit : 0ull;
+              }
+            }
+            const unsigned long long BB[4] = {b0, b1, b2, b3};
+            vis = march_full<R>(BB, vn);
+          } else {
+            vis = march<R>(B);
+          }
           wv = W49 & vis;
 
           // ---- faithful mode: among the visible LISTED entities that share a uid only the one the
@@ -199,34 +244,17 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
           // radius-D box; they are detected with a bitmap over uid < 64 (same-class entities never share a uid) plus a
           // wall look-up, and only then the first-visit order of the cells involved is derived from the ray tables.
           unsigned long long dup = 0ull;
-          const uint8_t* wall8 = reinterpret_cast<const uint8_t*>(s_wall);
-          const uint8_t* dmap8 = reinterpret_cast<const uint8_t*>(s_dmap);
-          auto blocks = [&](int dx, int dy) -> bool {              // blocks_light at an offset from the agent
-            const int x = ax + dx, y = ay + dy;
-            if (x < 0 || y < 0 || x >= sp->H || y >= sp->W) return false;
-            const int t = x * sp->W + y;
-            if (wall8[t]) return true;
-            const int d = dmap8[t];
-            return d != 0xFF && !((dopen >> d) & 1) && ((dlisted >> d) & 1);
-          };
-          // first-visit key of a box cell: (ray, step) of the first ray, in the reference's ray order, that reaches it
+          // first-visit rank of a box cell = lowest visited node id among the cell's trie nodes (own tile comes first)
           auto rank_of = [&](uint16_t q) -> int {
+            constexpr int BW = 2 * D + 1;
             const int bx = px(q) - ax, by = py(q) - ay;
             if (bx < -D || bx > D || by < -D || by > D) return 0x7FFF;
-            const int ci = (bx + D) * (2 * D + 1) + (by + D);
-            for (int v = br->cell_off[ci]; v < br->cell_off[ci + 1]; ++v) {
-              const int ray = br->cell_ray[v], stp = br->cell_step[v];
-              int pxo = 0, pyo = 0;
-              bool reached = false;
-              for (int t = 0; t <= stp; ++t) {
-                const int dx = br->dx[ray][t], dy = br->dy[ray][t];
-                const int cx = dx - pxo, cy = dy - pyo;
-                const bool diag = (cx != 0 && cy != 0) && blocks(dx, dy - cy) && blocks(dx - cx, dy);
-                if (t == stp) { reached = !diag; break; }
-                if (diag || blocks(dx, dy)) break;
-                pxo = dx; pyo = dy;
-              }
-              if (reached) return ray * 16 + stp;
+            if (bx == 0 && by == 0) return -1;
+            const int ci = (bx + D) * BW + (by + D);
+            for (int i = FullTrie<R>::cell_off(ci); i < FullTrie<R>::cell_off(ci + 1); ++i) {
+              const int n = FullTrie<R>::cell_node(i), w = n >> 6;
+              const unsigned long long word = w == 0 ? vn[0] : w == 1 ? vn[1] : w == 2 ? vn[2] : vn[3];
+              if ((word >> (n & 63)) & 1ull) return n;
             }
             return 0x7FFF;
           };
@@ -276,8 +304,7 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
             const int my = rank_of(q);
             if (wall_rival(uid) && rank_of(tb.wall_pos[uid]) < my) return true;
             if (cls != 0 && uid < sp->n_doors && ((dlisted >> uid) & 1) && rank_of(tb.door_pos[uid]) < my) return true;
-            for (int k = 0; k < sl.item0; ++k) {
-              if (cls == 1 && k == idx) continue;
+            for (int k = 0; k < sl.item0 && uid < 64 && cls != 1; ++k) {     // dirt uids are unique among dirt piles
               const uint16_t p2 = pos[k];
               if (p2 != NO_POS && ((dirtlisted >> k) & 1) && blk_dirt_uid[k * ENV_BLOCK + eb] == uid && rank_of(p2) < my) return true;
             }
@@ -558,6 +585,40 @@ static bool trie_matches(const WindowRays& wr) {
   return wr.n > 0;
 }
 
+// the generated full-radius trie must describe exactly the spec's rays (origin cell excluded), in the same order
+template <int R>
+static bool full_trie_matches(const MfgSpec& sp) {
+  using T = FullTrie<R>;
+  const int D = 2 * R + 1, BW = 2 * D + 1;
+  std::vector<int> used(T::N, 0);
+  int next_new = 0;
+  for (int k = 0; k < sp.n_rays; ++k) {
+    int parent = -1, pxo = 0, pyo = 0;
+    for (int s = 1; s < sp.ray_len[k]; ++s) {
+      const int dx = sp.ray_dx[k][s], dy = sp.ray_dy[k][s];
+      if (dx < -D || dx > D || dy < -D || dy > D) return false;
+      const int cx = dx - pxo, cy = dy - pyo;
+      const int cell = (dx + D) * BW + (dy + D);
+      const int da = (cx && cy) ? (dx + D) * BW + (dy - cy + D) : 255, db = (cx && cy) ? (dx - cx + D) * BW + (dy + D) : 255;
+      const int wc = (dx >= -R && dx <= R && dy >= -R && dy <= R) ? (dx + R) * D + (dy + R) : -1;
+      int found = -1;
+      for (int n = 0; n < T::N; ++n)
+        if (T::parent(n) == parent && T::cell(n) == cell && T::da(n) == da && T::db(n) == db && T::wcell(n) == wc) found = n;
+      if (found < 0) return false;
+      if (!used[found]) { if (found != next_new) return false; ++next_new; }     // node ids follow first-visit order
+      used[found] = 1;
+      parent = found; pxo = dx; pyo = dy;
+    }
+  }
+  for (int n = 0; n < T::N; ++n) {
+    if (!used[n]) return false;
+    bool listed = false;
+    for (int i = T::cell_off(T::cell(n)); i < T::cell_off(T::cell(n) + 1); ++i) listed |= T::cell_node(i) == n;
+    if (!listed) return false;
+  }
+  return true;
+}
+
 void plan_obs(MfgHandle* h) {
   const MfgSpec& sp = h->sp;
   ObsPlan& p = h->plan;
@@ -606,7 +667,6 @@ void plan_obs(MfgHandle* h) {
     b += (size_t)OBS_ENVS * sp.n_agents * 8 * 2;                           // vis, wv
     b += (size_t)OBS_ENVS * p.cap * 8;                                     // sprites (one list per env)
     b += OBS_ENVS * 4;                                                     // cnt
-    if (sp.faithful) b += 2 * (((size_t)sp.H * sp.W + 3) / 4 * 4) + 16;    // wall map + door map for the rank computation
     b += (size_t)sl.prefix_bytes + 32;                                     // staged block prefix
     return b;
   };
@@ -616,39 +676,6 @@ void plan_obs(MfgHandle* h) {
   build_window_rays(sp, wr);
   bool trie_ok = sp.pomdp_r == 1 ? trie_matches<1>(wr) : sp.pomdp_r == 2 ? trie_matches<2>(wr)
                : sp.pomdp_r == 3 ? trie_matches<3>(wr) : false;
-  // full rays per box cell, in visit order, for the faithful first-visit ranks
-  if (sp.faithful && !p.d_box_rays) {
-    BoxRays host{};
-    const int D = 2 * sp.pomdp_r + 1, BW = 2 * D + 1;
-    host.n_rays = sp.n_rays;
-    std::vector<std::vector<std::pair<int, int>>> per_cell(BW * BW);
-    bool fits = sp.n_rays <= 64;
-    for (int r = 0; r < sp.n_rays && fits; ++r) {
-      host.len[r] = (uint8_t)sp.ray_len[r];
-      if (sp.ray_len[r] > 16) { fits = false; break; }
-      for (int t = 0; t < sp.ray_len[r]; ++t) {
-        const int dx = sp.ray_dx[r][t], dy = sp.ray_dy[r][t];
-        host.dx[r][t] = (int8_t)dx; host.dy[r][t] = (int8_t)dy;
-        if (dx < -D || dx > D || dy < -D || dy > D) { fits = false; break; }
-        per_cell[(dx + D) * BW + (dy + D)].emplace_back(r, t);
-      }
-    }
-    int off = 0;
-    for (int c = 0; c < BW * BW && fits; ++c) {
-      host.cell_off[c] = (uint16_t)off;
-      for (auto& rt : per_cell[c]) {
-        if (off >= 512) { fits = false; break; }
-        host.cell_ray[off] = (uint8_t)rt.first; host.cell_step[off] = (uint8_t)rt.second; ++off;
-      }
-    }
-    host.cell_off[BW * BW] = (uint16_t)off;
-    void* d = nullptr;
-    if (fits && cudaMalloc(&d, sizeof(BoxRays)) == cudaSuccess) {
-      h->dev_allocs.push_back(d);
-      cudaMemcpy(d, &host, sizeof(BoxRays), cudaMemcpyHostToDevice);
-      p.d_box_rays = static_cast<BoxRays*>(d);
-    }
-  }
   // wall planes: (agent, packed channel) of every channel that contains Walls
   p.walls.n = 0;
   bool walls_fit = true;
@@ -660,7 +687,9 @@ void plan_obs(MfgHandle* h) {
         p.walls.plane[p.walls.n] = (uint16_t)(sp.ch_offset[a] + c);
         p.walls.n++;
       }
-  p.ok = trie_ok && walls_fit && p.smem <= 200 * 1024 && tcdd * p.ge <= 0xFFFF && (!sp.faithful || p.d_box_rays);
+  bool full_ok = !sp.faithful || (sp.pomdp_r == 1 ? full_trie_matches<1>(sp) : sp.pomdp_r == 2 ? full_trie_matches<2>(sp)
+                                  : sp.pomdp_r == 3 ? full_trie_matches<3>(sp) : false);
+  p.ok = trie_ok && full_ok && walls_fit && p.smem <= 200 * 1024 && tcdd * p.ge <= 0xFFFF;
 }
 
 template <int R, int GE, int NBUF, bool BULK, bool FAITHFUL>
@@ -672,7 +701,7 @@ static cudaError_t launch_tiled_f(MfgHandle* h, float* d_obs, cudaStream_t s) {
     if (e != cudaSuccess) return e;
   }
   const unsigned blocks = (unsigned)((h->N + ENV_BLOCK - 1) / ENV_BLOCK);
-  kern<<<blocks, p.nw * 32, p.smem, s>>>(h->d_sp, h->tb, h->st, p.slots, p.walls, p.d_box_rays, d_obs, h->total_channels, p.cap);
+  kern<<<blocks, p.nw * 32, p.smem, s>>>(h->d_sp, h->tb, h->st, p.slots, p.walls, d_obs, h->total_channels, p.cap);
   return cudaGetLastError();
 }
 
