@@ -42,6 +42,8 @@ int mfg_create(const MfgSpec* spec, int64_t n_envs, int64_t env_id_offset, MfgHa
   err = build_tables(*spec, ht);
   if (!err.empty()) return fail(MFG_E_INVALID, "mfg_create: " + err);
 
+  build_vis_tables(*spec, ht);
+
   MfgHandle* h = new MfgHandle();
   h->sp = *spec;
   h->sp.walls = nullptr; h->sp.floor_pos = nullptr; h->sp.door_pos = nullptr; h->sp.nexthop = nullptr;
@@ -49,6 +51,7 @@ int mfg_create(const MfgSpec* spec, int64_t n_envs, int64_t env_id_offset, MfgHa
   int rc;
 #define UP(field) if ((rc = upload(h, ht.field, &h->tb.field)) != MFG_OK) { mfg_destroy(h); return rc; }
   UP(wall) UP(door_map) UP(floor_pos) UP(floor_index) UP(wall_uid) UP(wall_pos) UP(door_pos) UP(nexthop) UP(wall_win) UP(wall_box)
+  UP(vis_box) UP(wall_cand64) UP(wall_cand_rng)
 #undef UP
   h->tb.env_id_offset = env_id_offset;
   void* d = nullptr;

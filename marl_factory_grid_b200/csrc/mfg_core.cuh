@@ -111,6 +111,10 @@ struct Tables {
   const uint8_t* nexthop;      // [F*F] or null
   const uint64_t* wall_win;    // [H*W] (2r+1)^2-bit wall mask of the window centred on the tile (r <= 3)
   const uint64_t* wall_box;    // [H*W][4] wall mask of the (2D+1)^2 box (D = 2r+1) centred on the tile, bit = (dx+D)*(2D+1)+(dy+D)
+  // faithful observation mode (built by build_vis_tables, mfg_obs.cu): static walls-only visibility
+  const uint64_t* vis_box;       // [H*W][4] box cells some full ray reaches when only walls block light (superset of the truth)
+  const uint64_t* wall_cand64;   // [H*W] bit u: wall with uid u < 64 lies on such a cell
+  const uint32_t* wall_cand_rng; // [H*W] lo | hi << 16: range of the wall uids >= 64 on such cells (lo > hi: none)
   int64_t env_id_offset;
   unsigned long long* stats;   // [MFG_N_STATS]
 };

@@ -74,7 +74,8 @@ inline void bind_state(const MfgSpec& sp, int64_t N, void* base, State& st) {
 struct HostTables {
   std::vector<uint8_t> wall, door_map, nexthop;
   std::vector<uint16_t> floor_pos, floor_index, wall_uid, wall_pos, door_pos;
-  std::vector<uint64_t> wall_win, wall_box;
+  std::vector<uint64_t> wall_win, wall_box, vis_box, wall_cand64;
+  std::vector<uint32_t> wall_cand_rng;
 };
 
 inline std::string build_tables(const MfgSpec& sp, HostTables& t) {

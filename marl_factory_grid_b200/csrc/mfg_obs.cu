@@ -59,40 +59,39 @@ __device__ __forceinline__ unsigned long long march(const unsigned long long B) 
   return vis;
 }
 
-// faithful mode: the same march over the FULL radius-D rays (box mask of up to 225 bits in four words).  Besides the
-// window visibility it yields `vn`: one bit per trie node that was visited and not diagonally occluded.  Node ids are
-// in the reference's visit order, so the first-visit rank of a box cell is the lowest set node id among its nodes.
-template <int R, int n>
-__device__ __forceinline__ void full_step(const unsigned long long (&B)[4], unsigned long long& vis,
-                                          unsigned long long (&cont)[4], unsigned long long (&vn)[4]) {
-  using T = FullTrie<R>;
-  constexpr int p = T::parent(n), c = T::cell(n), da = T::da(n), db = T::db(n), wc = T::wcell(n);
-  constexpr int pw = p < 0 ? 0 : (p >> 6), pb = p < 0 ? 0 : (p & 63);
-  const bool reach = p < 0 ? true : (((cont[pw] >> pb) & 1ull) != 0);
-  const bool hits = (B[c >> 6] & (1ull << (c & 63))) != 0;
-  bool diag = false;
-  if constexpr (da != 255) diag = ((B[da >> 6] & (1ull << (da & 63))) != 0) && ((B[db >> 6] & (1ull << (db & 63))) != 0);
-  if (reach && !diag) {
-    vn[n >> 6] |= 1ull << (n & 63);
-    if constexpr (wc >= 0) vis |= 1ull << wc;
-  }
-  if (reach && !hits && !diag) cont[n >> 6] |= 1ull << (n & 63);
-}
-template <int R, int... I>
-__device__ __forceinline__ void full_march_impl(const unsigned long long (&B)[4], unsigned long long& vis,
-                                                unsigned long long (&cont)[4], unsigned long long (&vn)[4],
-                                                std::integer_sequence<int, I...>) {
-  (full_step<R, I>(B, vis, cont, vn), ...);
-}
+// faithful mode: first-visit rank (= trie node id, the reference's visit order) of one cell of the radius-D box, or
+// 0x7FFF when no ray reaches it.  b0..b3 = light-block mask of the (2D+1)^2 box.  Only the trie paths that end in this
+// cell are walked: a node is visited iff every ancestor is visited and passable and the node is not diagonally occluded
+// (ray_caster.py:81-103).
 template <int R>
-__device__ __forceinline__ unsigned long long march_full(const unsigned long long (&B)[4], unsigned long long (&vn)[4]) {
-  constexpr int D = 2 * R + 1, BW = 2 * D + 1, origin = D * BW + D, centre = R * D + R;
-  unsigned long long vis = 1ull << centre;
-  unsigned long long cont[4] = {0ull, 0ull, 0ull, 0ull};
-  vn[0] = vn[1] = vn[2] = vn[3] = 0ull;
-  if (B[origin >> 6] & (1ull << (origin & 63))) return vis;
-  full_march_impl<R>(B, vis, cont, vn, std::make_integer_sequence<int, FullTrie<R>::N>());
-  return vis;
+__device__ __noinline__ int first_visit_rank(unsigned long long b0, unsigned long long b1, unsigned long long b2,
+                                             unsigned long long b3, int bx, int by) {
+  using T = FullTrie<R>;
+  constexpr int D = 2 * R + 1, BW = 2 * D + 1, origin = D * BW + D;
+  if (bx < -D || bx > D || by < -D || by > D) return 0x7FFF;
+  if (bx == 0 && by == 0) return -1;                                      // the own tile comes first
+  auto blk = [&](int ci) -> bool {
+    const int w = ci >> 6;
+    const unsigned long long word = w == 0 ? b0 : w == 1 ? b1 : w == 2 ? b2 : b3;
+    return ((word >> (ci & 63)) & 1ull) != 0;
+  };
+  if (blk(origin)) return 0x7FFF;                                         // inside a closed door: only the own tile
+  const int ci = (bx + D) * BW + (by + D);
+  for (int i = T::cell_off(ci); i < T::cell_off(ci + 1); ++i) {
+    const int n = T::cell_node(i);
+    uint32_t rec = T::node(n);
+    int da = (rec >> 16) & 255, db = rec >> 24;
+    bool ok = !(da != 255 && blk(da) && blk(db));
+    int p = rec & 255;
+    while (ok && p != 255) {
+      rec = T::node(p);
+      da = (rec >> 16) & 255; db = rec >> 24;
+      ok = !blk((rec >> 8) & 255) && !(da != 255 && blk(da) && blk(db));
+      p = rec & 255;
+    }
+    if (ok) return n;
+  }
+  return 0x7FFF;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -217,107 +216,121 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
             if (!((dopen >> d) & 1) && ((dlisted >> d) & 1) && (unsigned)dx < (unsigned)D && (unsigned)dy < (unsigned)D)
               B |= 1ull << (dx * D + dy);
           }
-          unsigned long long vn[4] = {0ull, 0ull, 0ull, 0ull};
-          if (FAITHFUL) {
-            // box-wide light-block mask: walls from the per-tile table, closed listed doors added
-            constexpr int BW = 2 * D + 1;
-            const unsigned long long* wb = reinterpret_cast<const unsigned long long*>(tb.wall_box) + (size_t)(ax * sp->W + ay) * 4;
-            unsigned long long b0 = wb[0], b1 = wb[1], b2 = wb[2], b3 = wb[3];
-            for (int d = 0; d < sp->n_doors; ++d) {
-              const uint16_t q = tb.door_pos[d];
-              const int dx = px(q) - ax + D, dy = py(q) - ay + D;
-              if (!((dopen >> d) & 1) && ((dlisted >> d) & 1) && (unsigned)dx < (unsigned)BW && (unsigned)dy < (unsigned)BW) {
-                const int bi = dx * BW + dy, w = bi >> 6;
-                const unsigned long long bit = 1ull << (bi & 63);
-                b0 |= w == 0 ? bit : 0ull; b1 |= w == 1 ? bit : 0ull; b2 |= w == 2 ? bit : 0ull; b3 |= w == 3 ? bit : 0ull;
-              }
-            }
-            const unsigned long long BB[4] = {b0, b1, b2, b3};
-            vis = march_full<R>(BB, vn);
-          } else {
-            vis = march<R>(B);
-          }
+          vis = march<R>(B);
           wv = W49 & vis;
 
           // ---- faithful mode: among the visible LISTED entities that share a uid only the one the
-          // rays visit first survives `set(visible_entities)`.  Conflicts need two listed entities with one uid inside the
-          // radius-D box; they are detected with a bitmap over uid < 64 (same-class entities never share a uid) plus a
-          // wall look-up, and only then the first-visit order of the cells involved is derived from the ray tables.
-          unsigned long long dup = 0ull;
-          // first-visit rank of a box cell = lowest visited node id among the cell's trie nodes (own tile comes first)
-          auto rank_of = [&](uint16_t q) -> int {
-            constexpr int BW = 2 * D + 1;
-            const int bx = px(q) - ax, by = py(q) - ay;
-            if (bx < -D || bx > D || by < -D || by > D) return 0x7FFF;
-            if (bx == 0 && by == 0) return -1;
-            const int ci = (bx + D) * BW + (by + D);
-            for (int i = FullTrie<R>::cell_off(ci); i < FullTrie<R>::cell_off(ci + 1); ++i) {
-              const int n = FullTrie<R>::cell_node(i), w = n >> 6;
-              const unsigned long long word = w == 0 ? vn[0] : w == 1 ? vn[1] : w == 2 ? vn[2] : vn[3];
-              if ((word >> (n & 63)) & 1ull) return n;
-            }
-            return 0x7FFF;
-          };
-          auto wall_rival = [&](int uid) -> bool {                   // is the wall with this uid inside the box?
-            if (uid >= sp->n_walls) return false;
-            const uint16_t w = tb.wall_pos[uid];
-            const int wx = px(w) - ax, wy = py(w) - ay;
-            return wx >= -D && wx <= D && wy >= -D && wy <= D;
-          };
+          // full radius-D rays visit first survives `set(visible_entities)`.  Fast filter: an entity can only take part
+          // if it is visible (window: exact `vis`; ring between window and radius D: the static walls-only visibility
+          // table, a superset).  Only for the uids that really have two candidates the first-visit ranks of the cells
+          // involved are derived (first_visit_rank walks the trie paths of just those cells).
+          unsigned long long door_sh = 0ull, dirt_sh = 0ull, grp_sh = 0ull;
           if (FAITHFUL) {
-            unsigned long long seen = 0ull;
-            auto touch = [&](int uid, uint16_t q) {
-              const int dx = px(q) - ax, dy = py(q) - ay;
-              if (dx < -D || dx > D || dy < -D || dy > D) return;
-              if (uid < 64) { dup |= seen & (1ull << uid); seen |= 1ull << uid; }
-              if (wall_rival(uid)) {
-                // a visible wall inside the window loses its plane entry if this entity is visited before it
-                const uint16_t w = tb.wall_pos[uid];
-                const int wx = px(w) - ax + R, wy = py(w) - ay + R;
-                if ((unsigned)wx < (unsigned)D && (unsigned)wy < (unsigned)D && ((wv >> (wx * D + wy)) & 1) &&
-                    rank_of(q) < rank_of(w))
-                  wv &= ~(1ull << (wx * D + wy));
-              }
+            constexpr int BW = 2 * D + 1;
+            const int tile = ax * sp->W + ay;
+            const unsigned long long* sb = reinterpret_cast<const unsigned long long*>(tb.vis_box) + (size_t)tile * 4;
+            auto cand = [&](uint16_t q) -> bool {
+              const int bx = px(q) - ax, by = py(q) - ay;
+              if (bx < -D || bx > D || by < -D || by > D) return false;
+              if (bx >= -R && bx <= R && by >= -R && by <= R) return ((vis >> ((bx + R) * D + by + R)) & 1ull) != 0;
+              const int ci = (bx + D) * BW + by + D;
+              return ((__ldg(sb + (ci >> 6)) >> (ci & 63)) & 1ull) != 0;
             };
-            for (int d = 0; d < sp->n_doors; ++d) if ((dlisted >> d) & 1) touch(d, tb.door_pos[d]);
-            for (int k = 0; k < sl.item0; ++k) {
-              const uint16_t q = pos[k];
-              if (q != NO_POS && ((dirtlisted >> k) & 1)) touch(blk_dirt_uid[k * ENV_BLOCK + eb], q);
-            }
-            {
-              const int lo[6] = {sl.item0, sl.pod0, sl.dest0, sl.drop0, sl.mach0, sl.maint0};
-              const int hi[6] = {sl.pod0, sl.dest0, sl.drop0, sl.mach0, sl.maint0, sl.agent0};
-#pragma unroll
-              for (int g = 0; g < 6; ++g)
-                for (int s = lo[g]; s < hi[g]; ++s) {
-                  const uint16_t q = pos[s];
-                  if (q != NO_POS && ((glisted[g] >> (s - lo[g])) & 1)) touch(s - lo[g], q);
-                }
-            }
-          }
-          // is the listed, visible entity (class code, index, uid) at q preceded by another visible listed entity of the
-          // same uid?  class codes: 0 door, 1 dirt, 2.. = small group g + 2
-          auto shadowed = [&](int cls, int idx, int uid, uint16_t q) -> bool {
-            if (!FAITHFUL) return false;
-            const bool maybe = (uid < 64 && ((dup >> uid) & 1)) || wall_rival(uid);
-            if (!maybe) return false;
-            const int my = rank_of(q);
-            if (wall_rival(uid) && rank_of(tb.wall_pos[uid]) < my) return true;
-            if (cls != 0 && uid < sp->n_doors && ((dlisted >> uid) & 1) && rank_of(tb.door_pos[uid]) < my) return true;
-            for (int k = 0; k < sl.item0 && uid < 64 && cls != 1; ++k) {     // dirt uids are unique among dirt piles
-              const uint16_t p2 = pos[k];
-              if (p2 != NO_POS && ((dirtlisted >> k) & 1) && blk_dirt_uid[k * ENV_BLOCK + eb] == uid && rank_of(p2) < my) return true;
-            }
             const int lo[6] = {sl.item0, sl.pod0, sl.dest0, sl.drop0, sl.mach0, sl.maint0};
             const int hi[6] = {sl.pod0, sl.dest0, sl.drop0, sl.mach0, sl.maint0, sl.agent0};
+            const unsigned long long wc64 = tb.wall_cand64[tile];      // walls with uid < 64 that may be visible from here
+            unsigned long long seen = wc64, dup = 0ull;
+            for (int d = 0; d < sp->n_doors; ++d)
+              if (((dlisted >> d) & 1) && cand(tb.door_pos[d])) { dup |= seen & (1ull << d); seen |= 1ull << d; }
 #pragma unroll
-            for (int g = 0; g < 6; ++g) {
-              if (cls == g + 2 || uid >= hi[g] - lo[g] || !((glisted[g] >> uid) & 1)) continue;
-              const uint16_t p2 = pos[lo[g] + uid];
-              if (p2 != NO_POS && rank_of(p2) < my) return true;
+            for (int g = 0; g < 6; ++g)
+              for (int s = lo[g]; s < hi[g]; ++s) {
+                const uint16_t q = pos[s];
+                if (q != NO_POS && ((glisted[g] >> (s - lo[g])) & 1) && cand(q)) {
+                  dup |= seen & (1ull << (s - lo[g]));
+                  seen |= 1ull << (s - lo[g]);
+                }
+              }
+            // dirt piles last (their uids are unique among dirt piles): conflicting ones go to a 4-entry packed list
+            const uint32_t wrng = tb.wall_cand_rng[tile];               // [lo, hi] of the candidate wall uids >= 64
+            unsigned long long dlist = 0ull;
+            int ndl = 0;
+            bool overflow = false;
+            for (int k = 0; k < sl.item0; ++k) {
+              const uint16_t q = pos[k];
+              if (q == NO_POS || !((dirtlisted >> k) & 1) || !cand(q)) continue;
+              const uint32_t uid = blk_dirt_uid[k * ENV_BLOCK + eb];
+              const bool c = uid < 64 ? (((seen >> uid) & 1ull) != 0) : (uid >= (wrng & 0xFFFFu) && uid <= (wrng >> 16));
+              if (!c) continue;
+              if (uid < 64) dup |= 1ull << uid;
+              if (ndl < 4 && uid < 1024) { dlist |= (unsigned long long)(uid | ((uint32_t)k << 10)) << (16 * ndl); ++ndl; }
+              else overflow = true;
             }
-            return false;
-          };
+            if (overflow) {
+              atomicAdd(s_cnt + lane, cap + 1);       // too many conflicts: the exact per-agent path redoes this env
+            } else if (dup != 0ull || ndl != 0) {
+              // true light-block mask of the radius-D box: walls from the per-tile table + closed listed doors
+              const unsigned long long* wb = reinterpret_cast<const unsigned long long*>(tb.wall_box) + (size_t)tile * 4;
+              unsigned long long b0 = wb[0], b1 = wb[1], b2 = wb[2], b3 = wb[3];
+              for (int d = 0; d < sp->n_doors; ++d) {
+                const uint16_t q = tb.door_pos[d];
+                const int dx = px(q) - ax + D, dy = py(q) - ay + D;
+                if (!((dopen >> d) & 1) && ((dlisted >> d) & 1) && (unsigned)dx < (unsigned)BW && (unsigned)dy < (unsigned)BW) {
+                  const int bi = dx * BW + dy, w = bi >> 6;
+                  const unsigned long long bit = 1ull << (bi & 63);
+                  b0 |= w == 0 ? bit : 0ull; b1 |= w == 1 ? bit : 0ull; b2 |= w == 2 ? bit : 0ull; b3 |= w == 3 ? bit : 0ull;
+                }
+              }
+              auto rk = [&](uint16_t q) -> int { return first_visit_rank<R>(b0, b1, b2, b3, px(q) - ax, py(q) - ay); };
+              auto drop_wall = [&](uint16_t w) {
+                const int wx = px(w) - ax + R, wy = py(w) - ay + R;
+                if ((unsigned)wx < (unsigned)D && (unsigned)wy < (unsigned)D) wv &= ~(1ull << (wx * D + wy));
+              };
+              constexpr int INF = 0x7FFF;
+              unsigned long long m = dup;
+              while (m) {
+                const int u = __ffsll((long long)m) - 1;
+                m &= m - 1;
+                const bool has_wall = u < sp->n_walls && ((wc64 >> u) & 1ull);
+                const int r_wall = has_wall ? rk(tb.wall_pos[u]) : INF;
+                const int r_door = (u < sp->n_doors && ((dlisted >> u) & 1)) ? rk(tb.door_pos[u]) : INF;
+                int r_g[6];
+#pragma unroll
+                for (int g = 0; g < 6; ++g) {
+                  r_g[g] = INF;
+                  if (u < hi[g] - lo[g] && ((glisted[g] >> u) & 1)) {
+                    const uint16_t q = pos[lo[g] + u];
+                    if (q != NO_POS) r_g[g] = rk(q);
+                  }
+                }
+                int r_dirt = INF, k_dirt = -1;
+                for (int i = 0; i < ndl; ++i) {
+                  const uint32_t en = (uint32_t)(dlist >> (16 * i)) & 0xFFFFu;
+                  if ((int)(en & 1023u) == u) { k_dirt = (int)(en >> 10); r_dirt = rk(pos[k_dirt]); }
+                }
+                int best = r_wall < r_door ? r_wall : r_door;
+                best = r_dirt < best ? r_dirt : best;
+#pragma unroll
+                for (int g = 0; g < 6; ++g) best = r_g[g] < best ? r_g[g] : best;
+                if (has_wall && r_wall > best) drop_wall(tb.wall_pos[u]);
+                if (r_door > best) door_sh |= 1ull << u;
+                if (k_dirt >= 0 && r_dirt > best) dirt_sh |= 1ull << k_dirt;
+#pragma unroll
+                for (int g = 0; g < 6; ++g)
+                  if (r_g[g] > best && u < hi[g] - lo[g]) grp_sh |= 1ull << (lo[g] + u - sl.item0);
+              }
+              // dirt piles with uid >= 64 can only meet the wall of that uid
+              for (int i = 0; i < ndl; ++i) {
+                const uint32_t en = (uint32_t)(dlist >> (16 * i)) & 0xFFFFu;
+                const int uid = (int)(en & 1023u), k = (int)(en >> 10);
+                if (uid < 64 || uid >= sp->n_walls) continue;
+                const uint16_t w = tb.wall_pos[uid];
+                const int rw = rk(w), rd = rk(pos[k]);
+                if (rw < rd) dirt_sh |= 1ull << k;
+                else if (rd < rw) drop_wall(w);
+              }
+            }
+          }
 
           const uint32_t* chm = sp->term_chmask[a];
           const int coff = sp->ch_offset[a];
@@ -361,7 +374,7 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
                 if (q == NO_POS || !((glisted[g] >> (s - lo[g])) & 1)) continue;
                 if (g == 2 && ((reached >> (s - lo[g])) & 1)) continue;      // a reached destination encodes as 0
                 const int cell = cell_of(q);
-                if (cell >= 0 && !shadowed(g + 2, s - lo[g], s - lo[g], q)) emit(m, cell, SK_INT, 0, g == 4 ? (float)ENC_MACHINE : 1.0f);
+                if (cell >= 0 && !((grp_sh >> (s - sl.item0)) & 1ull)) emit(m, cell, SK_INT, 0, g == 4 ? (float)ENC_MACHINE : 1.0f);
               }
             }
           }
@@ -370,7 +383,7 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
             for (int d = 0; d < sp->n_doors; ++d) {
               if (!((dlisted >> d) & 1)) continue;
               const int cell = cell_of(tb.door_pos[d]);
-              if (cell >= 0 && !shadowed(0, d, d, tb.door_pos[d])) emit(chm[MFG_G_DOORS], cell, SK_DOOR, (uint32_t)((dopen >> d) & 1), 0.f);
+              if (cell >= 0 && !((door_sh >> d) & 1ull)) emit(chm[MFG_G_DOORS], cell, SK_DOOR, (uint32_t)((dopen >> d) & 1), 0.f);
             }
           }
           // dirt piles
@@ -379,7 +392,7 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
               const uint16_t q = pos[k];
               if (q == NO_POS || !((dirtlisted >> k) & 1)) continue;
               const int cell = cell_of(q);
-              if (cell >= 0 && !shadowed(1, k, blk_dirt_uid[k * ENV_BLOCK + eb], q)) emit(chm[MFG_G_DIRT], cell, SK_DIRT, (uint32_t)k, 0.f);
+              if (cell >= 0 && !((dirt_sh >> k) & 1ull)) emit(chm[MFG_G_DIRT], cell, SK_DIRT, (uint32_t)k, 0.f);
             }
           }
           // scalar channels
@@ -619,6 +632,57 @@ static bool full_trie_matches(const MfgSpec& sp) {
   return true;
 }
 
+// static (walls-only) visibility tables of the faithful mode: per tile, the box cells reached by the full rays when only
+// walls block light, and which wall uids lie on such cells (walls are static, so this part of the conflict filter is free)
+template <int R>
+static void build_vis_tables_r(const MfgSpec& sp, HostTables& t) {
+  using T = FullTrie<R>;
+  constexpr int D = 2 * R + 1, BW = 2 * D + 1;
+  const int H = sp.H, W = sp.W;
+  t.vis_box.assign((size_t)H * W * 4, 0);
+  t.wall_cand64.assign((size_t)H * W, 0);
+  t.wall_cand_rng.assign((size_t)H * W, 0x0000FFFFu);
+  std::vector<char> cont(T::N);
+  for (int x = 0; x < H; ++x)
+    for (int y = 0; y < W; ++y) {
+      uint64_t* vb = &t.vis_box[((size_t)x * W + y) * 4];
+      auto blk = [&](int ci) -> bool {
+        const int xx = x + ci / BW - D, yy = y + ci % BW - D;
+        return xx >= 0 && yy >= 0 && xx < H && yy < W && t.wall[(size_t)xx * W + yy];
+      };
+      vb[(D * BW + D) >> 6] |= 1ull << ((D * BW + D) & 63);
+      if (!t.wall[(size_t)x * W + y]) {
+        for (int n = 0; n < T::N; ++n) {          // parents precede their children (node ids = first-visit order)
+          const int p = T::parent(n), c = T::cell(n), da = T::da(n), db = T::db(n);
+          const bool reach = p < 0 ? true : cont[p] != 0;
+          const bool diag = da != 255 && blk(da) && blk(db);
+          if (reach && !diag) vb[c >> 6] |= 1ull << (c & 63);
+          cont[n] = reach && !diag && !blk(c);
+        }
+      }
+      uint32_t lo = 0xFFFF, hi = 0;
+      for (int dx = -D; dx <= D; ++dx)
+        for (int dy = -D; dy <= D; ++dy) {
+          const int xx = x + dx, yy = y + dy, ci = (dx + D) * BW + (dy + D);
+          if (xx < 0 || yy < 0 || xx >= H || yy >= W || !t.wall[(size_t)xx * W + yy] || !((vb[ci >> 6] >> (ci & 63)) & 1)) continue;
+          const uint32_t u = t.wall_uid[(size_t)xx * W + yy];
+          if (u < 64) t.wall_cand64[(size_t)x * W + y] |= 1ull << u;
+          else { lo = u < lo ? u : lo; hi = u > hi ? u : hi; }
+        }
+      t.wall_cand_rng[(size_t)x * W + y] = lo | (hi << 16);
+    }
+}
+
+void build_vis_tables(const MfgSpec& sp, HostTables& t) {
+  if (!sp.faithful) return;
+  switch (sp.pomdp_r) {
+    case 1: build_vis_tables_r<1>(sp, t); break;
+    case 2: build_vis_tables_r<2>(sp, t); break;
+    case 3: build_vis_tables_r<3>(sp, t); break;
+    default: break;
+  }
+}
+
 void plan_obs(MfgHandle* h) {
   const MfgSpec& sp = h->sp;
   ObsPlan& p = h->plan;
@@ -689,6 +753,7 @@ void plan_obs(MfgHandle* h) {
       }
   bool full_ok = !sp.faithful || (sp.pomdp_r == 1 ? full_trie_matches<1>(sp) : sp.pomdp_r == 2 ? full_trie_matches<2>(sp)
                                   : sp.pomdp_r == 3 ? full_trie_matches<3>(sp) : false);
+  if (sp.faithful && (sl.agent0 - sl.item0 > 64 || sp.n_walls > 0xFFFE)) full_ok = false;   // shadow masks are 64-bit
   p.ok = trie_ok && full_ok && walls_fit && p.smem <= 200 * 1024 && tcdd * p.ge <= 0xFFFF;
 }
 
@@ -728,8 +793,10 @@ static cudaError_t launch_tiled_r(MfgHandle* h, float* d_obs, cudaStream_t s) {
 
 cudaError_t launch_obs_tiled(MfgHandle* h, float* d_obs, cudaStream_t s) {
   switch (h->sp.pomdp_r) {
+#ifndef MFG_OBS_R3_ONLY          // development builds: -DMFG_OBS_R3_ONLY compiles a third of the template instances
     case 1: return launch_tiled_r<1>(h, d_obs, s);
     case 2: return launch_tiled_r<2>(h, d_obs, s);
+#endif
     case 3: return launch_tiled_r<3>(h, d_obs, s);
     default: return cudaErrorInvalidValue;
   }
