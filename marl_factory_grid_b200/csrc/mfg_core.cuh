@@ -56,9 +56,9 @@ enum { C_DOOR = 0, C_DIRT, C_ITEM, C_POD, C_DEST, C_DROP, C_MACH, C_MAINT, C_NON
   F(uint16_t, apos, sp.n_agents)                                                   \
   F(uint64_t, door_open, sp.n_doors ? 1 : 0)                                       \
   F(uint32_t, dest_reached, sp.n_dest ? 1 : 0)                                     \
+  F(uint64_t, dirt_listed, sp.has_dirt ? 1 : 0)   /* identity mode: = the live piles */ \
   /* ---- end of the identity-mode observation prefix; the faithful mode also needs listing bits and dirt uids */ \
   F(uint64_t, door_listed, sp.n_doors ? 1 : 0)                                     \
-  F(uint64_t, dirt_listed, sp.has_dirt ? 1 : 0)                                    \
   F(uint32_t, item_listed, sp.n_items ? 1 : 0)                                     \
   F(uint32_t, pod_listed, sp.n_pods ? 1 : 0)                                       \
   F(uint32_t, dest_listed, sp.n_dest ? 1 : 0)                                      \
@@ -110,11 +110,13 @@ struct Tables {
   const uint16_t* door_pos;    // [ND] pos16
   const uint8_t* nexthop;      // [F*F] or null
   const uint64_t* wall_win;    // [H*W] (2r+1)^2-bit wall mask of the window centred on the tile (r <= 3)
+  const uint64_t* door_near;   // [H*W] doors inside the radius-D box centred on the tile (bit = door index)
   const uint64_t* wall_box;    // [H*W][4] wall mask of the (2D+1)^2 box (D = 2r+1) centred on the tile, bit = (dx+D)*(2D+1)+(dy+D)
   // faithful observation mode (built by build_vis_tables, mfg_obs.cu): static walls-only visibility
   const uint64_t* vis_box;       // [H*W][4] box cells some full ray reaches when only walls block light (superset of the truth)
   const uint64_t* wall_cand64;   // [H*W] bit u: wall with uid u < 64 lies on such a cell
   const uint32_t* wall_cand_rng; // [H*W] lo | hi << 16: range of the wall uids >= 64 on such cells (lo > hi: none)
+  const uint64_t* wall_win64;    // [H*W] bit u: wall with uid u < 64 lies inside the window of the tile
   int64_t env_id_offset;
   unsigned long long* stats;   // [MFG_N_STATS]
 };

@@ -38,6 +38,7 @@ struct ObsPlan {
   bool ok = false;        // tiled kernel usable for this spec
   int ge = 1;             // envs per output tile (tile = whole number of 16-byte vectors)
   int nw = 4;             // warps per CTA
+  int apad_log2 = 0;      // log2 of the agent count rounded up to a power of two (lanes per env in phase 1)
   int nbuf = 1;           // tile buffers per warp (2 = overlap the bulk store with the next env)
   int cap = 48;           // sprite slots per env (all agents share one list)
   int cap_max = 48;

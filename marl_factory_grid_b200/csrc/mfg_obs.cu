@@ -142,26 +142,35 @@ __device__ __forceinline__ void mbar_wait0(unsigned long long* bar) {
       "}\n" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// CTA = one 128-env state block, processed as four groups of 32 envs.
-template <int R, int GE, int NBUF, bool BULK, bool FAITHFUL>
-__global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st, ObsSlots sl, WallPlanes wp,
-                            float* __restrict__ obs, int total_channels, int cap) {
+// CTA = one 128-env state block.  Every warp works on its own sub-groups of EPW = 32 / APAD envs (APAD = agent count
+// rounded up to a power of two): lane = (env, agent) in phase 1, the same warp expands the tiles of those envs in phase 2,
+// so after the prefix has landed no CTA-wide barrier is needed and warps in different phases overlap on the SM.
+template <int R, bool FAITHFUL>
+__global__ void __launch_bounds__(256) k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st, ObsSlots sl, WallPlanes wp,
+                                                    float* __restrict__ obs, int total_channels, int cap, int apad_log2,
+                                                    int GE, int bulk) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long bar;
+  // per-agent channel program (lanes of one warp belong to different agents, so it is read with per-lane indices)
+  __shared__ uint32_t s_chm[MFG_MAX_AGENTS][MFG_N_TERMS];      // term -> channel bit mask
+  __shared__ uint16_t s_scal[MFG_MAX_AGENTS][4];               // scalar channels: channel | kind << 8
+  __shared__ uint8_t s_nscal[MFG_MAX_AGENTS];
+  __shared__ int s_coff[MFG_MAX_AGENTS];
   constexpr int D = 2 * R + 1, DD = D * D;
   const int A = sp->n_agents;
   const int NW = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int EPW = 32 >> apad_log2;                                 // envs per warp pass
   const int64_t blk0 = (int64_t)blockIdx.x * ENV_BLOCK;
   const int tile_floats = GE * total_channels * DD;
 
-  // shared memory carve-up (every region start stays 16-byte aligned)
+  // shared memory carve-up (every region start stays 16-byte aligned): prefix | per warp: tile, sprite lists, counters
   unsigned char* s_blk = smem_raw;                                                          // staged block prefix
-  float* tiles = reinterpret_cast<float*>(smem_raw + sl.prefix_bytes);                      // [NW][NBUF][tile_floats]
-  unsigned long long* s_vis = reinterpret_cast<unsigned long long*>(tiles + (size_t)NW * NBUF * tile_floats);  // [32][A]
-  unsigned long long* s_wv = s_vis + OBS_ENVS * A;                                          // [32][A]
-  Sprite* s_spr = reinterpret_cast<Sprite*>(s_wv + OBS_ENVS * A);                           // [32][cap]  one list per env
-  int* s_cnt = reinterpret_cast<int*>(s_spr + (size_t)OBS_ENVS * cap);                      // [32] sprites emitted per env
+  const size_t per_warp = (size_t)tile_floats * 4 + (size_t)EPW * cap * 8 + 128;
+  unsigned char* wbase = smem_raw + sl.prefix_bytes + (size_t)warp * per_warp;
+  float* tile = reinterpret_cast<float*>(wbase);
+  Sprite* s_spr = reinterpret_cast<Sprite*>(wbase + (size_t)tile_floats * 4);               // [EPW][cap]
+  int* s_cnt = reinterpret_cast<int*>(wbase + (size_t)tile_floats * 4 + (size_t)EPW * cap * 8);   // [EPW]
   // ---- stage the positional prefix of this block: one TMA bulk copy (dirt/item/.../agent positions, door + dest masks)
   if (threadIdx.x == 0) {
     mbar_init1(&bar);
@@ -169,6 +178,18 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(s_blk)),
                  "l"(st.base_i + (size_t)blockIdx.x * st.blk_i), "r"((uint32_t)sl.prefix_bytes), "r"(smem_u32(&bar)) : "memory");
   }
+  for (int i = threadIdx.x; i < A * MFG_N_TERMS; i += blockDim.x) s_chm[i / MFG_N_TERMS][i % MFG_N_TERMS] = sp->term_chmask[i / MFG_N_TERMS][i % MFG_N_TERMS];
+  if (threadIdx.x < A) {
+    const int a = threadIdx.x, C = sp->n_channels[a];
+    int n = 0;
+    for (int c = 0; c < C; ++c) {
+      const int kind = sp->ch_kind[a][c];
+      if ((kind == MFG_CH_BATTERY || kind == MFG_CH_GLOBALPOS) && n < 4) s_scal[a][n++] = (uint16_t)(c | (kind << 8));
+    }
+    s_nscal[a] = (uint8_t)n;
+    s_coff[a] = sp->ch_offset[a];
+  }
+  const int spW = sp->W, spH = sp->H, n_doors = sp->n_doors, n_dest = sp->n_dest, has_dirt = sp->has_dirt, n_walls = sp->n_walls;
   __syncthreads();
   mbar_wait0(&bar);
   const uint16_t* blk16 = reinterpret_cast<const uint16_t*>(s_blk);
@@ -177,275 +198,282 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
   const unsigned long long* blk_dlisted = reinterpret_cast<const unsigned long long*>(s_blk + sl.off_door_listed);
   const unsigned long long* blk_dirtlisted = reinterpret_cast<const unsigned long long*>(s_blk + sl.off_dirt_listed);
   const uint16_t* blk_dirt_uid = reinterpret_cast<const uint16_t*>(s_blk + sl.off_dirt_uid);
+  const int lo[6] = {sl.item0, sl.pod0, sl.dest0, sl.drop0, sl.mach0, sl.maint0};
+  const int hi[6] = {sl.pod0, sl.dest0, sl.drop0, sl.mach0, sl.maint0, sl.agent0};
 
-  if (warp == 0) s_cnt[lane] = 0;
-  int buf = 0;
-  for (int grp = 0; grp < ENV_BLOCK / OBS_ENVS; ++grp) {
-    const int64_t env0 = blk0 + (int64_t)grp * OBS_ENVS;
+  for (int sub = warp; sub * EPW < ENV_BLOCK; sub += NW) {
+    const int64_t env0 = blk0 + (int64_t)sub * EPW;
     if (env0 >= st.N) break;
-    // s_cnt is zero here: initialised before the loop, and re-zeroed by the phase-2 warp that consumed each list
-    __syncthreads();            // fences the previous group's phase 2 against the reuse of s_spr / s_vis / s_wv / s_cnt
+    if (lane < EPW) s_cnt[lane] = 0;
+    __syncwarp();
 
-    // ---------------- phase 1: one thread per (env = lane, agent = warp, warp + NW, ..) -------------------------
+    // ---------------- phase 1: lane = (env el, agent a) ---------------------------------------------------------
+    const int el = lane >> apad_log2, a = lane & ((1 << apad_log2) - 1);
+    unsigned long long wv = 0ull;
     {
-      const int64_t e = env0 + lane;
-      const bool live = e < st.N;
-      const int eb = grp * OBS_ENVS + lane;
-      const BlkPos pos{blk16, eb};
-      const unsigned long long dopen = sp->n_doors ? blk_dopen[eb] : 0ull;
-      const uint32_t reached = sp->n_dest ? blk_reached[eb] : 0u;
-      // listing bits (uid-equality artefact): everything is listed in identity mode
-      const unsigned long long dlisted = (FAITHFUL && sp->n_doors) ? blk_dlisted[eb] : ~0ull;
-      const unsigned long long dirtlisted = (FAITHFUL && sp->has_dirt) ? blk_dirtlisted[eb] : ~0ull;
-      uint32_t glisted[6] = {~0u, ~0u, ~0u, ~0u, ~0u, ~0u};
-      if (FAITHFUL) {
+      const int64_t e = env0 + el;
+      const int eb = sub * EPW + el;
+      if (a < A && e < st.N) {
+        const BlkPos pos{blk16, eb};
+        const unsigned long long dopen = n_doors ? blk_dopen[eb] : 0ull;
+        const uint32_t reached = n_dest ? blk_reached[eb] : 0u;
+        // listing bits (uid-equality artefact): everything is listed in identity mode
+        const unsigned long long dlisted = (FAITHFUL && n_doors) ? blk_dlisted[eb] : ~0ull;
+        const unsigned long long dirtlisted = has_dirt ? blk_dirtlisted[eb] : 0ull;
+        uint32_t glisted[6] = {~0u, ~0u, ~0u, ~0u, ~0u, ~0u};
+        if (FAITHFUL) {
+#pragma unroll
+          for (int g = 0; g < 6; ++g)
+            if (sl.off_listed[g] >= 0) glisted[g] = reinterpret_cast<const uint32_t*>(s_blk + sl.off_listed[g])[eb];
+        }
+        const uint16_t p = pos[sl.agent0 + a];
+        const int ax = px(p), ay = py(p);
+        const int tile_id = ax * spW + ay;
+        const unsigned long long W49 = tb.wall_win[tile_id];
+        // static walls-only visibility of the radius-D box (faithful conflict filter); requested early, used late
+        unsigned long long sb0 = 0ull, sb1 = 0ull, sb2 = 0ull, sb3 = 0ull;
+        if (FAITHFUL) {
+          const ulonglong2* sbp = reinterpret_cast<const ulonglong2*>(tb.vis_box) + (size_t)tile_id * 2;
+          const ulonglong2 u0 = __ldg(sbp), u1 = __ldg(sbp + 1);
+          sb0 = u0.x; sb1 = u0.y; sb2 = u1.x; sb3 = u1.y;
+        }
+        // doors inside the radius-D box of this tile (static table): usually 0..3 of them
+        const unsigned long long dnear = n_doors ? (tb.door_near[tile_id] & dlisted) : 0ull;
+        unsigned long long B = W49;
+        for (unsigned long long m = dnear & ~dopen; m; m &= m - 1) {
+          const uint16_t q = tb.door_pos[__ffsll((long long)m) - 1];
+          const int dx = px(q) - ax + R, dy = py(q) - ay + R;
+          if ((unsigned)dx < (unsigned)D && (unsigned)dy < (unsigned)D) B |= 1ull << (dx * D + dy);
+        }
+        const unsigned long long vis = march<R>(B);
+        wv = W49 & vis;
+
+        // ---- one pass over the listed entities: which are visible inside the window (`*_w` masks), and (faithful
+        // mode) which uids have two candidates.  Among the visible LISTED entities that share a uid
+        // only the one the full radius-D rays visit first survives `set(visible_entities)`.  An entity can only take
+        // part if it is visible: exact `vis` inside the window, the static walls-only visibility (a superset) on the
+        // ring between window and radius D.  Ranks are derived only for the uids that really have two candidates.
+        constexpr int BW = 2 * D + 1;
+        // returns 0 = not a candidate, 1 = candidate on the ring, 3 = visible inside the window
+        auto classify = [&](uint16_t q) -> int {
+          const int bx = px(q) - ax, by = py(q) - ay;
+          if (bx >= -R && bx <= R && by >= -R && by <= R) return ((vis >> ((bx + R) * D + by + R)) & 1ull) ? 3 : 0;
+          if (!FAITHFUL || bx < -D || bx > D || by < -D || by > D) return 0;
+          const int ci = (bx + D) * BW + by + D, w = ci >> 6;
+          const unsigned long long word = w == 0 ? sb0 : w == 1 ? sb1 : w == 2 ? sb2 : sb3;
+          return (int)((word >> (ci & 63)) & 1ull);
+        };
+        unsigned long long door_w = 0ull, dirt_w = 0ull, grp_w = 0ull;
+        const unsigned long long wc64 = FAITHFUL ? tb.wall_cand64[tile_id] : 0ull;   // walls with uid < 64 that may be visible
+        // uids seen so far / seen twice / seen inside the window.  A shared uid only matters when one of its holders is
+        // inside the window (nothing outside the window is drawn), which prunes most ring-ring pairs.
+        unsigned long long seen = wc64, dup = 0ull, win_uids = FAITHFUL ? tb.wall_win64[tile_id] : 0ull;
+        for (unsigned long long m = dnear; m; m &= m - 1) {
+          const int d = __ffsll((long long)m) - 1;
+          const int c = classify(tb.door_pos[d]);
+          if (c) { dup |= seen & (1ull << d); seen |= 1ull << d; }
+          if (c == 3) { door_w |= 1ull << d; win_uids |= 1ull << d; }
+        }
 #pragma unroll
         for (int g = 0; g < 6; ++g)
-          if (sl.off_listed[g] >= 0) glisted[g] = reinterpret_cast<const uint32_t*>(s_blk + sl.off_listed[g])[eb];
-      }
-      for (int a = warp; a < A; a += NW) {
-        unsigned long long vis = 0ull, wv = 0ull;
-        if (live) {
-          const uint16_t p = pos[sl.agent0 + a];
-          const int ax = px(p), ay = py(p);
-          const unsigned long long W49 = tb.wall_win[ax * sp->W + ay];
-          unsigned long long B = W49;
-          for (int d = 0; d < sp->n_doors; ++d) {
-            const uint16_t q = tb.door_pos[d];
-            const int dx = px(q) - ax + R, dy = py(q) - ay + R;
-            if (!((dopen >> d) & 1) && ((dlisted >> d) & 1) && (unsigned)dx < (unsigned)D && (unsigned)dy < (unsigned)D)
-              B |= 1ull << (dx * D + dy);
+          for (int s = lo[g]; s < hi[g]; ++s) {
+            const uint16_t q = pos[s];
+            if (q == NO_POS || !((glisted[g] >> (s - lo[g])) & 1)) continue;
+            const int c = classify(q);
+            if (c) { dup |= seen & (1ull << (s - lo[g])); seen |= 1ull << (s - lo[g]); }
+            if (c == 3) { grp_w |= 1ull << (s - sl.item0); win_uids |= 1ull << (s - lo[g]); }
           }
-          vis = march<R>(B);
-          wv = W49 & vis;
-
-          // ---- faithful mode: among the visible LISTED entities that share a uid only the one the
-          // full radius-D rays visit first survives `set(visible_entities)`.  Fast filter: an entity can only take part
-          // if it is visible (window: exact `vis`; ring between window and radius D: the static walls-only visibility
-          // table, a superset).  Only for the uids that really have two candidates the first-visit ranks of the cells
-          // involved are derived (first_visit_rank walks the trie paths of just those cells).
-          unsigned long long door_sh = 0ull, dirt_sh = 0ull, grp_sh = 0ull;
-          if (FAITHFUL) {
-            constexpr int BW = 2 * D + 1;
-            const int tile = ax * sp->W + ay;
-            const unsigned long long* sb = reinterpret_cast<const unsigned long long*>(tb.vis_box) + (size_t)tile * 4;
-            auto cand = [&](uint16_t q) -> bool {
-              const int bx = px(q) - ax, by = py(q) - ay;
-              if (bx < -D || bx > D || by < -D || by > D) return false;
-              if (bx >= -R && bx <= R && by >= -R && by <= R) return ((vis >> ((bx + R) * D + by + R)) & 1ull) != 0;
-              const int ci = (bx + D) * BW + by + D;
-              return ((__ldg(sb + (ci >> 6)) >> (ci & 63)) & 1ull) != 0;
-            };
-            const int lo[6] = {sl.item0, sl.pod0, sl.dest0, sl.drop0, sl.mach0, sl.maint0};
-            const int hi[6] = {sl.pod0, sl.dest0, sl.drop0, sl.mach0, sl.maint0, sl.agent0};
-            const unsigned long long wc64 = tb.wall_cand64[tile];      // walls with uid < 64 that may be visible from here
-            unsigned long long seen = wc64, dup = 0ull;
-            for (int d = 0; d < sp->n_doors; ++d)
-              if (((dlisted >> d) & 1) && cand(tb.door_pos[d])) { dup |= seen & (1ull << d); seen |= 1ull << d; }
-#pragma unroll
-            for (int g = 0; g < 6; ++g)
-              for (int s = lo[g]; s < hi[g]; ++s) {
-                const uint16_t q = pos[s];
-                if (q != NO_POS && ((glisted[g] >> (s - lo[g])) & 1) && cand(q)) {
-                  dup |= seen & (1ull << (s - lo[g]));
-                  seen |= 1ull << (s - lo[g]);
-                }
-              }
-            // dirt piles last (their uids are unique among dirt piles): conflicting ones go to a 4-entry packed list
-            const uint32_t wrng = tb.wall_cand_rng[tile];               // [lo, hi] of the candidate wall uids >= 64
-            unsigned long long dlist = 0ull;
-            int ndl = 0;
-            bool overflow = false;
-            for (int k = 0; k < sl.item0; ++k) {
-              const uint16_t q = pos[k];
-              if (q == NO_POS || !((dirtlisted >> k) & 1) || !cand(q)) continue;
+        // dirt piles last (their uids are unique among dirt piles): conflicting ones go to a 4-entry packed list
+        unsigned long long dlist = 0ull;
+        int ndl = 0;
+        bool overflow = false;
+        {
+          const uint32_t wrng = FAITHFUL ? tb.wall_cand_rng[tile_id] : 0xFFFFu;     // [lo, hi] of the candidate wall uids >= 64
+          for (unsigned long long dm = dirtlisted; dm; dm &= dm - 1) {     // listed piles (identity mode: the live ones)
+            const int k = __ffsll((long long)dm) - 1;
+            const uint16_t q = pos[k];
+            const int c = classify(q);
+            if (c == 3) dirt_w |= 1ull << k;
+            if (FAITHFUL && c) {
               const uint32_t uid = blk_dirt_uid[k * ENV_BLOCK + eb];
-              const bool c = uid < 64 ? (((seen >> uid) & 1ull) != 0) : (uid >= (wrng & 0xFFFFu) && uid <= (wrng >> 16));
-              if (!c) continue;
-              if (uid < 64) dup |= 1ull << uid;
-              if (ndl < 4 && uid < 1024) { dlist |= (unsigned long long)(uid | ((uint32_t)k << 10)) << (16 * ndl); ++ndl; }
-              else overflow = true;
+              bool cf;
+              if (uid < 64) {
+                cf = ((seen >> uid) & 1ull) != 0;
+                if (c == 3) win_uids |= 1ull << uid;
+              } else {
+                cf = uid >= (wrng & 0xFFFFu) && uid <= (wrng >> 16);
+                if (cf && c != 3) {                 // pile on the ring: only matters if the wall of that uid is inside the window
+                  const uint16_t w = tb.wall_pos[uid];
+                  const int wx = px(w) - ax, wy = py(w) - ay;
+                  cf = wx >= -R && wx <= R && wy >= -R && wy <= R;
+                }
+              }
+              if (cf) {
+                if (uid < 64) dup |= 1ull << uid;
+                if (ndl < 4 && uid < 1024) { dlist |= (unsigned long long)(uid | ((uint32_t)k << 10)) << (16 * ndl); ++ndl; }
+                else overflow = true;
+              }
             }
-            if (overflow) {
-              atomicAdd(s_cnt + lane, cap + 1);       // too many conflicts: the exact per-agent path redoes this env
-            } else if (dup != 0ull || ndl != 0) {
-              // true light-block mask of the radius-D box: walls from the per-tile table + closed listed doors
-              const unsigned long long* wb = reinterpret_cast<const unsigned long long*>(tb.wall_box) + (size_t)tile * 4;
-              unsigned long long b0 = wb[0], b1 = wb[1], b2 = wb[2], b3 = wb[3];
-              for (int d = 0; d < sp->n_doors; ++d) {
-                const uint16_t q = tb.door_pos[d];
-                const int dx = px(q) - ax + D, dy = py(q) - ay + D;
-                if (!((dopen >> d) & 1) && ((dlisted >> d) & 1) && (unsigned)dx < (unsigned)BW && (unsigned)dy < (unsigned)BW) {
-                  const int bi = dx * BW + dy, w = bi >> 6;
-                  const unsigned long long bit = 1ull << (bi & 63);
-                  b0 |= w == 0 ? bit : 0ull; b1 |= w == 1 ? bit : 0ull; b2 |= w == 2 ? bit : 0ull; b3 |= w == 3 ? bit : 0ull;
+          }
+        }
+        if (FAITHFUL) {
+          if (overflow) {
+            atomicAdd(s_cnt + el, cap + 1);           // too many conflicts: the exact per-agent path redoes this env
+          } else if ((dup &= win_uids) != 0ull || ndl != 0) {
+            // true light-block mask of the radius-D box: walls from the per-tile table + closed listed doors
+            const unsigned long long* wb = reinterpret_cast<const unsigned long long*>(tb.wall_box) + (size_t)tile_id * 4;
+            unsigned long long b0 = wb[0], b1 = wb[1], b2 = wb[2], b3 = wb[3];
+            for (unsigned long long m = dnear & ~dopen; m; m &= m - 1) {
+              const uint16_t q = tb.door_pos[__ffsll((long long)m) - 1];
+              const int bi = (px(q) - ax + D) * BW + (py(q) - ay + D), w = bi >> 6;
+              const unsigned long long bit = 1ull << (bi & 63);
+              b0 |= w == 0 ? bit : 0ull; b1 |= w == 1 ? bit : 0ull; b2 |= w == 2 ? bit : 0ull; b3 |= w == 3 ? bit : 0ull;
+            }
+            auto rk = [&](uint16_t q) -> int { return first_visit_rank<R>(b0, b1, b2, b3, px(q) - ax, py(q) - ay); };
+            auto drop_wall = [&](uint16_t w) {
+              const int wx = px(w) - ax + R, wy = py(w) - ay + R;
+              if ((unsigned)wx < (unsigned)D && (unsigned)wy < (unsigned)D) wv &= ~(1ull << (wx * D + wy));
+            };
+            constexpr int INF = 0x7FFF;
+            for (unsigned long long m = dup; m; m &= m - 1) {
+              const int u = __ffsll((long long)m) - 1;
+              const bool has_wall = u < n_walls && ((wc64 >> u) & 1ull);
+              const int r_wall = has_wall ? rk(tb.wall_pos[u]) : INF;
+              const int r_door = (u < n_doors && ((dlisted >> u) & 1)) ? rk(tb.door_pos[u]) : INF;
+              int r_g[6];
+#pragma unroll
+              for (int g = 0; g < 6; ++g) {
+                r_g[g] = INF;
+                if (u < hi[g] - lo[g] && ((glisted[g] >> u) & 1)) {
+                  const uint16_t q = pos[lo[g] + u];
+                  if (q != NO_POS) r_g[g] = rk(q);
                 }
               }
-              auto rk = [&](uint16_t q) -> int { return first_visit_rank<R>(b0, b1, b2, b3, px(q) - ax, py(q) - ay); };
-              auto drop_wall = [&](uint16_t w) {
-                const int wx = px(w) - ax + R, wy = py(w) - ay + R;
-                if ((unsigned)wx < (unsigned)D && (unsigned)wy < (unsigned)D) wv &= ~(1ull << (wx * D + wy));
-              };
-              constexpr int INF = 0x7FFF;
-              unsigned long long m = dup;
-              while (m) {
-                const int u = __ffsll((long long)m) - 1;
-                m &= m - 1;
-                const bool has_wall = u < sp->n_walls && ((wc64 >> u) & 1ull);
-                const int r_wall = has_wall ? rk(tb.wall_pos[u]) : INF;
-                const int r_door = (u < sp->n_doors && ((dlisted >> u) & 1)) ? rk(tb.door_pos[u]) : INF;
-                int r_g[6];
-#pragma unroll
-                for (int g = 0; g < 6; ++g) {
-                  r_g[g] = INF;
-                  if (u < hi[g] - lo[g] && ((glisted[g] >> u) & 1)) {
-                    const uint16_t q = pos[lo[g] + u];
-                    if (q != NO_POS) r_g[g] = rk(q);
-                  }
-                }
-                int r_dirt = INF, k_dirt = -1;
-                for (int i = 0; i < ndl; ++i) {
-                  const uint32_t en = (uint32_t)(dlist >> (16 * i)) & 0xFFFFu;
-                  if ((int)(en & 1023u) == u) { k_dirt = (int)(en >> 10); r_dirt = rk(pos[k_dirt]); }
-                }
-                int best = r_wall < r_door ? r_wall : r_door;
-                best = r_dirt < best ? r_dirt : best;
-#pragma unroll
-                for (int g = 0; g < 6; ++g) best = r_g[g] < best ? r_g[g] : best;
-                if (has_wall && r_wall > best) drop_wall(tb.wall_pos[u]);
-                if (r_door > best) door_sh |= 1ull << u;
-                if (k_dirt >= 0 && r_dirt > best) dirt_sh |= 1ull << k_dirt;
-#pragma unroll
-                for (int g = 0; g < 6; ++g)
-                  if (r_g[g] > best && u < hi[g] - lo[g]) grp_sh |= 1ull << (lo[g] + u - sl.item0);
-              }
-              // dirt piles with uid >= 64 can only meet the wall of that uid
+              int r_dirt = INF, k_dirt = -1;
               for (int i = 0; i < ndl; ++i) {
                 const uint32_t en = (uint32_t)(dlist >> (16 * i)) & 0xFFFFu;
-                const int uid = (int)(en & 1023u), k = (int)(en >> 10);
-                if (uid < 64 || uid >= sp->n_walls) continue;
-                const uint16_t w = tb.wall_pos[uid];
-                const int rw = rk(w), rd = rk(pos[k]);
-                if (rw < rd) dirt_sh |= 1ull << k;
-                else if (rd < rw) drop_wall(w);
+                if ((int)(en & 1023u) == u) { k_dirt = (int)(en >> 10); r_dirt = rk(pos[k_dirt]); }
               }
-            }
-          }
-
-          const uint32_t* chm = sp->term_chmask[a];
-          const int coff = sp->ch_offset[a];
-          Sprite* spr = s_spr + (size_t)lane * cap;
-          int* cnt = s_cnt + lane;
-          auto put = [&](uint32_t w, float val) {      // the A agent-threads of an env append to one list
-            const int slot = atomicAdd(cnt, 1);
-            if (slot < cap) spr[slot] = Sprite{w, val};
-          };
-          auto emit = [&](uint32_t m, int cell, uint32_t kind, uint32_t aux, float val) {
-            while (m) {
-              const int c = __ffs(m) - 1;
-              m &= m - 1;
-              put((uint32_t)((coff + c) * DD + cell) | (kind << 16) | (aux << 24), val);
-            }
-          };
-          auto cell_of = [&](uint16_t q) -> int {        // window cell if inside the window and visible, else -1
-            const int dx = px(q) - ax + R, dy = py(q) - ay + R;
-            if ((unsigned)dx >= (unsigned)D || (unsigned)dy >= (unsigned)D) return -1;
-            const int cell = dx * D + dy;
-            return ((vis >> cell) & 1) ? cell : -1;
-          };
-          // agents (each agent plane is 1.0 at the agent's cell; stacks add up in Combined planes)
-          for (int j = 0; j < A; ++j) {
-            const uint32_t m = chm[MFG_G_AGENT0 + j];
-            if (!m) continue;
-            const int cell = cell_of(pos[sl.agent0 + j]);
-            if (cell >= 0) emit(m, cell, SK_INT, 0, 1.0f);
-          }
-          // small groups
-          {
-            const int lo[6] = {sl.item0, sl.pod0, sl.dest0, sl.drop0, sl.mach0, sl.maint0};
-            const int hi[6] = {sl.pod0, sl.dest0, sl.drop0, sl.mach0, sl.maint0, sl.agent0};
-            const int term[6] = {MFG_G_ITEMS, MFG_G_PODS, MFG_G_DEST, MFG_G_DROPOFF, MFG_G_MACHINES, MFG_G_MAINT};
+              int best = r_wall < r_door ? r_wall : r_door;
+              best = r_dirt < best ? r_dirt : best;
 #pragma unroll
-            for (int g = 0; g < 6; ++g) {
-              const uint32_t m = chm[term[g]];
-              if (!m) continue;
-              for (int s = lo[g]; s < hi[g]; ++s) {
-                const uint16_t q = pos[s];
-                if (q == NO_POS || !((glisted[g] >> (s - lo[g])) & 1)) continue;
-                if (g == 2 && ((reached >> (s - lo[g])) & 1)) continue;      // a reached destination encodes as 0
-                const int cell = cell_of(q);
-                if (cell >= 0 && !((grp_sh >> (s - sl.item0)) & 1ull)) emit(m, cell, SK_INT, 0, g == 4 ? (float)ENC_MACHINE : 1.0f);
-              }
+              for (int g = 0; g < 6; ++g) best = r_g[g] < best ? r_g[g] : best;
+              if (has_wall && r_wall > best) drop_wall(tb.wall_pos[u]);
+              if (r_door > best) door_w &= ~(1ull << u);
+              if (k_dirt >= 0 && r_dirt > best) dirt_w &= ~(1ull << k_dirt);
+#pragma unroll
+              for (int g = 0; g < 6; ++g)
+                if (r_g[g] > best && u < hi[g] - lo[g]) grp_w &= ~(1ull << (lo[g] + u - sl.item0));
             }
-          }
-          // doors
-          if (chm[MFG_G_DOORS]) {
-            for (int d = 0; d < sp->n_doors; ++d) {
-              if (!((dlisted >> d) & 1)) continue;
-              const int cell = cell_of(tb.door_pos[d]);
-              if (cell >= 0 && !((door_sh >> d) & 1ull)) emit(chm[MFG_G_DOORS], cell, SK_DOOR, (uint32_t)((dopen >> d) & 1), 0.f);
-            }
-          }
-          // dirt piles
-          if (chm[MFG_G_DIRT]) {
-            for (int k = 0; k < sl.item0; ++k) {
-              const uint16_t q = pos[k];
-              if (q == NO_POS || !((dirtlisted >> k) & 1)) continue;
-              const int cell = cell_of(q);
-              if (cell >= 0 && !((dirt_sh >> k) & 1ull)) emit(chm[MFG_G_DIRT], cell, SK_DIRT, (uint32_t)k, 0.f);
-            }
-          }
-          // scalar channels
-          const int C = sp->n_channels[a];
-          for (int c = 0; c < C; ++c) {
-            const int kind = sp->ch_kind[a][c];
-            if (kind == MFG_CH_BATTERY) {
-              put((uint32_t)((coff + c) * DD) | (SK_STORE << 16), (float)field_at(st, st.bat, a, e));
-            } else if (kind == MFG_CH_GLOBALPOS) {
-              put((uint32_t)((coff + c) * DD) | (SK_STORE << 16), (float)((double)ax / (double)sp->H));
-              put((uint32_t)((coff + c) * DD + 1) | (SK_STORE << 16), (float)((double)ay / (double)sp->W));
+            // dirt piles with uid >= 64 can only meet the wall of that uid
+            for (int i = 0; i < ndl; ++i) {
+              const uint32_t en = (uint32_t)(dlist >> (16 * i)) & 0xFFFFu;
+              const int uid = (int)(en & 1023u), k = (int)(en >> 10);
+              if (uid < 64 || uid >= n_walls) continue;
+              const uint16_t w = tb.wall_pos[uid];
+              const int rw = rk(w), rd = rk(pos[k]);
+              if (rw < rd) dirt_w &= ~(1ull << k);
+              else if (rd < rw) drop_wall(w);
             }
           }
         }
-        s_vis[lane * A + a] = vis;
-        s_wv[lane * A + a] = wv;
+
+        // ---- emission: every surviving visible entity becomes one sprite per channel that shows its group
+        const uint32_t* chm = s_chm[a];
+        const int coff = s_coff[a];
+        Sprite* spr = s_spr + (size_t)el * cap;
+        int* cnt = s_cnt + el;
+        auto put = [&](uint32_t w, float val) {      // the A agent-lanes of an env append to one list
+          const int slot = atomicAdd(cnt, 1);
+          if (slot < cap) spr[slot] = Sprite{w, val};
+        };
+        auto emit = [&](uint32_t m, int cell, uint32_t kind, uint32_t aux, float val) {
+          while (m) {
+            const int c = __ffs(m) - 1;
+            m &= m - 1;
+            put((uint32_t)((coff + c) * DD + cell) | (kind << 16) | (aux << 24), val);
+          }
+        };
+        auto wcell = [&](uint16_t q) -> int { return (px(q) - ax + R) * D + (py(q) - ay + R); };   // q is inside the window
+        // agents (each agent plane is 1.0 at the agent's cell; stacks add up in Combined planes)
+        for (int j = 0; j < A; ++j) {
+          const uint32_t m = chm[MFG_G_AGENT0 + j];
+          if (!m) continue;
+          const uint16_t q = pos[sl.agent0 + j];
+          if (classify(q) == 3) emit(m, wcell(q), SK_INT, 0, 1.0f);
+        }
+        // small groups
+        {
+          const int term[6] = {MFG_G_ITEMS, MFG_G_PODS, MFG_G_DEST, MFG_G_DROPOFF, MFG_G_MACHINES, MFG_G_MAINT};
+#pragma unroll
+          for (int g = 0; g < 6; ++g) {
+            const uint32_t cm = chm[term[g]];
+            if (!cm || hi[g] == lo[g]) continue;
+            uint32_t m = (uint32_t)(grp_w >> (lo[g] - sl.item0)) & (uint32_t)((1ull << (hi[g] - lo[g])) - 1ull);
+            if (g == 2) m &= ~reached;                                   // a reached destination encodes as 0
+            for (; m; m &= m - 1) {
+              const int s = lo[g] + __ffs(m) - 1;
+              emit(cm, wcell(pos[s]), SK_INT, 0, g == 4 ? (float)ENC_MACHINE : 1.0f);
+            }
+          }
+        }
+        // doors
+        if (chm[MFG_G_DOORS]) {
+          for (unsigned long long m = door_w; m; m &= m - 1) {
+            const int d = __ffsll((long long)m) - 1;
+            emit(chm[MFG_G_DOORS], wcell(tb.door_pos[d]), SK_DOOR, (uint32_t)((dopen >> d) & 1), 0.f);
+          }
+        }
+        // dirt piles
+        if (chm[MFG_G_DIRT]) {
+          for (unsigned long long m = dirt_w; m; m &= m - 1) {
+            const int k = __ffsll((long long)m) - 1;
+            emit(chm[MFG_G_DIRT], wcell(pos[k]), SK_DIRT, (uint32_t)k, 0.f);
+          }
+        }
+        // scalar channels
+        for (int i = 0; i < s_nscal[a]; ++i) {
+          const int c = s_scal[a][i] & 0xFF, kind = s_scal[a][i] >> 8;
+          if (kind == MFG_CH_BATTERY) {
+            put((uint32_t)((coff + c) * DD) | (SK_STORE << 16), (float)field_at(st, st.bat, a, e));
+          } else if (kind == MFG_CH_GLOBALPOS) {
+            put((uint32_t)((coff + c) * DD) | (SK_STORE << 16), (float)((double)ax / (double)spH));
+            put((uint32_t)((coff + c) * DD + 1) | (SK_STORE << 16), (float)((double)ay / (double)spW));
+          }
+        }
       }
     }
-    __syncthreads();
+    __syncwarp();
 
-    // ---------------- phase 2: one warp per tile of GE envs ------------------------------------------------------
-    const int n_tiles = OBS_ENVS / GE;
-    for (int g = warp; g < n_tiles; g += NW) {
+    // ---------------- phase 2: the warp expands its EPW envs, one tile of GE envs at a time ----------------------
+    const uint32_t wv_lo = (uint32_t)wv, wv_hi = (uint32_t)(wv >> 32);
+    for (int g = 0; g * GE < EPW; ++g) {
       const int64_t eg = env0 + (int64_t)g * GE;
       if (eg >= st.N) break;
-      float* tile = tiles + ((size_t)warp * NBUF + buf) * tile_floats;
-      if (BULK) {
-        // the bulk store that last read this buffer must have finished reading shared memory
-        if (lane == 0) {
-          if (NBUF == 1) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
-          else asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
-        }
-        __syncwarp();
-      }
-      {
-        float4* t4 = reinterpret_cast<float4*>(tile);
-        const int n4 = tile_floats >> 2;
-        for (int i = lane; i < n4; i += 32) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      __syncwarp();
       // Each lane keeps (up to) two sprites of the env in registers across the three passes; further rounds only exist
       // with a raised sprite capacity.  Dirt amounts (f64, uncoalesced) are requested as soon as the sprite is decoded
       // so that their latency overlaps the integer pass.
-      for (int ge = 0; ge < GE; ++ge) {
-        const int el = g * GE + ge;
-        const int64_t e = env0 + el;
-        if (e >= st.N) break;
-        float* te = tile + (size_t)ge * total_channels * DD;
-        const int cnt = s_cnt[el];
+      auto clear_tile = [&]() {
+        if (bulk) {
+          // the bulk store that last read the tile buffer must have finished reading shared memory
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+          __syncwarp();
+        }
+        float4* t4 = reinterpret_cast<float4*>(tile);
+        const int n4 = tile_floats >> 2;
+#pragma unroll 4
+        for (int i = lane; i < n4; i += 32) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncwarp();
-        if (lane == 0) s_cnt[el] = 0;         // every lane holds `cnt`; the list counter is ready for the next group
+      };
+      for (int ge = 0; ge < GE; ++ge) {
+        const int elx = g * GE + ge;
+        const int64_t e = env0 + elx;
+        if (elx >= EPW || e >= st.N) break;
+        float* te = tile + (size_t)ge * total_channels * DD;
+        const int cnt = s_cnt[elx];
         if (cnt > cap) {                      // sprite list overflowed: exact per-agent path straight into the tile
-          for (int a = lane; a < A; a += 32) exact_agent_floats(sp, tb, st, e, a, te + sp->ch_offset[a] * DD, DD);
+          if (ge == 0) clear_tile();
+          for (int a2 = lane; a2 < A; a2 += 32) exact_agent_floats(sp, tb, st, e, a2, te + sp->ch_offset[a2] * DD, DD);
           __syncwarp();
           continue;
         }
@@ -453,22 +481,25 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
         uint32_t k0 = 0xFF, k1 = 0xFF;
         double d0 = 0.0, d1 = 0.0;
         if (lane < cnt) {
-          s0 = s_spr[(size_t)el * cap + lane];
+          s0 = s_spr[(size_t)elx * cap + lane];
           k0 = (s0.w >> 16) & 0xFF;
           if (k0 == SK_DIRT) d0 = field_at(st, st.dirt_amt, (int)(s0.w >> 24), e);
         }
         if (lane + 32 < cnt) {
-          s1 = s_spr[(size_t)el * cap + lane + 32];
+          s1 = s_spr[(size_t)elx * cap + lane + 32];
           k1 = (s1.w >> 16) & 0xFF;
           if (k1 == SK_DIRT) d1 = field_at(st, st.dirt_amt, (int)(s1.w >> 24), e);
         }
+        // (the sprite / dirt-amount loads above are in flight while the previous bulk store drains and the tile is cleared)
+        if (ge == 0) clear_tile();
         // wall planes: 1.0 where a visible wall is.  Nothing else can be on a wall cell, so the (predicated) store has
         // a unique writer and needs no ordering against the sprite adds below.
         for (int w = 0; w < wp.n; ++w) {
-          const uint32_t* wv32 = reinterpret_cast<const uint32_t*>(s_wv + el * A + wp.agent[w]);
+          const int src = (elx << apad_log2) + wp.agent[w];
+          const uint32_t m_lo = __shfl_sync(0xffffffffu, wv_lo, src), m_hi = __shfl_sync(0xffffffffu, wv_hi, src);
           float* plane = te + (int)wp.plane[w] * DD;
-          if ((wv32[0] >> lane) & 1u) plane[lane] = 1.0f;
-          if (lane + 32 < DD && ((wv32[1] >> lane) & 1u)) plane[lane + 32] = 1.0f;
+          if ((m_lo >> lane) & 1u) plane[lane] = 1.0f;
+          if (lane + 32 < DD && ((m_hi >> lane) & 1u)) plane[lane + 32] = 1.0f;
         }
         // pass A: integer-valued sprites (stacks add up exactly) and direct stores
         if (k0 == SK_INT) atomicAdd(&te[s0.w & 0xFFFF], s0.val);
@@ -476,7 +507,7 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
         if (k1 == SK_INT) atomicAdd(&te[s1.w & 0xFFFF], s1.val);
         else if (k1 == SK_STORE) te[s1.w & 0xFFFF] = s1.val;
         for (int i = lane + 64; i < cnt; i += 32) {
-          const Sprite s = s_spr[(size_t)el * cap + i];
+          const Sprite s = s_spr[(size_t)elx * cap + i];
           const uint32_t kind = (s.w >> 16) & 0xFF;
           if (kind == SK_INT) atomicAdd(&te[s.w & 0xFFFF], s.val);
           else if (kind == SK_STORE) te[s.w & 0xFFFF] = s.val;
@@ -489,7 +520,7 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
           if (k0 == SK_DOOR) { float* f = &te[s0.w & 0xFFFF]; *f = (float)((double)*f + ((s0.w >> 24) ? ENC_DOOR_OPEN : ENC_DOOR_CLOSED)); }
           if (k1 == SK_DOOR) { float* f = &te[s1.w & 0xFFFF]; *f = (float)((double)*f + ((s1.w >> 24) ? ENC_DOOR_OPEN : ENC_DOOR_CLOSED)); }
           for (int i = lane + 64; i < cnt; i += 32) {
-            const Sprite s = s_spr[(size_t)el * cap + i];
+            const Sprite s = s_spr[(size_t)elx * cap + i];
             if (((s.w >> 16) & 0xFF) == SK_DOOR) { float* f = &te[s.w & 0xFFFF]; *f = (float)((double)*f + ((s.w >> 24) ? ENC_DOOR_OPEN : ENC_DOOR_CLOSED)); }
           }
         }
@@ -498,19 +529,19 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
           if (k0 == SK_DIRT) { float* f = &te[s0.w & 0xFFFF]; *f = (float)((double)*f + d0); }
           if (k1 == SK_DIRT) { float* f = &te[s1.w & 0xFFFF]; *f = (float)((double)*f + d1); }
           for (int i = lane + 64; i < cnt; i += 32) {
-            const Sprite s = s_spr[(size_t)el * cap + i];
+            const Sprite s = s_spr[(size_t)elx * cap + i];
             if (((s.w >> 16) & 0xFF) == SK_DIRT) { float* f = &te[s.w & 0xFFFF]; *f = (float)((double)*f + field_at(st, st.dirt_amt, (int)(s.w >> 24), e)); }
           }
         }
       }
       // ---- stream the tile out
-      const int ne = (int)((st.N - eg) < GE ? (st.N - eg) : GE);
+      int ne = EPW - g * GE < GE ? EPW - g * GE : GE;
+      if (st.N - eg < ne) ne = (int)(st.N - eg);
       float* dst = obs + (size_t)eg * total_channels * DD;
-      if (BULK && ne == GE) {
+      if (bulk && ne == GE) {
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> visible to the async proxy
         __syncwarp();
         if (lane == 0) bulk_store_tile(dst, tile, (uint32_t)(tile_floats * sizeof(float)));
-        buf = (buf + 1) % NBUF;
       } else {
         __syncwarp();
         const int nfl = ne * total_channels * DD;
@@ -526,7 +557,7 @@ __global__ void k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st,
       }
     }
   }
-  if (BULK && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // smem must outlive the copies
+  if (bulk && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // smem must outlive the copies
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -642,6 +673,7 @@ static void build_vis_tables_r(const MfgSpec& sp, HostTables& t) {
   t.vis_box.assign((size_t)H * W * 4, 0);
   t.wall_cand64.assign((size_t)H * W, 0);
   t.wall_cand_rng.assign((size_t)H * W, 0x0000FFFFu);
+  t.wall_win64.assign((size_t)H * W, 0);
   std::vector<char> cont(T::N);
   for (int x = 0; x < H; ++x)
     for (int y = 0; y < W; ++y) {
@@ -666,7 +698,10 @@ static void build_vis_tables_r(const MfgSpec& sp, HostTables& t) {
           const int xx = x + dx, yy = y + dy, ci = (dx + D) * BW + (dy + D);
           if (xx < 0 || yy < 0 || xx >= H || yy >= W || !t.wall[(size_t)xx * W + yy] || !((vb[ci >> 6] >> (ci & 63)) & 1)) continue;
           const uint32_t u = t.wall_uid[(size_t)xx * W + yy];
-          if (u < 64) t.wall_cand64[(size_t)x * W + y] |= 1ull << u;
+          if (u < 64) {
+            t.wall_cand64[(size_t)x * W + y] |= 1ull << u;
+            if (dx >= -R && dx <= R && dy >= -R && dy <= R) t.wall_win64[(size_t)x * W + y] |= 1ull << u;
+          }
           else { lo = u < lo ? u : lo; hi = u > hi ? u : hi; }
         }
       t.wall_cand_rng[(size_t)x * W + y] = lo | (hi << 16);
@@ -714,7 +749,7 @@ void plan_obs(MfgHandle* h) {
     sl.off_dirt_uid = off_of("dirt_uid");
     const char* ln[6] = {"item_listed", "pod_listed", "dest_listed", "drop_listed", "mach_listed", "maint_listed"};
     for (int g = 0; g < 6; ++g) sl.off_listed[g] = off_of(ln[g]);
-    sl.prefix_bytes = sp.faithful ? end_of("dirt_uid") : end_of("dest_reached");
+    sl.prefix_bytes = sp.faithful ? end_of("dirt_uid") : (sp.has_dirt ? end_of("dirt_listed") : end_of("dest_reached"));
     const bool order_ok = (!sp.has_dirt || off_of("dirt_pos") == 0) && off_of("apos") == sl.agent0 * ENV_BLOCK * 2 &&
                           end_of("apos") <= sl.prefix_bytes && end_of("door_open") <= sl.prefix_bytes;
     if (!order_ok || sl.prefix_bytes % 16) { p.ok = false; return; }
@@ -723,19 +758,20 @@ void plan_obs(MfgHandle* h) {
   }
   const int tcdd = h->total_channels * h->DD;
   p.ge = (tcdd % 4 == 0) ? 1 : (tcdd % 2 == 0) ? 2 : 4;
-  p.nw = sp.n_agents < 2 ? 2 : (sp.n_agents > 8 ? 8 : sp.n_agents);
+  p.apad_log2 = 0;
+  while ((1 << p.apad_log2) < sp.n_agents) ++p.apad_log2;
+  const int epw = 32 >> p.apad_log2;                            // envs per warp pass
   p.cap = 8 * sp.n_agents < 16 ? 16 : 8 * sp.n_agents;        // sprite slots per env (overflow => generic slow path)
   p.cap_max = p.cap;
-  auto smem_for = [&](int nbuf) {
-    size_t b = (size_t)p.nw * nbuf * p.ge * tcdd * sizeof(float);
-    b += (size_t)OBS_ENVS * sp.n_agents * 8 * 2;                           // vis, wv
-    b += (size_t)OBS_ENVS * p.cap * 8;                                     // sprites (one list per env)
-    b += OBS_ENVS * 4;                                                     // cnt
-    b += (size_t)sl.prefix_bytes + 32;                                     // staged block prefix
-    return b;
+  auto smem_for = [&](int nw) {
+    size_t per_warp = (size_t)p.ge * tcdd * sizeof(float) + (size_t)epw * p.cap_max * 8 + 128;   // tile, sprite lists, counters
+    return (size_t)sl.prefix_bytes + 32 + (size_t)nw * per_warp;
   };
-  p.nbuf = smem_for(2) <= 56 * 1024 ? 2 : 1;
-  p.smem = smem_for(p.nbuf);
+  // as many warps as there are sub-groups in a block, at most 8; fewer when the tiles are large
+  p.nw = ENV_BLOCK / epw < 8 ? ENV_BLOCK / epw : 8;
+  while (p.nw > 1 && smem_for(p.nw) > 110 * 1024) p.nw >>= 1;
+  p.smem = smem_for(p.nw);
+  p.nbuf = 1;
   WindowRays wr;
   build_window_rays(sp, wr);
   bool trie_ok = sp.pomdp_r == 1 ? trie_matches<1>(wr) : sp.pomdp_r == 2 ? trie_matches<2>(wr)
@@ -753,50 +789,33 @@ void plan_obs(MfgHandle* h) {
       }
   bool full_ok = !sp.faithful || (sp.pomdp_r == 1 ? full_trie_matches<1>(sp) : sp.pomdp_r == 2 ? full_trie_matches<2>(sp)
                                   : sp.pomdp_r == 3 ? full_trie_matches<3>(sp) : false);
-  if (sp.faithful && (sl.agent0 - sl.item0 > 64 || sp.n_walls > 0xFFFE)) full_ok = false;   // shadow masks are 64-bit
+  if (sl.agent0 - sl.item0 > 64 || sp.n_walls > 0xFFFE || epw < p.ge) full_ok = false;   // 64-bit visibility masks; whole tiles per warp pass
   p.ok = trie_ok && full_ok && walls_fit && p.smem <= 200 * 1024 && tcdd * p.ge <= 0xFFFF;
 }
 
-template <int R, int GE, int NBUF, bool BULK, bool FAITHFUL>
+template <int R, bool FAITHFUL>
 static cudaError_t launch_tiled_f(MfgHandle* h, float* d_obs, cudaStream_t s) {
-  auto kern = k_obs_tiled<R, GE, NBUF, BULK, FAITHFUL>;
+  auto kern = k_obs_tiled<R, FAITHFUL>;
   const ObsPlan& p = h->plan;
   if (p.smem > 40 * 1024) {         // (static shared memory counts against the 48 KB default limit too)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return e;
   }
   const unsigned blocks = (unsigned)((h->N + ENV_BLOCK - 1) / ENV_BLOCK);
-  kern<<<blocks, p.nw * 32, p.smem, s>>>(h->d_sp, h->tb, h->st, p.slots, p.walls, d_obs, h->total_channels, p.cap);
+  kern<<<blocks, p.nw * 32, p.smem, s>>>(h->d_sp, h->tb, h->st, p.slots, p.walls, d_obs, h->total_channels, p.cap, p.apad_log2,
+                                         p.ge, h->obs_store != 0 ? 1 : 0);
   return cudaGetLastError();
-}
-
-template <int R, int GE, int NBUF, bool BULK>
-static cudaError_t launch_tiled_t(MfgHandle* h, float* d_obs, cudaStream_t s) {
-  return h->sp.faithful ? launch_tiled_f<R, GE, NBUF, BULK, true>(h, d_obs, s) : launch_tiled_f<R, GE, NBUF, BULK, false>(h, d_obs, s);
-}
-
-template <int R, int GE>
-static cudaError_t launch_tiled_rg(MfgHandle* h, float* d_obs, cudaStream_t s) {
-  const bool bulk = h->obs_store != 0;
-  if (h->plan.nbuf == 2) return bulk ? launch_tiled_t<R, GE, 2, true>(h, d_obs, s) : launch_tiled_t<R, GE, 1, false>(h, d_obs, s);
-  return bulk ? launch_tiled_t<R, GE, 1, true>(h, d_obs, s) : launch_tiled_t<R, GE, 1, false>(h, d_obs, s);
 }
 
 template <int R>
 static cudaError_t launch_tiled_r(MfgHandle* h, float* d_obs, cudaStream_t s) {
-  switch (h->plan.ge) {
-    case 1: return launch_tiled_rg<R, 1>(h, d_obs, s);
-    case 2: return launch_tiled_rg<R, 2>(h, d_obs, s);
-    default: return launch_tiled_rg<R, 4>(h, d_obs, s);
-  }
+  return h->sp.faithful ? launch_tiled_f<R, true>(h, d_obs, s) : launch_tiled_f<R, false>(h, d_obs, s);
 }
 
 cudaError_t launch_obs_tiled(MfgHandle* h, float* d_obs, cudaStream_t s) {
   switch (h->sp.pomdp_r) {
-#ifndef MFG_OBS_R3_ONLY          // development builds: -DMFG_OBS_R3_ONLY compiles a third of the template instances
     case 1: return launch_tiled_r<1>(h, d_obs, s);
     case 2: return launch_tiled_r<2>(h, d_obs, s);
-#endif
     case 3: return launch_tiled_r<3>(h, d_obs, s);
     default: return cudaErrorInvalidValue;
   }
