@@ -87,6 +87,7 @@ void mfg_destroy(MfgHandle* h) {
   if (h->d_obs) cudaFree(h->d_obs);
   if (h->d_reset_list) cudaFree(h->d_reset_list);
   if (h->d_reset_count) cudaFree(h->d_reset_count);
+  if (h->d_redo) cudaFree(h->d_redo);
   delete h;
 }
 
@@ -145,7 +146,7 @@ int mfg_observe(MfgHandle* h, float* d_obs, void* stream) {
   if (h->obs_kernel == 2 && !h->plan.ok) return fail(MFG_E_UNSUPPORTED, "tiled observation kernel not available for this spec");
   const bool tiled = h->plan.ok && h->obs_kernel != 1;
   CUDA_TRY(tiled ? launch_obs_tiled(h, d_obs, s) : launch_obs_direct(h, d_obs, s));
-  h->launches++;
+  h->launches += tiled ? 2 : 1;       // tiled kernel + its redo pass
   return MFG_OK;
 }
 

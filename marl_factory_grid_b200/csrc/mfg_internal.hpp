@@ -68,6 +68,7 @@ struct MfgHandle {
   int64_t launches = 0;
   uint32_t* d_reset_list = nullptr;   // [N] ids of envs that finished in the current step
   uint32_t* d_reset_count = nullptr;
+  uint32_t* d_redo = nullptr;         // [1 + N] observation redo list: count, env ids (tiled kernel's rare exact path)
   int defer_reset = 1;
 };
 

@@ -113,17 +113,19 @@ __device__ __forceinline__ void bulk_store_tile(float* dst, const float* src_sme
   asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// exact per-agent path (mfg_core.cuh obs_agent_exact) used by the tiled kernel for the rare cases its fast path
-// does not cover: sprite-list overflow (any mode) and possible uid conflicts (faithful mode)
-// ---------------------------------------------------------------------------------------------------------------
-// writes the agent's planes (already zeroed) straight into `out`; rank table on the thread's stack
-__device__ __noinline__ void exact_agent_floats(const MfgSpec* __restrict__ sp, const Tables& tb, const State& st, int64_t e,
-                                                int a, float* out, int DD) {
-  uint8_t rank[RANK_CELLS];
-  FloatSink sink{out, DD, sp->term_chmask[a][MFG_G_WALLS]};
-  if (sp->n_agents <= 4) obs_agent_exact<4>(*sp, tb, st, e, a, rank, sink);
-  else obs_agent_exact<16>(*sp, tb, st, e, a, rank, sink);
+// Envs whose sprite list overflowed (any mode) or that have more uid conflicts than the packed list holds (faithful mode)
+// are appended to a redo list; this kernel rewrites their observations with the exact per-agent path of mfg_core.cuh.
+template <int AMAX>
+__global__ void __launch_bounds__(128) k_obs_redo(const MfgSpec* __restrict__ sp, Tables tb, State st, float* obs, int total_channels,
+                                                  const uint32_t* __restrict__ redo) {
+  const int A = sp->n_agents;
+  const int DD = (2 * sp->pomdp_r + 1) * (2 * sp->pomdp_r + 1);
+  const uint32_t n = redo[0] * (uint32_t)A;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int64_t e = redo[1 + i / A];
+    const int a = (int)(i % A);
+    obs_agent_direct<AMAX>(*sp, tb, st, e, a, obs + ((size_t)e * total_channels + sp->ch_offset[a]) * DD);
+  }
 }
 
 __device__ __forceinline__ void mbar_init1(unsigned long long* bar) {
@@ -148,7 +150,7 @@ __device__ __forceinline__ void mbar_wait0(unsigned long long* bar) {
 template <int R, bool FAITHFUL>
 __global__ void __launch_bounds__(256) k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st, ObsSlots sl, WallPlanes wp,
                                                     float* __restrict__ obs, int total_channels, int cap, int apad_log2,
-                                                    int GE, int bulk) {
+                                                    int GE, int bulk, uint32_t* __restrict__ redo) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long bar;
   // per-agent channel program (lanes of one warp belong to different agents, so it is read with per-lane indices)
@@ -156,6 +158,7 @@ __global__ void __launch_bounds__(256) k_obs_tiled(const MfgSpec* __restrict__ s
   __shared__ uint16_t s_scal[MFG_MAX_AGENTS][4];               // scalar channels: channel | kind << 8
   __shared__ uint8_t s_nscal[MFG_MAX_AGENTS];
   __shared__ int s_coff[MFG_MAX_AGENTS];
+  __shared__ float s_gx[256], s_gy[256];                       // GlobalPosition encodings x / H, y / W (entity/util.py:56-66)
   constexpr int D = 2 * R + 1, DD = D * D;
   const int A = sp->n_agents;
   const int NW = blockDim.x >> 5;
@@ -189,7 +192,11 @@ __global__ void __launch_bounds__(256) k_obs_tiled(const MfgSpec* __restrict__ s
     s_nscal[a] = (uint8_t)n;
     s_coff[a] = sp->ch_offset[a];
   }
-  const int spW = sp->W, spH = sp->H, n_doors = sp->n_doors, n_dest = sp->n_dest, has_dirt = sp->has_dirt, n_walls = sp->n_walls;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    s_gx[i] = (float)((double)i / (double)sp->H);
+    s_gy[i] = (float)((double)i / (double)sp->W);
+  }
+  const int spW = sp->W, n_doors = sp->n_doors, n_dest = sp->n_dest, has_dirt = sp->has_dirt, n_walls = sp->n_walls;
   __syncthreads();
   mbar_wait0(&bar);
   const uint16_t* blk16 = reinterpret_cast<const uint16_t*>(s_blk);
@@ -437,8 +444,8 @@ __global__ void __launch_bounds__(256) k_obs_tiled(const MfgSpec* __restrict__ s
           if (kind == MFG_CH_BATTERY) {
             put((uint32_t)((coff + c) * DD) | (SK_STORE << 16), (float)field_at(st, st.bat, a, e));
           } else if (kind == MFG_CH_GLOBALPOS) {
-            put((uint32_t)((coff + c) * DD) | (SK_STORE << 16), (float)((double)ax / (double)spH));
-            put((uint32_t)((coff + c) * DD + 1) | (SK_STORE << 16), (float)((double)ay / (double)spW));
+            put((uint32_t)((coff + c) * DD) | (SK_STORE << 16), s_gx[ax]);
+            put((uint32_t)((coff + c) * DD + 1) | (SK_STORE << 16), s_gy[ay]);
           }
         }
       }
@@ -471,10 +478,9 @@ __global__ void __launch_bounds__(256) k_obs_tiled(const MfgSpec* __restrict__ s
         if (elx >= EPW || e >= st.N) break;
         float* te = tile + (size_t)ge * total_channels * DD;
         const int cnt = s_cnt[elx];
-        if (cnt > cap) {                      // sprite list overflowed: exact per-agent path straight into the tile
+        if (cnt > cap) {                      // sprite list overflowed (or too many uid conflicts): k_obs_redo rewrites this env
           if (ge == 0) clear_tile();
-          for (int a2 = lane; a2 < A; a2 += 32) exact_agent_floats(sp, tb, st, e, a2, te + sp->ch_offset[a2] * DD, DD);
-          __syncwarp();
+          if (lane == 0) redo[1 + atomicAdd(redo, 1u)] = (uint32_t)(e);
           continue;
         }
         Sprite s0{0u, 0.f}, s1{0u, 0.f};
@@ -801,9 +807,20 @@ static cudaError_t launch_tiled_f(MfgHandle* h, float* d_obs, cudaStream_t s) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return e;
   }
+  if (!h->d_redo) {                  // [0] = count, [1..N] = env ids
+    cudaError_t e = cudaMalloc(&h->d_redo, ((size_t)h->N + 1) * sizeof(uint32_t));
+    if (e != cudaSuccess) return e;
+  }
+  cudaError_t e = cudaMemsetAsync(h->d_redo, 0, sizeof(uint32_t), s);
+  if (e != cudaSuccess) return e;
   const unsigned blocks = (unsigned)((h->N + ENV_BLOCK - 1) / ENV_BLOCK);
   kern<<<blocks, p.nw * 32, p.smem, s>>>(h->d_sp, h->tb, h->st, p.slots, p.walls, d_obs, h->total_channels, p.cap, p.apad_log2,
-                                         p.ge, h->obs_store != 0 ? 1 : 0);
+                                         p.ge, h->obs_store != 0 ? 1 : 0, h->d_redo);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  const unsigned rblocks = blocks < 296u ? blocks : 296u;
+  const int A = h->sp.n_agents;
+  if (A <= 4) k_obs_redo<4><<<rblocks, 128, 0, s>>>(h->d_sp, h->tb, h->st, d_obs, h->total_channels, h->d_redo);
+  else k_obs_redo<16><<<rblocks, 128, 0, s>>>(h->d_sp, h->tb, h->st, d_obs, h->total_channels, h->d_redo);
   return cudaGetLastError();
 }
 
