@@ -160,18 +160,9 @@ def run_engine(args):
     acts = torch.zeros((n_local, A), dtype=torch.int32, device=dev)
     eng.reset()
 
-    def one_step(i, ev=None):
-        if ev is not None:
-            ev[2].record()
+    def one_step(i):
         eng.random_actions(acts, seed=0, step_index=i)
-        if ev is not None:
-            ev[3].record()
-        eng.step(acts, auto_reset=True)
-        if ev is not None:
-            ev[0].record()
-        eng.observe()
-        if ev is not None:
-            ev[1].record()
+        eng.step_observe(acts, auto_reset=True)      # ONE C-ABI call: k_step, packed re-spawn || k_obs_tiled, redo passes
 
     def barrier():
         if world > 1:
@@ -182,26 +173,30 @@ def run_engine(args):
         one_step(i)
     barrier()
     launches0 = eng.info('launches')
-    obs_events = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(4)) for _ in range(args.steps)]
+    # per-kernel durations: CUDA event pairs recorded by the library around its launches, on the launching streams,
+    # during the timed region below (mfg_set_option "timing"; read back after the region)
+    eng.set_option('timing', 1)
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         barrier()
         start.record()
         for i in range(args.steps):
-            one_step(args.warmup + i, obs_events[i])
+            one_step(args.warmup + i)
         stop.record()
         barrier()
     elapsed_ms = start.elapsed_time(stop)
-    obs_ms = sum(ev[0].elapsed_time(ev[1]) for ev in obs_events) / max(args.steps, 1)
-    step_ms = sum(ev[3].elapsed_time(ev[0]) for ev in obs_events) / max(args.steps, 1)
-    rand_ms = sum(ev[2].elapsed_time(ev[3]) for ev in obs_events) / max(args.steps, 1)
+    obs_ms = eng.info('obs_ns') * 1e-6 / max(args.steps, 1)
+    step_ms = eng.info('step_ns') * 1e-6 / max(args.steps, 1)
+    reset_ms = eng.info('reset_ns') * 1e-6 / max(args.steps, 1)
+    eng.set_option('timing', 0)
+    rand_ms = max(elapsed_ms / max(args.steps, 1) - obs_ms - step_ms, 0.0)      # remainder: k_random_actions, redo of re-spawned envs, gaps
     launches = eng.info('launches') - launches0
 
     # episode statistics: the only cross-GPU exchange of the path (one small all-reduce over NVLink)
     from marl_factory_grid_b200.distributed import allreduce_max, allreduce_stats
     stats = allreduce_stats(eng.stats(), device=dev)
     elapsed_ms, obs_ms = allreduce_max(elapsed_ms, dev), allreduce_max(obs_ms, dev)
-    step_ms, rand_ms = allreduce_max(step_ms, dev), allreduce_max(rand_ms, dev)
+    step_ms, rand_ms, reset_ms = allreduce_max(step_ms, dev), allreduce_max(rand_ms, dev), allreduce_max(reset_ms, dev)
 
     # ---- e2e: host buffers through the C-ABI host entry point (H2D actions, D2H reward + done + obs inside the timed region)
     e2e = None
@@ -264,7 +259,8 @@ def run_engine(args):
                                     'achieved': step_bytes * env_steps_per_s / world / 1e9,
                                     'frac': step_bytes * env_steps_per_s / world / 1e9 / peak}},
         'gpu_launches': launches,
-        'kernel_ms': {'k_random_actions': rand_ms, 'k_step': step_ms, 'k_obs': obs_ms},
+        'kernel_ms': {'k_step': step_ms, 'k_obs_tiled+redo': obs_ms, 'k_reset_list (side stream, overlaps k_obs_tiled)': reset_ms,
+                      'rest (k_random_actions, joins, gaps)': rand_ms},
         'clocks': clocks.summary(),
         'episode_stats': {'episodes': int(stats[0]), 'env_steps_in_finished_episodes': int(stats[1]),
                           'collisions': int(stats[8]), 'dirt_overflow': int(stats[9]), 'spawn_fail': int(stats[10])},

@@ -26,6 +26,26 @@ static int upload(MfgHandle* h, const std::vector<T>& v, const T** out) {
   return MFG_OK;
 }
 
+// live kernel timing: event pairs on the launching stream, read back (and released) by mfg_get_info
+struct Timed {
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>>* v; cudaStream_t s; cudaEvent_t b = nullptr, e = nullptr;
+  Timed(MfgHandle* h, std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& vec, cudaStream_t st) : v(h->timing ? &vec : nullptr), s(st) {
+    if (v && cudaEventCreate(&b) == cudaSuccess && cudaEventCreate(&e) == cudaSuccess) cudaEventRecord(b, s); else v = nullptr;
+  }
+  ~Timed() { if (v) { cudaEventRecord(e, s); v->emplace_back(b, e); } }
+};
+static int64_t drain_ns(std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& v) {
+  double ms = 0.0;
+  for (auto& p : v) {
+    float t = 0.f;
+    cudaEventSynchronize(p.second);
+    if (cudaEventElapsedTime(&t, p.first, p.second) == cudaSuccess) ms += t;
+    cudaEventDestroy(p.first); cudaEventDestroy(p.second);
+  }
+  v.clear();
+  return (int64_t)(ms * 1e6);
+}
+
 extern "C" {
 
 const char* mfg_last_error(void) { return g_err.c_str(); }
@@ -88,6 +108,10 @@ void mfg_destroy(MfgHandle* h) {
   if (h->d_reset_list) cudaFree(h->d_reset_list);
   if (h->d_reset_count) cudaFree(h->d_reset_count);
   if (h->d_redo) cudaFree(h->d_redo);
+  drain_ns(h->t_step); drain_ns(h->t_obs); drain_ns(h->t_reset);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->side) cudaStreamDestroy(h->side);
   delete h;
 }
 
@@ -117,8 +141,8 @@ int mfg_reset(MfgHandle* h, const uint8_t* d_env_mask, void* stream) {
   return MFG_OK;
 }
 
-int mfg_step(MfgHandle* h, const int32_t* d_actions, const MfgTape* tape, float* d_reward, uint8_t* d_done,
-             int auto_reset, void* stream) {
+static int step_impl(MfgHandle* h, const int32_t* d_actions, const MfgTape* tape, float* d_reward, uint8_t* d_done,
+                     int auto_reset, void* stream, bool split_reset) {
   NEED_BOUND(h);
   if (!d_actions || !d_reward || !d_done) return fail(MFG_E_INVALID, "mfg_step: NULL buffer");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -134,9 +158,27 @@ int mfg_step(MfgHandle* h, const int32_t* d_actions, const MfgTape* tape, float*
   for (int r = 0; r < h->sp.n_rules; ++r) need_policy |= h->sp.rule_op[r] == MFG_R_MOVE_MAINTAINERS;
   if (need_policy && !io.maint_act && !h->tb.nexthop)
     return fail(MFG_E_INVALID, "mfg_step: MoveMaintainers without a tape needs the next-hop table (MfgSpec.nexthop)");
-  CUDA_TRY(launch_step(h, io, s));
+  if (split_reset) {                 // mfg_step_observe runs the re-spawn itself (overlapped with the observation kernel)
+    Timed t(h, h->t_step, s);
+    CUDA_TRY(launch_step_kernel(h, io, s));
+    h->launches++;
+    return MFG_OK;
+  }
+  {
+    Timed t(h, h->t_step, s);
+    CUDA_TRY(launch_step_kernel(h, io, s));
+  }
+  {
+    Timed t(h, h->t_reset, s);
+    CUDA_TRY(launch_reset_list(h, io, s));
+  }
   h->launches += defer ? 2 : 1;
   return MFG_OK;
+}
+
+int mfg_step(MfgHandle* h, const int32_t* d_actions, const MfgTape* tape, float* d_reward, uint8_t* d_done,
+             int auto_reset, void* stream) {
+  return step_impl(h, d_actions, tape, d_reward, d_done, auto_reset, stream, false);
 }
 
 int mfg_observe(MfgHandle* h, float* d_obs, void* stream) {
@@ -145,6 +187,7 @@ int mfg_observe(MfgHandle* h, float* d_obs, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (h->obs_kernel == 2 && !h->plan.ok) return fail(MFG_E_UNSUPPORTED, "tiled observation kernel not available for this spec");
   const bool tiled = h->plan.ok && h->obs_kernel != 1;
+  Timed t(h, h->t_obs, s);
   CUDA_TRY(tiled ? launch_obs_tiled(h, d_obs, s) : launch_obs_direct(h, d_obs, s));
   h->launches += tiled ? 2 : 1;       // tiled kernel + its redo pass
   return MFG_OK;
@@ -152,9 +195,44 @@ int mfg_observe(MfgHandle* h, float* d_obs, void* stream) {
 
 int mfg_step_observe(MfgHandle* h, const int32_t* d_actions, const MfgTape* tape, float* d_reward, uint8_t* d_done,
                      float* d_obs, int auto_reset, void* stream) {
-  int rc = mfg_step(h, d_actions, tape, d_reward, d_done, auto_reset, stream);
+  NEED_BOUND(h);
+  const bool tiled = h->plan.ok && h->obs_kernel != 1;
+  if (!(auto_reset && h->defer_reset && h->overlap_reset && tiled && d_obs)) {
+    int rc = mfg_step(h, d_actions, tape, d_reward, d_done, auto_reset, stream);
+    if (rc != MFG_OK) return rc;
+    return mfg_observe(h, d_obs, stream);
+  }
+  // Overlapped form.  Finished envs are re-spawned by the packed reset kernel and then observed by the exact per-agent
+  // kernel over the same list, both on a high-priority side stream, WHILE the tiled observation kernel (caller's
+  // stream) covers every other env - it skips the finished ones via the done flags and does not write their tiles.
+  // The side work is latency-bound (a few thousand busy threads); serialised it costs ~8 % of the step.
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!h->side) {
+    int prio_lo = 0, prio_hi = 0;      // highest priority: the few CTAs of the side work must not queue behind the observation grid
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CUDA_TRY(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_hi));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  }
+  int rc = step_impl(h, d_actions, tape, d_reward, d_done, auto_reset, stream, true);
   if (rc != MFG_OK) return rc;
-  return mfg_observe(h, d_obs, stream);
+  StepIO io{};
+  io.auto_reset = 1; io.reset_list = h->d_reset_list; io.reset_count = h->d_reset_count;
+  CUDA_TRY(cudaEventRecord(h->ev_fork, s));
+  CUDA_TRY(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+  {
+    Timed t(h, h->t_reset, h->side);
+    CUDA_TRY(launch_reset_list(h, io, h->side));
+  }
+  CUDA_TRY(launch_obs_list(h, d_obs, h->side, h->d_reset_list, h->d_reset_count));
+  CUDA_TRY(cudaEventRecord(h->ev_join, h->side));
+  {
+    Timed t(h, h->t_obs, s);
+    CUDA_TRY(launch_obs_tiled(h, d_obs, s, d_done));
+  }
+  CUDA_TRY(cudaStreamWaitEvent(s, h->ev_join, 0));
+  h->launches += 4;                   // reset list, tiled observation + its redo pass, observation of the re-spawned envs
+  return MFG_OK;
 }
 
 int mfg_random_actions(MfgHandle* h, int32_t* d_actions, uint64_t seed, uint64_t step_index, void* stream) {
@@ -213,6 +291,8 @@ int mfg_set_option(MfgHandle* h, const char* name, int64_t value) {
     h->plan.cap = (int)value;
     return MFG_OK;
   }
+  if (strcmp(name, "overlap_reset") == 0) { h->overlap_reset = value != 0; return MFG_OK; }
+  if (strcmp(name, "timing") == 0) { h->timing = value != 0; return MFG_OK; }
   if (strcmp(name, "obs_store") == 0) {        // 1 = TMA bulk store of the tile (default), 0 = LDS/STG loop
     h->obs_store = value != 0;
     return MFG_OK;
@@ -223,6 +303,9 @@ int mfg_set_option(MfgHandle* h, const char* name, int64_t value) {
 int64_t mfg_get_info(const MfgHandle* h, const char* name) {
   if (!h || !name) return -1;
   if (strcmp(name, "launches") == 0) return h->launches;
+  if (strcmp(name, "step_ns") == 0) return drain_ns(const_cast<MfgHandle*>(h)->t_step);      // sum since the last read (synchronises)
+  if (strcmp(name, "obs_ns") == 0) return drain_ns(const_cast<MfgHandle*>(h)->t_obs);
+  if (strcmp(name, "reset_ns") == 0) return drain_ns(const_cast<MfgHandle*>(h)->t_reset);
   if (strcmp(name, "tiled_ok") == 0) return h->plan.ok ? 1 : 0;
   if (strcmp(name, "obs_smem") == 0) return (int64_t)h->plan.smem;
   if (strcmp(name, "obs_threads") == 0) return h->plan.nw * 32;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <string>
+#include <utility>
 #include <vector>
 #include "mfg_host.hpp"
 
@@ -70,16 +71,26 @@ struct MfgHandle {
   uint32_t* d_reset_count = nullptr;
   uint32_t* d_redo = nullptr;         // [1 + N] observation redo list: count, env ids (tiled kernel's rare exact path)
   int defer_reset = 1;
+  // mfg_step_observe overlaps the packed re-spawn (side stream) with the observation kernel (caller's stream)
+  int overlap_reset = 1;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // optional live kernel timing (mfg_set_option "timing"): event pairs recorded around the kernels, summed by mfg_get_info
+  int timing = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> t_step, t_obs, t_reset;
 };
 
 namespace mfg {
 // mfg_step.cu
 cudaError_t launch_reset(MfgHandle* h, const uint8_t* d_mask, cudaStream_t s);
 cudaError_t launch_step(MfgHandle* h, const StepIO& io, cudaStream_t s);
+cudaError_t launch_step_kernel(MfgHandle* h, const StepIO& io, cudaStream_t s);
+cudaError_t launch_reset_list(MfgHandle* h, const StepIO& io, cudaStream_t s);
 cudaError_t launch_random_actions(MfgHandle* h, int32_t* d_actions, uint64_t seed, uint32_t step_index, cudaStream_t s);
 // mfg_obs.cu
 void plan_obs(MfgHandle* h);
 void build_vis_tables(const MfgSpec& sp, HostTables& t);
 cudaError_t launch_obs_direct(MfgHandle* h, float* d_obs, cudaStream_t s);
-cudaError_t launch_obs_tiled(MfgHandle* h, float* d_obs, cudaStream_t s);
+cudaError_t launch_obs_tiled(MfgHandle* h, float* d_obs, cudaStream_t s, const uint8_t* skip = nullptr);
+cudaError_t launch_obs_list(MfgHandle* h, float* d_obs, cudaStream_t s, const uint32_t* d_list, const uint32_t* d_count);
 }  // namespace mfg

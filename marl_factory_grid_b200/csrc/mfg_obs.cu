@@ -117,12 +117,12 @@ __device__ __forceinline__ void bulk_store_tile(float* dst, const float* src_sme
 // are appended to a redo list; this kernel rewrites their observations with the exact per-agent path of mfg_core.cuh.
 template <int AMAX>
 __global__ void __launch_bounds__(128) k_obs_redo(const MfgSpec* __restrict__ sp, Tables tb, State st, float* obs, int total_channels,
-                                                  const uint32_t* __restrict__ redo) {
+                                                  const uint32_t* __restrict__ list, const uint32_t* __restrict__ count) {
   const int A = sp->n_agents;
   const int DD = (2 * sp->pomdp_r + 1) * (2 * sp->pomdp_r + 1);
-  const uint32_t n = redo[0] * (uint32_t)A;
+  const uint32_t n = *count * (uint32_t)A;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int64_t e = redo[1 + i / A];
+    const int64_t e = list[i / A];
     const int a = (int)(i % A);
     obs_agent_direct<AMAX>(*sp, tb, st, e, a, obs + ((size_t)e * total_channels + sp->ch_offset[a]) * DD);
   }
@@ -150,7 +150,8 @@ __device__ __forceinline__ void mbar_wait0(unsigned long long* bar) {
 template <int R, bool FAITHFUL>
 __global__ void __launch_bounds__(256) k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st, ObsSlots sl, WallPlanes wp,
                                                     float* __restrict__ obs, int total_channels, int cap, int apad_log2,
-                                                    int GE, int bulk, uint32_t* __restrict__ redo) {
+                                                    int GE, int bulk, uint32_t* __restrict__ redo,
+                                                    const uint8_t* __restrict__ skip) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long bar;
   // per-agent channel program (lanes of one warp belong to different agents, so it is read with per-lane indices)
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(256) k_obs_tiled(const MfgSpec* __restrict__ s
     {
       const int64_t e = env0 + el;
       const int eb = sub * EPW + el;
-      if (a < A && e < st.N) {
+      if (a < A && e < st.N && !(skip && skip[e])) {      // skipped envs (being re-spawned concurrently) are rewritten later
         const BlkPos pos{blk16, eb};
         const unsigned long long dopen = n_doors ? blk_dopen[eb] : 0ull;
         const uint32_t reached = n_dest ? blk_reached[eb] : 0u;
@@ -544,7 +545,18 @@ __global__ void __launch_bounds__(256) k_obs_tiled(const MfgSpec* __restrict__ s
       int ne = EPW - g * GE < GE ? EPW - g * GE : GE;
       if (st.N - eg < ne) ne = (int)(st.N - eg);
       float* dst = obs + (size_t)eg * total_channels * DD;
-      if (bulk && ne == GE) {
+      // envs that are being re-spawned concurrently (skip flags) are written by k_obs_redo, not here
+      bool any_skip = false;
+      if (skip) for (int ge = 0; ge < ne; ++ge) any_skip |= skip[eg + ge] != 0;
+      if (any_skip) {
+        __syncwarp();
+        const int per = total_channels * DD;
+        for (int ge = 0; ge < ne; ++ge) {
+          if (skip[eg + ge]) continue;
+          for (int i = lane; i < per; i += 32) dst[ge * per + i] = tile[ge * per + i];
+        }
+        __syncwarp();
+      } else if (bulk && ne == GE) {
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> visible to the async proxy
         __syncwarp();
         if (lane == 0) bulk_store_tile(dst, tile, (uint32_t)(tile_floats * sizeof(float)));
@@ -799,8 +811,17 @@ void plan_obs(MfgHandle* h) {
   p.ok = trie_ok && full_ok && walls_fit && p.smem <= 200 * 1024 && tcdd * p.ge <= 0xFFFF;
 }
 
+// exact per-agent observation of the envs in a device-side list (k_obs_redo)
+cudaError_t launch_obs_list(MfgHandle* h, float* d_obs, cudaStream_t s, const uint32_t* d_list, const uint32_t* d_count) {
+  const unsigned blocks = (unsigned)((h->N + ENV_BLOCK - 1) / ENV_BLOCK);
+  const unsigned rblocks = blocks < 296u ? blocks : 296u;
+  if (h->sp.n_agents <= 4) k_obs_redo<4><<<rblocks, 128, 0, s>>>(h->d_sp, h->tb, h->st, d_obs, h->total_channels, d_list, d_count);
+  else k_obs_redo<16><<<rblocks, 128, 0, s>>>(h->d_sp, h->tb, h->st, d_obs, h->total_channels, d_list, d_count);
+  return cudaGetLastError();
+}
+
 template <int R, bool FAITHFUL>
-static cudaError_t launch_tiled_f(MfgHandle* h, float* d_obs, cudaStream_t s) {
+static cudaError_t launch_tiled_f(MfgHandle* h, float* d_obs, cudaStream_t s, const uint8_t* skip) {
   auto kern = k_obs_tiled<R, FAITHFUL>;
   const ObsPlan& p = h->plan;
   if (p.smem > 40 * 1024) {         // (static shared memory counts against the 48 KB default limit too)
@@ -815,25 +836,21 @@ static cudaError_t launch_tiled_f(MfgHandle* h, float* d_obs, cudaStream_t s) {
   if (e != cudaSuccess) return e;
   const unsigned blocks = (unsigned)((h->N + ENV_BLOCK - 1) / ENV_BLOCK);
   kern<<<blocks, p.nw * 32, p.smem, s>>>(h->d_sp, h->tb, h->st, p.slots, p.walls, d_obs, h->total_channels, p.cap, p.apad_log2,
-                                         p.ge, h->obs_store != 0 ? 1 : 0, h->d_redo);
+                                         p.ge, h->obs_store != 0 ? 1 : 0, h->d_redo, skip);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  const unsigned rblocks = blocks < 296u ? blocks : 296u;
-  const int A = h->sp.n_agents;
-  if (A <= 4) k_obs_redo<4><<<rblocks, 128, 0, s>>>(h->d_sp, h->tb, h->st, d_obs, h->total_channels, h->d_redo);
-  else k_obs_redo<16><<<rblocks, 128, 0, s>>>(h->d_sp, h->tb, h->st, d_obs, h->total_channels, h->d_redo);
-  return cudaGetLastError();
+  return launch_obs_list(h, d_obs, s, h->d_redo + 1, h->d_redo);
 }
 
 template <int R>
-static cudaError_t launch_tiled_r(MfgHandle* h, float* d_obs, cudaStream_t s) {
-  return h->sp.faithful ? launch_tiled_f<R, true>(h, d_obs, s) : launch_tiled_f<R, false>(h, d_obs, s);
+static cudaError_t launch_tiled_r(MfgHandle* h, float* d_obs, cudaStream_t s, const uint8_t* skip) {
+  return h->sp.faithful ? launch_tiled_f<R, true>(h, d_obs, s, skip) : launch_tiled_f<R, false>(h, d_obs, s, skip);
 }
 
-cudaError_t launch_obs_tiled(MfgHandle* h, float* d_obs, cudaStream_t s) {
+cudaError_t launch_obs_tiled(MfgHandle* h, float* d_obs, cudaStream_t s, const uint8_t* skip) {
   switch (h->sp.pomdp_r) {
-    case 1: return launch_tiled_r<1>(h, d_obs, s);
-    case 2: return launch_tiled_r<2>(h, d_obs, s);
-    case 3: return launch_tiled_r<3>(h, d_obs, s);
+    case 1: return launch_tiled_r<1>(h, d_obs, s, skip);
+    case 2: return launch_tiled_r<2>(h, d_obs, s, skip);
+    case 3: return launch_tiled_r<3>(h, d_obs, s, skip);
     default: return cudaErrorInvalidValue;
   }
 }

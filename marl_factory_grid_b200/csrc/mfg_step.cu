@@ -185,7 +185,8 @@ cudaError_t launch_reset(MfgHandle* h, const uint8_t* d_mask, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_step(MfgHandle* h, const StepIO& io, cudaStream_t s) {
+// k_step alone (the deferred auto-reset list is filled but not consumed)
+cudaError_t launch_step_kernel(MfgHandle* h, const StepIO& io, cudaStream_t s) {
   const unsigned blocks = (unsigned)((h->N + STEP_ENVS - 1) / STEP_ENVS);
   const size_t hw4 = ((size_t)h->sp.H * h->sp.W + 3) / 4 * 4;
   const size_t smem = h->st.blk_i + 2 * hw4 + 2 * MFG_MAX_DOORS + 16;
@@ -198,14 +199,30 @@ cudaError_t launch_step(MfgHandle* h, const StepIO& io, cudaStream_t s) {
     if (smem > 48 * 1024) err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err == cudaSuccess && io.auto_reset && io.reset_list) err = cudaMemsetAsync(io.reset_count, 0, sizeof(uint32_t), s);
     if (err == cudaSuccess) kern<<<blocks, STEP_ENVS, smem, s>>>(hs, h->d_sp, h->tb, h->st, io);
-    if (err == cudaSuccess && io.auto_reset && io.reset_list) {
-      const unsigned rblocks = blocks < 592 ? blocks : 592;
-      auto rk = k_reset_list<AMAX>;
-      if (h->st.blk_i > 48 * 1024) err = cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->st.blk_i);
-      if (err == cudaSuccess) rk<<<rblocks, STEP_ENVS_R, h->st.blk_i, s>>>(h->d_sp, h->tb, h->st, io.reset_list, io.reset_count);
-    }
   });
   return err != cudaSuccess ? err : cudaGetLastError();
+}
+
+// packed re-spawn of the envs k_step appended to the reset list
+cudaError_t launch_reset_list(MfgHandle* h, const StepIO& io, cudaStream_t s) {
+  if (!(io.auto_reset && io.reset_list)) return cudaSuccess;
+  const unsigned blocks = (unsigned)((h->N + STEP_ENVS - 1) / STEP_ENVS);
+  cudaError_t err = cudaSuccess;
+  dispatch_amax(h->sp.n_agents, [&](auto amax) {
+    constexpr int AMAX = decltype(amax)::value;
+    // few CTAs: ~0.2 % of the envs finish per step, and every resident CTA holds a block image in shared memory that
+    // the concurrently running observation kernel could use (grid-stride loop covers larger lists)
+    const unsigned rblocks = blocks < 48 ? blocks : 48;
+    auto rk = k_reset_list<AMAX>;
+    if (h->st.blk_i > 48 * 1024) err = cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->st.blk_i);
+    if (err == cudaSuccess) rk<<<rblocks, STEP_ENVS_R, h->st.blk_i, s>>>(h->d_sp, h->tb, h->st, io.reset_list, io.reset_count);
+  });
+  return err != cudaSuccess ? err : cudaGetLastError();
+}
+
+cudaError_t launch_step(MfgHandle* h, const StepIO& io, cudaStream_t s) {
+  cudaError_t err = launch_step_kernel(h, io, s);
+  return err != cudaSuccess ? err : launch_reset_list(h, io, s);
 }
 
 cudaError_t launch_random_actions(MfgHandle* h, int32_t* d_actions, uint64_t seed, uint32_t step_index, cudaStream_t s) {

@@ -154,22 +154,27 @@ def test_tiled_observation_kernel_equals_direct_kernel_at_scale(cfg, faithful):
 
 
 def test_inline_and_deferred_auto_reset_agree():
-    """The packed reset kernel (default) and the in-line reset inside k_step re-spawn finished envs identically."""
+    """Three forms of auto-reset give identical results: the packed reset kernel overlapped with the observation kernel
+    on a side stream (default of mfg_step_observe), the same kernel serialised, and the in-line reset inside k_step."""
     es = spec_for('cfg4')
-    a, b = _engine(es, 640, faithful=True, seed=9), _engine(es, 640, faithful=True, seed=9)
+    engs = [_engine(es, 640, faithful=True, seed=9) for _ in range(3)]
+    a, b, c = engs
     b.set_option('defer_reset', 0)
-    a.reset()
-    b.reset()
+    c.set_option('overlap_reset', 0)
+    for e in engs:
+        e.reset()
     acts = torch.zeros((640, es.n_agents), dtype=torch.int32, device='cuda:0')
     for t in range(60):
         a.random_actions(acts, seed=2, step_index=t)
         o1, r1, d1 = a.step_observe(acts, auto_reset=True)
-        o2, r2, d2 = b.step_observe(acts, auto_reset=True)
-        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2), t
+        for other in (b, c):
+            o2, r2, d2 = other.step_observe(acts, auto_reset=True)
+            assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2), t
     np.testing.assert_array_equal(a.stats()[:11], b.stats()[:11])
+    np.testing.assert_array_equal(a.stats()[:11], c.stats()[:11])
     assert a.stats()[0] > 0
-    a.close()
-    b.close()
+    for e in engs:
+        e.close()
 
 
 def test_env_shards_are_independent_of_the_partition():
