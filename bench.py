@@ -259,6 +259,7 @@ def run_engine(args):
                                     'achieved': step_bytes * env_steps_per_s / world / 1e9,
                                     'frac': step_bytes * env_steps_per_s / world / 1e9 / peak}},
         'gpu_launches': launches,
+        'obs_launch': {'threads': eng.info('obs_threads'), 'dyn_smem': eng.info('obs_smem'), 'ctas_per_sm': eng.info('obs_ctas_per_sm')},
         'kernel_ms': {'k_step': step_ms, 'k_obs_tiled+redo': obs_ms, 'k_reset_list (side stream, overlaps k_obs_tiled)': reset_ms,
                       'rest (k_random_actions, joins, gaps)': rand_ms},
         'clocks': clocks.summary(),

@@ -89,6 +89,7 @@ cudaError_t launch_reset_list(MfgHandle* h, const StepIO& io, cudaStream_t s);
 cudaError_t launch_random_actions(MfgHandle* h, int32_t* d_actions, uint64_t seed, uint32_t step_index, cudaStream_t s);
 // mfg_obs.cu
 void plan_obs(MfgHandle* h);
+int obs_ctas_per_sm(const MfgHandle* h);
 void build_vis_tables(const MfgSpec& sp, HostTables& t);
 cudaError_t launch_obs_direct(MfgHandle* h, float* d_obs, cudaStream_t s);
 cudaError_t launch_obs_tiled(MfgHandle* h, float* d_obs, cudaStream_t s, const uint8_t* skip = nullptr);

@@ -155,11 +155,9 @@ __global__ void __launch_bounds__(256) k_obs_tiled(const MfgSpec* __restrict__ s
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long bar;
   // per-agent channel program (lanes of one warp belong to different agents, so it is read with per-lane indices)
-  __shared__ uint32_t s_chm[MFG_MAX_AGENTS][MFG_N_TERMS];      // term -> channel bit mask
   __shared__ uint16_t s_scal[MFG_MAX_AGENTS][4];               // scalar channels: channel | kind << 8
   __shared__ uint8_t s_nscal[MFG_MAX_AGENTS];
   __shared__ int s_coff[MFG_MAX_AGENTS];
-  __shared__ float s_gx[256], s_gy[256];                       // GlobalPosition encodings x / H, y / W (entity/util.py:56-66)
   constexpr int D = 2 * R + 1, DD = D * D;
   const int A = sp->n_agents;
   const int NW = blockDim.x >> 5;
@@ -175,6 +173,12 @@ __global__ void __launch_bounds__(256) k_obs_tiled(const MfgSpec* __restrict__ s
   float* tile = reinterpret_cast<float*>(wbase);
   Sprite* s_spr = reinterpret_cast<Sprite*>(wbase + (size_t)tile_floats * 4);               // [EPW][cap]
   int* s_cnt = reinterpret_cast<int*>(wbase + (size_t)tile_floats * 4 + (size_t)EPW * cap * 8);   // [EPW]
+  // misc region behind the per-warp regions: candidate masks (faithful), channel masks, GlobalPosition encodings
+  unsigned char* misc = smem_raw + sl.prefix_bytes + (size_t)NW * per_warp;
+  unsigned long long* s_cm = reinterpret_cast<unsigned long long*>(misc) + (size_t)warp * 128 + lane;      // [NW][4][32]: word w of this lane = s_cm[w * 32]
+  uint32_t* s_chm = reinterpret_cast<uint32_t*>(misc + (FAITHFUL ? (size_t)NW * 1024 : 0));                   // [A][MFG_N_TERMS] term -> channel bits
+  float* s_gx = reinterpret_cast<float*>(s_chm + ((A * MFG_N_TERMS + 3) & ~3));                               // x / H, y / W (entity/util.py:56-66)
+  float* s_gy = s_gx + ((sp->H + 3) & ~3);
   // ---- stage the positional prefix of this block: one TMA bulk copy (dirt/item/.../agent positions, door + dest masks)
   if (threadIdx.x == 0) {
     mbar_init1(&bar);
@@ -182,7 +186,7 @@ __global__ void __launch_bounds__(256) k_obs_tiled(const MfgSpec* __restrict__ s
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(s_blk)),
                  "l"(st.base_i + (size_t)blockIdx.x * st.blk_i), "r"((uint32_t)sl.prefix_bytes), "r"(smem_u32(&bar)) : "memory");
   }
-  for (int i = threadIdx.x; i < A * MFG_N_TERMS; i += blockDim.x) s_chm[i / MFG_N_TERMS][i % MFG_N_TERMS] = sp->term_chmask[i / MFG_N_TERMS][i % MFG_N_TERMS];
+  for (int i = threadIdx.x; i < A * MFG_N_TERMS; i += blockDim.x) s_chm[i] = sp->term_chmask[i / MFG_N_TERMS][i % MFG_N_TERMS];
   if (threadIdx.x < A) {
     const int a = threadIdx.x, C = sp->n_channels[a];
     int n = 0;
@@ -193,10 +197,8 @@ __global__ void __launch_bounds__(256) k_obs_tiled(const MfgSpec* __restrict__ s
     s_nscal[a] = (uint8_t)n;
     s_coff[a] = sp->ch_offset[a];
   }
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-    s_gx[i] = (float)((double)i / (double)sp->H);
-    s_gy[i] = (float)((double)i / (double)sp->W);
-  }
+  for (int i = threadIdx.x; i < sp->H; i += blockDim.x) s_gx[i] = (float)((double)i / (double)sp->H);
+  for (int i = threadIdx.x; i < sp->W; i += blockDim.x) s_gy[i] = (float)((double)i / (double)sp->W);
   const int spW = sp->W, n_doors = sp->n_doors, n_dest = sp->n_dest, has_dirt = sp->has_dirt, n_walls = sp->n_walls;
   __syncthreads();
   mbar_wait0(&bar);
@@ -262,14 +264,28 @@ __global__ void __launch_bounds__(256) k_obs_tiled(const MfgSpec* __restrict__ s
         // part if it is visible: exact `vis` inside the window, the static walls-only visibility (a superset) on the
         // ring between window and radius D.  Ranks are derived only for the uids that really have two candidates.
         constexpr int BW = 2 * D + 1;
-        // returns 0 = not a candidate, 1 = candidate on the ring, 3 = visible inside the window
+        if (FAITHFUL) {
+          // candidate mask of the radius-D box: static walls-only visibility on the ring, the exact `vis` inside the window
+          unsigned long long cm[4] = {sb0, sb1, sb2, sb3};
+#pragma unroll
+          for (int r = 0; r < D; ++r) {
+            constexpr unsigned long long ROW = (1ull << D) - 1ull;
+            const int pos = (r + D - R) * BW + (D - R), w = pos >> 6, sh = pos & 63;      // compile-time after unrolling
+            const unsigned long long row = (vis >> (r * D)) & ROW;
+            cm[w] = (cm[w] & ~(ROW << sh)) | (row << sh);
+            if (sh + D > 64) cm[w + 1] = (cm[w + 1] & ~(ROW >> (64 - sh))) | (row >> (64 - sh));
+          }
+          s_cm[0] = cm[0]; s_cm[32] = cm[1]; s_cm[64] = cm[2]; s_cm[96] = cm[3];
+        }
+        // returns 0 = not a candidate, 1 = candidate on the ring, 3 = visible inside the window (branch-free)
         auto classify = [&](uint16_t q) -> int {
           const int bx = px(q) - ax, by = py(q) - ay;
-          if (bx >= -R && bx <= R && by >= -R && by <= R) return ((vis >> ((bx + R) * D + by + R)) & 1ull) ? 3 : 0;
-          if (!FAITHFUL || bx < -D || bx > D || by < -D || by > D) return 0;
-          const int ci = (bx + D) * BW + by + D, w = ci >> 6;
-          const unsigned long long word = w == 0 ? sb0 : w == 1 ? sb1 : w == 2 ? sb2 : sb3;
-          return (int)((word >> (ci & 63)) & 1ull);
+          const bool inwin = (unsigned)(bx + R) < (unsigned)D && (unsigned)(by + R) < (unsigned)D;
+          if (!FAITHFUL) return (inwin && ((vis >> ((bx + R) * D + by + R)) & 1ull)) ? 3 : 0;
+          const bool inbox = (unsigned)(bx + D) < (unsigned)BW && (unsigned)(by + D) < (unsigned)BW;
+          const int ci = inbox ? (bx + D) * BW + by + D : 0;
+          const uint32_t bit = (uint32_t)(s_cm[(ci >> 6) * 32] >> (ci & 63)) & 1u;
+          return inbox ? (int)(bit | ((inwin ? bit : 0u) << 1)) : 0;
         };
         unsigned long long door_w = 0ull, dirt_w = 0ull, grp_w = 0ull;
         const unsigned long long wc64 = FAITHFUL ? tb.wall_cand64[tile_id] : 0ull;   // walls with uid < 64 that may be visible
@@ -279,18 +295,24 @@ __global__ void __launch_bounds__(256) k_obs_tiled(const MfgSpec* __restrict__ s
         for (unsigned long long m = dnear; m; m &= m - 1) {
           const int d = __ffsll((long long)m) - 1;
           const int c = classify(tb.door_pos[d]);
-          if (c) { dup |= seen & (1ull << d); seen |= 1ull << d; }
-          if (c == 3) { door_w |= 1ull << d; win_uids |= 1ull << d; }
+          const unsigned long long bit = c ? 1ull << d : 0ull, wbit = c == 3 ? bit : 0ull;
+          dup |= seen & bit; seen |= bit;
+          door_w |= wbit; win_uids |= wbit;
         }
+        {
+          // small groups hold at most 32 members: 32-bit uid masks, merged below
+          uint32_t seen32 = (uint32_t)seen, dup32 = 0u, win32 = 0u;
 #pragma unroll
-        for (int g = 0; g < 6; ++g)
-          for (int s = lo[g]; s < hi[g]; ++s) {
-            const uint16_t q = pos[s];
-            if (q == NO_POS || !((glisted[g] >> (s - lo[g])) & 1)) continue;
-            const int c = classify(q);
-            if (c) { dup |= seen & (1ull << (s - lo[g])); seen |= 1ull << (s - lo[g]); }
-            if (c == 3) { grp_w |= 1ull << (s - sl.item0); win_uids |= 1ull << (s - lo[g]); }
-          }
+          for (int g = 0; g < 6; ++g)
+            for (int s = lo[g]; s < hi[g]; ++s) {
+              const uint16_t q = pos[s];
+              const int c = (q != NO_POS && ((glisted[g] >> (s - lo[g])) & 1)) ? classify(q) : 0;
+              const uint32_t bit = c ? 1u << (s - lo[g]) : 0u;
+              dup32 |= seen32 & bit; seen32 |= bit;
+              if (c == 3) { grp_w |= 1ull << (s - sl.item0); win32 |= bit; }
+            }
+          seen |= seen32; dup |= dup32; win_uids |= win32;
+        }
         // dirt piles last (their uids are unique among dirt piles): conflicting ones go to a 4-entry packed list
         unsigned long long dlist = 0ull;
         int ndl = 0;
@@ -387,7 +409,7 @@ __global__ void __launch_bounds__(256) k_obs_tiled(const MfgSpec* __restrict__ s
         }
 
         // ---- emission: every surviving visible entity becomes one sprite per channel that shows its group
-        const uint32_t* chm = s_chm[a];
+        const uint32_t* chm = s_chm + a * MFG_N_TERMS;
         const int coff = s_coff[a];
         Sprite* spr = s_spr + (size_t)el * cap;
         int* cnt = s_cnt + el;
@@ -783,11 +805,13 @@ void plan_obs(MfgHandle* h) {
   p.cap_max = p.cap;
   auto smem_for = [&](int nw) {
     size_t per_warp = (size_t)p.ge * tcdd * sizeof(float) + (size_t)epw * p.cap_max * 8 + 128;   // tile, sprite lists, counters
-    return (size_t)sl.prefix_bytes + 32 + (size_t)nw * per_warp;
+    size_t misc = (sp.faithful ? (size_t)nw * 1024 : 0) + (size_t)((sp.n_agents * MFG_N_TERMS + 3) & ~3) * 4 +
+                  (size_t)((sp.H + 3) & ~3) * 4 + (size_t)((sp.W + 3) & ~3) * 4;      // candidate masks, channel masks, x / H, y / W
+    return (size_t)sl.prefix_bytes + 32 + (size_t)nw * per_warp + misc;
   };
   // as many warps as there are sub-groups in a block, at most 8; fewer when the tiles are large
   p.nw = ENV_BLOCK / epw < 8 ? ENV_BLOCK / epw : 8;
-  while (p.nw > 1 && smem_for(p.nw) > 110 * 1024) p.nw >>= 1;
+  while (p.nw > 1 && smem_for(p.nw) > 115200) p.nw >>= 1;        // two CTAs per SM: (228 KB - 2 x 1 KB reserve) / 2, minus static
   p.smem = smem_for(p.nw);
   p.nbuf = 1;
   WindowRays wr;
@@ -853,6 +877,25 @@ cudaError_t launch_obs_tiled(MfgHandle* h, float* d_obs, cudaStream_t s, const u
     case 3: return launch_tiled_r<3>(h, d_obs, s, skip);
     default: return cudaErrorInvalidValue;
   }
+}
+
+// resident CTAs per SM of the tiled kernel as planned (diagnostics: mfg_get_info "obs_ctas_per_sm")
+template <int R>
+static int ctas_per_sm_r(const MfgHandle* h) {
+  int n = 0;
+  const ObsPlan& p = h->plan;
+  if (h->sp.faithful) {
+    cudaFuncSetAttribute(k_obs_tiled<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_obs_tiled<R, true>, p.nw * 32, p.smem);
+  } else {
+    cudaFuncSetAttribute(k_obs_tiled<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_obs_tiled<R, false>, p.nw * 32, p.smem);
+  }
+  return n;
+}
+int obs_ctas_per_sm(const MfgHandle* h) {
+  if (!h->plan.ok) return 0;
+  return h->sp.pomdp_r == 1 ? ctas_per_sm_r<1>(h) : h->sp.pomdp_r == 2 ? ctas_per_sm_r<2>(h) : ctas_per_sm_r<3>(h);
 }
 
 cudaError_t launch_obs_direct(MfgHandle* h, float* d_obs, cudaStream_t s) {
