@@ -226,8 +226,21 @@ inline void fill_hot_spec(const MfgSpec& s, HotSpec<AMAX>& h) {
   }
 }
 
+// k_step runs against a shared-memory image of the block (integer fields) and of the small level tables; telling the
+// compiler so turns the generic loads / stores of that path into LDS / STS.
+template <typename SpecT> struct spec_traits { static constexpr bool staged = false; };
+template <int AMAX> struct spec_traits<HotSpec<AMAX>> { static constexpr bool staged = true; };
+template <bool STAGED, typename T>
+MFG_HD T& in_stage(T& r) {
+#if defined(__CUDA_ARCH__)
+  if constexpr (STAGED) __builtin_assume(__isShared(&r));
+#endif
+  return r;
+}
+
 template <int AMAX, typename SpecT = MfgSpec>
 struct Env {
+  static constexpr bool STAGED = spec_traits<SpecT>::staged;
   const SpecT& sp;
   const Tables& tb;
   const State& st;
@@ -246,8 +259,10 @@ struct Env {
   }
   template <typename T> MFG_HD T& at(T* base, int row) const {
     if constexpr (std::is_same<T, double>::value) return field_at(st, base, row, eg);
-    else return field_at(st, base, row, e);
+    else return in_stage<STAGED>(field_at(st, base, row, e));
   }
+  // small level tables (wall map, tile -> door map, door positions): staged copies in k_step
+  template <typename T> MFG_HD T tbl(const T* base, int i) const { return in_stage<STAGED>(base[i]); }
 
   MFG_HD void load() {
 #pragma unroll
@@ -278,7 +293,7 @@ struct Env {
 
   // ---------------------------------------------------------------- tile queries
   MFG_HD bool in_grid(int x, int y) const { return x >= 0 && y >= 0 && x < sp.H && y < sp.W; }
-  MFG_HD int door_at(int x, int y) const { int d = tb.door_map[x * sp.W + y]; return d == 0xFF ? -1 : d; }
+  MFG_HD int door_at(int x, int y) const { int d = tbl(tb.door_map, x * sp.W + y); return d == 0xFF ? -1 : d; }
   MFG_HD bool closed_listed_door(int x, int y) const {
     if (!sp.n_doors) return false;
     int d = door_at(x, y);
@@ -300,7 +315,7 @@ struct Env {
   }
   // states.py:259-270 check_pos_validity (negated): wall / off-grid / closed listed door / blocking agent
   MFG_HD bool blocked(int x, int y) const {
-    if (!in_grid(x, y) || tb.wall[x * sp.W + y]) return true;
+    if (!in_grid(x, y) || tbl(tb.wall, x * sp.W + y)) return true;
     if (closed_listed_door(x, y)) return true;
     uint16_t p = mkpos(x, y);
 #pragma unroll
@@ -310,13 +325,13 @@ struct Env {
   // number of collidable LISTED entities on an in-grid tile: agents, maintainers, closed doors, walls
   MFG_HD int n_coll(int x, int y) const {
     uint16_t p = mkpos(x, y);
-    return agents_at(p) + listed_maints_at(p) + (closed_listed_door(x, y) ? 1 : 0) + (tb.wall[x * sp.W + y] ? 1 : 0);
+    return agents_at(p) + listed_maints_at(p) + (closed_listed_door(x, y) ? 1 : 0) + (tbl(tb.wall, x * sp.W + y) ? 1 : 0);
   }
   MFG_HD bool is_free(int x, int y) const { return !blocked(x, y) && n_coll(x, y) == 0; }
 
   // ---------------------------------------------------------------- uid listing (objects.py:193-214)
   MFG_HD bool find_listed(int uid, uint16_t p, int& cls, int& idx) const {
-    if (uid < sp.n_doors && tb.door_pos[uid] == p && ((dlisted >> uid) & 1)) { cls = C_DOOR; idx = uid; return true; }
+    if (uid < sp.n_doors && tbl(tb.door_pos, uid) == p && ((dlisted >> uid) & 1)) { cls = C_DOOR; idx = uid; return true; }
     if (sp.has_dirt && uid < (int)at(st.dirt_next_uid, 0)) {
       for (int k = 0; k < dirt_end; ++k)
         if (at(st.dirt_pos, k) == p && at(st.dirt_uid, k) == uid && ((dirt_listed >> k) & 1)) { cls = C_DIRT; idx = k; return true; }
@@ -350,7 +365,7 @@ struct Env {
     bool valid = false;
     int x = px(p), y = py(p);
     for (int d = 0; d < sp.n_doors; ++d) {
-      uint16_t q = tb.door_pos[d];
+      uint16_t q = tbl(tb.door_pos, d);
       int dx = px(q) - x, dy = py(q) - y;
       if (((dlisted >> d) & 1) && dx >= -1 && dx <= 1 && dy >= -1 && dy <= 1) {
         if ((dopen >> d) & 1) dopen &= ~(1ull << d);
@@ -710,7 +725,7 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
       uint64_t c0 = v.dlisted, c1 = 0;
       auto add = [&](uint16_t q) {
         if (q == NO_POS) return;
-        int d = tb.door_map[px(q) * sp.W + py(q)];
+        int d = v.tbl(tb.door_map, px(q) * sp.W + py(q));
         if (d == 0xFF) return;
         uint64_t b = 1ull << d, carry = c0 & b;
         c0 ^= b;
@@ -836,7 +851,7 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
           }
         }
         for (int d = 0; d < sp.n_doors; ++d) {
-          uint16_t q = tb.door_pos[d];
+          uint16_t q = v.tbl(tb.door_pos, d);
           if (((v.dlisted >> d) & 1) && !((v.dopen >> d) & 1) && v.n_coll(px(q), py(q)) >= 2) {
             if (sp.faithful && d < 32 && ((seen >> d) & 1)) continue;   // `x.entity == guest` is uid equality
             ++n_other;
@@ -974,7 +989,7 @@ struct ObsCtx {
   MFG_HD ObsCtx(Env<AMAX>& v_, uint8_t* rank_) : v(v_), rank(rank_) {}
   MFG_HD bool blocks_light(int x, int y) const {
     if (!v.in_grid(x, y)) return false;
-    return v.tb.wall[x * v.sp.W + y] || v.closed_listed_door(x, y);
+    return v.tbl(v.tb.wall, x * v.sp.W + y) || v.closed_listed_door(x, y);
   }
   MFG_HD int rank_of(uint16_t p) const {
     if (p == NO_POS) return RANK_INF;
@@ -990,7 +1005,7 @@ template <int AMAX>
 MFG_HD bool uid_shadowed(const ObsCtx<AMAX>& o, int cls, int idx, int uid, int my_rank) {
   const Env<AMAX>& v = o.v; const MfgSpec& sp = v.sp; const State& st = v.st; const Tables& tb = v.tb;
   if (uid < sp.n_walls && o.rank_of(tb.wall_pos[uid]) < my_rank) return true;      // walls are always listed
-  if (uid < sp.n_doors && cls != C_DOOR && ((v.dlisted >> uid) & 1) && o.rank_of(tb.door_pos[uid]) < my_rank) return true;
+  if (uid < sp.n_doors && cls != C_DOOR && ((v.dlisted >> uid) & 1) && o.rank_of(v.tbl(tb.door_pos, uid)) < my_rank) return true;
   if (sp.has_dirt && uid < (int)v.at(st.dirt_next_uid, 0)) {
     for (int k = 0; k < v.dirt_end; ++k) {
       if (cls == C_DIRT && k == idx) continue;
@@ -1055,14 +1070,14 @@ MFG_HDN void obs_agent_exact(const MfgSpec& sp, const Tables& tb, const State& s
   if (chm[MFG_G_WALLS]) {
     for (int dx = -r; dx <= r; ++dx) for (int dy = -r; dy <= r; ++dy) {
       int x = o.ax + dx, y = o.ay + dy;
-      if (!v.in_grid(x, y) || !tb.wall[x * sp.W + y]) continue;
+      if (!v.in_grid(x, y) || !v.tbl(tb.wall, x * sp.W + y)) continue;
       int rk = rank[(dx + R) * BW + (dy + R)];
       if (rk == RANK_INF) continue;
       if (sp.faithful) {
         // walls are never shadowed by other walls; only a dynamic entity with the same uid seen earlier hides it
         int uid = tb.wall_uid[x * sp.W + y];
         bool sh = false;
-        if (uid < sp.n_doors && ((v.dlisted >> uid) & 1) && o.rank_of(tb.door_pos[uid]) < rk) sh = true;
+        if (uid < sp.n_doors && ((v.dlisted >> uid) & 1) && o.rank_of(v.tbl(tb.door_pos, uid)) < rk) sh = true;
         if (!sh && sp.has_dirt && uid < (int)v.at(st.dirt_next_uid, 0))
           for (int k = 0; k < v.dirt_end && !sh; ++k)
             sh = v.at(st.dirt_uid, k) == uid && ((v.dirt_listed >> k) & 1) && o.rank_of(v.at(st.dirt_pos, k)) < rk;
@@ -1101,7 +1116,7 @@ MFG_HDN void obs_agent_exact(const MfgSpec& sp, const Tables& tb, const State& s
   // ---- doors, then dirt (fractional encodings go last so that integer stacks are summed exactly first)
   if (chm[MFG_G_DOORS]) {
     for (int d = 0; d < sp.n_doors; ++d) {
-      uint16_t p = tb.door_pos[d];
+      uint16_t p = v.tbl(tb.door_pos, d);
       int cell;
       if (!((v.dlisted >> d) & 1) || !in_window(p, cell)) continue;
       int rk = o.rank_of(p);
