@@ -970,7 +970,13 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
       if (io.reset_list) io.reset_list[atomicAdd(io.reset_count, 1u)] = (uint32_t)v.eg;
       else
 #endif
-        env_reset<AMAX>(full, tb, st, v.e, v.at(st.episode, 0) + 1, v.eg);
+      {
+        // copies: the call must not make the caller's State / Tables escape (they would then live in local memory and
+        // every field access of the hot path would become a dependent local load)
+        const State st2 = st;
+        const Tables tb2 = tb;
+        env_reset<AMAX>(full, tb2, st2, v.e, v.at(st.episode, 0) + 1, v.eg);
+      }
     }
   }
 }
