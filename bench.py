@@ -104,7 +104,7 @@ class ClockSampler:
                     self.rows.append([x.strip() for x in out.split(',')])
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(0.1)
 
     def __enter__(self):
         self.thread.start()
@@ -135,25 +135,18 @@ def hbm_peak():
 # ---------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------------
-def run_engine(args):
+def measure(args, parity, steps, warmup, dev, rank, world, local, with_e2e):
+    """One timed pass in one parity mode.  Returns the measurements of this rank (times max-reduced over ranks)."""
     import torch
     import torch.distributed as dist
     from marl_factory_grid_b200 import FactoryConfigParser
+    from marl_factory_grid_b200.distributed import allreduce_max, allreduce_stats
     from marl_factory_grid_b200.engine import Engine
-
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
 
     es = FactoryConfigParser(CONFIGS / f'{args.config}.yaml').compile()
     n_local = args.envs_per_gpu
     A = es.n_agents
-    eng = Engine(es, n_local, device=dev, faithful=args.parity == 'faithful', seed=es.env_seed,
-                 env_id_offset=rank * n_local)
+    eng = Engine(es, n_local, device=dev, faithful=parity == 'faithful', seed=es.env_seed, env_id_offset=rank * n_local)
     if args.obs_kernel:
         eng.set_option('obs_kernel', args.obs_kernel)
     eng.set_option('obs_store', args.obs_store)
@@ -162,14 +155,14 @@ def run_engine(args):
 
     def one_step(i):
         eng.random_actions(acts, seed=0, step_index=i)
-        eng.step_observe(acts, auto_reset=True)      # ONE C-ABI call: k_step, packed re-spawn || k_obs_tiled, redo passes
+        eng.step_observe(acts, auto_reset=True)      # ONE C-ABI call: k_step, then packed re-spawn || k_obs_tiled, redo passes
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for i in range(args.warmup):
+    for i in range(warmup):
         one_step(i)
     barrier()
     launches0 = eng.info('launches')
@@ -180,28 +173,27 @@ def run_engine(args):
     with ClockSampler(local) as clocks:
         barrier()
         start.record()
-        for i in range(args.steps):
-            one_step(args.warmup + i)
+        for i in range(steps):
+            one_step(warmup + i)
         stop.record()
         barrier()
     elapsed_ms = start.elapsed_time(stop)
-    obs_ms = eng.info('obs_ns') * 1e-6 / max(args.steps, 1)
-    step_ms = eng.info('step_ns') * 1e-6 / max(args.steps, 1)
-    reset_ms = eng.info('reset_ns') * 1e-6 / max(args.steps, 1)
+    obs_ms = eng.info('obs_ns') * 1e-6 / max(steps, 1)
+    step_ms = eng.info('step_ns') * 1e-6 / max(steps, 1)
+    reset_ms = eng.info('reset_ns') * 1e-6 / max(steps, 1)
     eng.set_option('timing', 0)
-    rand_ms = max(elapsed_ms / max(args.steps, 1) - obs_ms - step_ms, 0.0)      # remainder: k_random_actions, redo of re-spawned envs, gaps
     launches = eng.info('launches') - launches0
 
     # episode statistics: the only cross-GPU exchange of the path (one small all-reduce over NVLink)
-    from marl_factory_grid_b200.distributed import allreduce_max, allreduce_stats
     stats = allreduce_stats(eng.stats(), device=dev)
     elapsed_ms, obs_ms = allreduce_max(elapsed_ms, dev), allreduce_max(obs_ms, dev)
-    step_ms, rand_ms, reset_ms = allreduce_max(step_ms, dev), allreduce_max(rand_ms, dev), allreduce_max(reset_ms, dev)
+    step_ms, reset_ms = allreduce_max(step_ms, dev), allreduce_max(reset_ms, dev)
+    rest_ms = max(elapsed_ms / max(steps, 1) - obs_ms - step_ms, 0.0)
 
     # ---- e2e: host buffers through the C-ABI host entry point (H2D actions, D2H reward + done + obs inside the timed region)
     e2e = None
-    if not args.no_e2e:
-        k2 = max(1, min(args.steps, args.e2e_steps))
+    if with_e2e:
+        k2 = max(1, min(steps, args.e2e_steps))
         h_act = torch.zeros((n_local, A), dtype=torch.int32).pin_memory()
         h_rew = torch.zeros((n_local, eng.n_rew), dtype=torch.float32).pin_memory()
         h_done = torch.zeros(n_local, dtype=torch.uint8).pin_memory()
@@ -222,37 +214,28 @@ def run_engine(args):
         e2e = {'value': world * n_local * A * k2 / float(t_e2e[0]), 'unit': UNIT, 'steps': k2,
                'h2d_bytes_per_step': int(h_act.numel() * 4) * world,
                'd2h_bytes_per_step': int(h_rew.numel() * 4 + h_done.numel() + h_obs.numel() * 4) * world,
-               'note': 'mfg_step_host: pinned host actions in, reward + done + full observation tensor out, synchronous'}
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+               'note': 'mfg_step_host: pinned host actions in, reward + done + full observation tensor out, synchronous '
+                       '(PCIe-bound: the dense f32 observation tensor is 7 KB per env)'}
+        del h_obs
 
     total_envs = world * n_local
-    env_steps_per_s = total_envs * args.steps / (elapsed_ms * 1e-3)
-    value = env_steps_per_s * A
+    env_steps_per_s = total_envs * steps / (elapsed_ms * 1e-3)
     peak, peak_src = hbm_peak()
     obs_bytes = 4 * es.obs_d ** 2 * es.total_channels + es.algorithmic_state_bytes()       # obs write + state read, per env
     step_bytes = es.algorithmic_bytes_per_env_step()
     achieved = obs_bytes * n_local / (obs_ms * 1e-3) / 1e9
+    tiled = bool(eng.info('tiled_ok')) and args.obs_kernel != 1
     traffic = None
     tp = ROOT / 'profiles' / 'obs_kernel_traffic.json'
     if tp.exists():
         try:
-            traffic = json.loads(tp.read_text()).get(f'{args.config}:{n_local}')
+            traffic = json.loads(tp.read_text()).get(f'{args.config}:{parity}:{n_local}')
         except Exception:
             traffic = None
-    line = {
-        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': elapsed_ms / max(args.steps, 1), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'u16/f64 state, f32 obs', 'data': 'synthetic',
-        'config': {'workload': f'{args.config} all-modules (level large, 4 agents, POMDP r=3), {n_local} envs per GPU',
-                   'envs_total': total_envs, 'agents': A, 'parity': args.parity, 'obs_kernel': 'tiled' if eng.info('tiled_ok') and args.obs_kernel != 1 else 'direct',
-                   'l2': f'per-step working set {step_bytes * n_local / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed)',
-                   'actions': 'device Philox, regenerated every step (inside the timed region)', 'auto_reset': True},
-        'env_steps_per_s': env_steps_per_s,
-        'roofline': {'bound': 'hbm', 'kernel': 'k_obs_tiled' if eng.info('tiled_ok') and args.obs_kernel != 1 else 'k_obs_direct',
+    out = {
+        'A': A, 'parity': parity, 'steps': steps, 'value': env_steps_per_s * A, 'env_steps_per_s': env_steps_per_s,
+        'ms_per_step': elapsed_ms / max(steps, 1), 'tiled': tiled, 'step_bytes': step_bytes, 'n_local': n_local,
+        'roofline': {'bound': 'hbm', 'kernel': 'k_obs_tiled' if tiled else 'k_obs_direct',
                      'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
                      'peak_source': peak_src, 'bytes_per_env': obs_bytes, 'ms_per_launch': obs_ms,
                      'whole_step': {'bytes_per_env_step': step_bytes,
@@ -260,14 +243,63 @@ def run_engine(args):
                                     'frac': step_bytes * env_steps_per_s / world / 1e9 / peak}},
         'gpu_launches': launches,
         'obs_launch': {'threads': eng.info('obs_threads'), 'dyn_smem': eng.info('obs_smem'), 'ctas_per_sm': eng.info('obs_ctas_per_sm')},
-        'kernel_ms': {'k_step': step_ms, 'k_obs_tiled+redo': obs_ms, 'k_reset_list (side stream, overlaps k_obs_tiled)': reset_ms,
-                      'rest (k_random_actions, joins, gaps)': rand_ms},
+        'kernel_ms': {'k_step': step_ms, 'k_obs_tiled+redo': obs_ms, 'k_reset_list+k_obs_redo (side stream, overlaps k_obs_tiled)': reset_ms,
+                      'rest (k_random_actions, joins, gaps)': rest_ms},
         'clocks': clocks.summary(),
         'episode_stats': {'episodes': int(stats[0]), 'env_steps_in_finished_episodes': int(stats[1]),
                           'collisions': int(stats[8]), 'dirt_overflow': int(stats[9]), 'spawn_fail': int(stats[10])},
+        'e2e': e2e,
     }
-    if e2e is not None:
-        line['e2e'] = e2e
+    eng.close()
+    del eng, acts
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_engine(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    m = measure(args, args.parity, args.steps, args.warmup, dev, rank, world, local, with_e2e=not args.no_e2e)
+    other = None
+    if not args.no_other_mode:
+        other_parity = 'identity' if args.parity == 'faithful' else 'faithful'
+        other = measure(args, other_parity, min(args.steps, 50), min(args.warmup, 5), dev, rank, world, local, with_e2e=False)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    n_local, A = m['n_local'], m['A']
+    line = {
+        'metric': METRIC, 'value': m['value'], 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': m['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'u16/f64 state, f32 obs', 'data': 'synthetic',
+        'config': {'workload': f'{args.config} all-modules (level large, 4 agents, POMDP r=3), {n_local} envs per GPU',
+                   'envs_total': world * n_local, 'agents': A, 'parity': m['parity'],
+                   'parity_note': 'faithful = the untouched reference incl. its uid-equality artefact (bit-exact vs oracle-U traces); '
+                                  'identity = the identity-patched reference (oracle-I), reported under other_parity_mode',
+                   'obs_kernel': 'tiled' if m['tiled'] else 'direct',
+                   'l2': f'per-step working set {m["step_bytes"] * n_local / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed)',
+                   'actions': 'device Philox, regenerated every step (inside the timed region)', 'auto_reset': True},
+        'env_steps_per_s': m['env_steps_per_s'],
+        'roofline': m['roofline'], 'gpu_launches': m['gpu_launches'], 'obs_launch': m['obs_launch'], 'kernel_ms': m['kernel_ms'],
+        'clocks': m['clocks'], 'episode_stats': m['episode_stats'],
+    }
+    if other is not None:
+        line['other_parity_mode'] = {k: other[k] for k in ('parity', 'steps', 'value', 'env_steps_per_s', 'ms_per_step', 'kernel_ms')}
+        line['other_parity_mode']['roofline'] = {k: other['roofline'][k] for k in ('kernel', 'achieved', 'frac', 'ms_per_launch', 'whole_step')}
+    if m['e2e'] is not None:
+        line['e2e'] = m['e2e']
     if world == 1 and not args.no_cpu:
         procs = os.cpu_count() or 1
         pool = CpuPool(args.config, args.parity == 'faithful', procs)
@@ -285,18 +317,19 @@ def run_engine(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='engine', choices=['engine', 'reference'])
     ap.add_argument('--config', default='cfg4')
     ap.add_argument('--envs-per-gpu', type=int, default=1 << 20)
-    ap.add_argument('--parity', default='identity', choices=['identity', 'faithful'])
+    ap.add_argument('--parity', default='faithful', choices=['identity', 'faithful'])
     ap.add_argument('--obs-kernel', type=int, default=0, help='0 auto, 1 direct, 2 tiled')
     ap.add_argument('--obs-store', type=int, default=1, help='1 TMA bulk store of the tile, 0 LDS/STG loop')
     ap.add_argument('--e2e-steps', type=int, default=5)
     ap.add_argument('--cpu-steps', type=int, default=3000, help='env-steps per CPU worker for the baseline sample')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-other-mode', action='store_true', help='skip the short second pass in the other parity mode')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'engine':
         args.warmup = 3
