@@ -21,9 +21,14 @@
 #if defined(__CUDACC__)
 #define MFG_HD __host__ __device__ __forceinline__
 #define MFG_HDN __host__ __device__
+#define MFG_HDNI __host__ __device__ __noinline__      // rare, large: kept out of the callers' instruction stream
+// tiny run-time trip counts, inlined at dozens of call sites: unrolling them quadruples the kernel image (icache misses)
+#define MFG_NOUNROLL _Pragma("unroll 1")
 #else
 #define MFG_HD inline
 #define MFG_HDN inline
+#define MFG_HDNI inline
+#define MFG_NOUNROLL
 #endif
 
 namespace mfg {
@@ -309,6 +314,7 @@ struct Env {
     int n = 0;
     if (sp.n_maint) {
       uint32_t l = at(st.maint_listed, 0);
+      MFG_NOUNROLL
       for (int k = 0; k < sp.n_maint; ++k) n += (((l >> k) & 1) && at(st.maint_pos, k) == p) ? 1 : 0;
     }
     return n;
@@ -333,9 +339,11 @@ struct Env {
   MFG_HD bool find_listed(int uid, uint16_t p, int& cls, int& idx) const {
     if (uid < sp.n_doors && tbl(tb.door_pos, uid) == p && ((dlisted >> uid) & 1)) { cls = C_DOOR; idx = uid; return true; }
     if (sp.has_dirt && uid < (int)at(st.dirt_next_uid, 0)) {
+      MFG_NOUNROLL
       for (int k = 0; k < dirt_end; ++k)
         if (at(st.dirt_pos, k) == p && at(st.dirt_uid, k) == uid && ((dirt_listed >> k) & 1)) { cls = C_DIRT; idx = k; return true; }
     }
+    MFG_NOUNROLL
     for (int c = C_ITEM; c <= C_MAINT; ++c) {
       if (uid < cls_count(c) && at(cls_pos(c), uid) == p && ((at(cls_listed(c), 0) >> uid) & 1)) { cls = c; idx = uid; return true; }
     }
@@ -364,6 +372,7 @@ struct Env {
   MFG_HD bool toggle_near(uint16_t p) {
     bool valid = false;
     int x = px(p), y = py(p);
+    MFG_NOUNROLL
     for (int d = 0; d < sp.n_doors; ++d) {
       uint16_t q = tbl(tb.door_pos, d);
       int dx = px(q) - x, dy = py(q) - y;
@@ -378,17 +387,20 @@ struct Env {
 
   // ---------------------------------------------------------------- dirt (clean_up/groups.py:70-95, actions.py:19-36)
   MFG_HD int dirt_at(uint16_t p) const {
+    MFG_NOUNROLL
     for (int k = 0; k < dirt_end; ++k) if (at(st.dirt_pos, k) == p) return k;
     return -1;
   }
   MFG_HD double dirt_sum() const {
     double s = 0.0;
+    MFG_NOUNROLL
     for (int k = 0; k < dirt_end; ++k) if (at(st.dirt_pos, k) != NO_POS) s += at(st.dirt_amt, k);
     return s;
   }
   MFG_HD void dirt_compact() {
     int w = 0;
     uint64_t nl = 0;
+    MFG_NOUNROLL
     for (int k = 0; k < dirt_end; ++k) {
       uint16_t p = at(st.dirt_pos, k);
       if (p == NO_POS) continue;
@@ -396,6 +408,7 @@ struct Env {
       if ((dirt_listed >> k) & 1) nl |= 1ull << w;
       ++w;
     }
+    MFG_NOUNROLL
     for (int k = w; k < dirt_end; ++k) at(st.dirt_pos, k) = NO_POS;
     dirt_end = w; dirt_listed = nl;
   }
@@ -453,6 +466,7 @@ struct Env {
       uint16_t p = tb.floor_pos[rng.below((uint32_t)sp.n_floor)];
       int x = px(p), y = py(p);
       bool ok = must_be_empty ? (agents_at(p) == 0 && (sp.n_doors == 0 || door_at(x, y) < 0)) : is_free(x, y);
+      MFG_NOUNROLL
       for (int j = 0; ok && j < n_taken; ++j) ok = taken[j] != p;
       if (ok) return p;
     }
@@ -479,7 +493,7 @@ MFG_HD void stat_add_f64(const Tables& tb, int idx, double v) {
 // reset: Factory.reset with a fresh Factory: SpawnAgents, then the groups in Entities order
 // ================================================================================================
 template <int AMAX>
-MFG_HDN void env_reset(const MfgSpec& sp, const Tables& tb, const State& st, int64_t e, uint32_t episode,
+MFG_HDNI void env_reset(const MfgSpec& sp, const Tables& tb, const State& st, int64_t e, uint32_t episode,
                        int64_t eg = -1) {
   Env<AMAX> v(sp, tb, st, e, eg);
   const int A = v.A;
@@ -510,8 +524,10 @@ MFG_HDN void env_reset(const MfgSpec& sp, const Tables& tb, const State& st, int
     for (int r = 0; r < sp.n_rules; ++r) if (sp.rule_op[r] == MFG_R_RESPAWN_DIRT) next = (int16_t)sp.rule_param[r][0];
     v.at(st.dirt_next_spawn, 0) = next;              // clean_up/rules.py:47 (fresh rule object)
   }
+  MFG_NOUNROLL
   for (int c = C_ITEM; c <= C_MAINT; ++c) {
     int n = v.cls_count(c);
+    MFG_NOUNROLL
     for (int k = 0; k < n; ++k) v.at(v.cls_pos(c), k) = NO_POS;
     if (n) v.at(v.cls_listed(c), 0) = 0;
   }
@@ -693,16 +709,19 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
       }
     } else if (op == MFG_OP_ITEM) {                            // items/actions.py:41-63
       bool on_drop = false;
+      MFG_NOUNROLL
       for (int k = 0; k < sp.n_dropoff; ++k) on_drop |= v.at(st.drop_pos, k) == p;
       if (on_drop) { use_extra = true; r_extra = sp.act_aux[i][a]; }
       else {
         int it = -1;
+        MFG_NOUNROLL
         for (int k = 0; k < sp.n_items && it < 0; ++k) if (v.at(st.item_pos, k) == p) it = k;
         ok = it >= 0;
         if (ok) { v.l_del(C_ITEM, it, it, p); v.set_listed(C_ITEM, it, false); v.at(st.item_pos, it) = NO_POS; }
       }
     } else if (op == MFG_OP_CHARGE) {                          // batteries/actions.py:20-31, entitites.py:98-111
       bool on_pod = false;
+      MFG_NOUNROLL
       for (int k = 0; k < sp.n_pods; ++k) on_pod |= v.at(st.pod_pos, k) == p;
       if (on_pod) {
         double b = bat[i];
@@ -711,6 +730,7 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
     } else if (op == MFG_OP_DEST) {                            // destinations/actions.py:17-24 (reference raises on a dest)
       ok = false;
     } else if (op == MFG_OP_MACHINE) {                         // machines/actions.py:19-25
+      MFG_NOUNROLL
       for (int k = 0; k < sp.n_machines; ++k) ok |= v.at(st.mach_pos, k) == p;
     }
     rew[i] += use_extra ? r_extra : (ok ? sp.act_valid[i][a] : sp.act_fail[i][a]);
@@ -736,12 +756,15 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
 #pragma unroll
       for (int i = 0; i < AMAX; ++i) if (i < A) add(v.apos[i]);
       if (sp.has_dirt) for (int k = 0; k < v.dirt_end; ++k) if ((v.dirt_listed >> k) & 1) add(v.at(st.dirt_pos, k));
+      MFG_NOUNROLL
       for (int c = C_ITEM; c <= C_MAINT; ++c) {
         int n = v.cls_count(c);
         if (!n) continue;
         uint32_t l = v.at(v.cls_listed(c), 0);
+        MFG_NOUNROLL
         for (int k = 0; k < n; ++k) if ((l >> k) & 1) add(v.at(v.cls_pos(c), k));
       }
+      MFG_NOUNROLL
       for (int d = 0; d < sp.n_doors; ++d) {
         int n = (int)((c0 >> d) & 1) + 2 * (int)((c1 >> d) & 1);
         if (n <= 2) {
@@ -907,6 +930,7 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
       for (int i = 0; i < AMAX; ++i) {
         if (i >= A) continue;
         bool hit = false;
+        MFG_NOUNROLL
         for (int k = 0; k < sp.n_maint; ++k) hit |= v.at(st.maint_pos, k) == v.apos[i];
         if (hit) { fired = true; rew[i] += -5.0; }
       }
