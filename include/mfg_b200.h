@@ -141,7 +141,7 @@ void mfg_destroy(MfgHandle* h);
 const char* mfg_last_error(void);
 const char* mfg_version(void);
 
-/* State lives in ONE caller-owned device buffer of mfg_state_bytes(h) bytes, laid out field-major:
+/* State lives in ONE caller-owned device buffer of mfg_state_bytes(h) bytes:
  * BLOCKED struct-of-arrays: envs are grouped in blocks of 128; a block stores every row of every integer / byte field
  * back to back as [rows][128] slabs (one contiguous range => one TMA bulk copy stages it), a second region stores the
  * f64 fields the same way.  Within a slab the env index is the fastest one (coalesced per warp). */
@@ -155,8 +155,11 @@ int mfg_reset(MfgHandle* h, const uint8_t* d_env_mask, void* stream);
  * are not individual), d_done [N] uint8.  auto_reset != 0 re-spawns finished envs in the same launch. */
 int mfg_step(MfgHandle* h, const int32_t* d_actions, const MfgTape* tape, float* d_reward, uint8_t* d_done,
              int auto_reset, void* stream);
-/* OBSBuilder.build_for_all: packed observation tensor [N][sum(C_a)][D][D] float32. */
+/* OBSBuilder.build_for_all (observation_builder.py:98-235): packed observation tensor [N][sum(C_a)][D][D] float32. */
 int mfg_observe(MfgHandle* h, float* d_obs, void* stream);
+/* Factory.step as one call (factory.py:189-220: tick, done, reward fold, observations).  With auto_reset != 0 the finished
+ * envs are re-spawned and observed on an internal high-priority stream while the tiled observation kernel covers all
+ * other envs on `stream`; the call joins before returning control to `stream`, so the caller sees plain stream order. */
 int mfg_step_observe(MfgHandle* h, const int32_t* d_actions, const MfgTape* tape, float* d_reward, uint8_t* d_done,
                      float* d_obs, int auto_reset, void* stream);
 /* uniform random actions in [0, n_actions[a]) from Philox (seed, global env id, step_index). */
@@ -166,7 +169,10 @@ int mfg_step_host(MfgHandle* h, const int32_t* h_actions, float* h_reward, uint8
                   int auto_reset, void* stream);
 /* copies the MFG_N_STATS int64 statistics vector (device) into d_out; zero_after != 0 clears it afterwards */
 int mfg_stats(MfgHandle* h, int64_t* d_out, int zero_after, void* stream);
-/* selects the observation kernel: 0 = tiled shared-memory kernel (identity mode only), 1 = direct per-agent kernel */
+/* options: "obs_kernel" (0 auto, 1 direct per-agent kernel, 2 tiled shared-memory kernel), "obs_store" (1 TMA bulk store),
+ * "obs_cap" (sprite slots per env), "defer_reset" (1 packed reset kernel), "overlap_reset" (1 side stream in
+ * mfg_step_observe), "timing" (1: CUDA event pairs around the kernels, read with mfg_get_info "step_ns" / "obs_ns" /
+ * "reset_ns").  info: "launches", "tiled_ok", "obs_smem", "obs_threads", "obs_ctas_per_sm", "obs_cap", "obs_cap_max". */
 int mfg_set_option(MfgHandle* h, const char* name, int64_t value);
 int64_t mfg_get_info(const MfgHandle* h, const char* name);
 

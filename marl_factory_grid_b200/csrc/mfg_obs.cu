@@ -220,10 +220,14 @@ __global__ void __launch_bounds__(256) k_obs_tiled(const MfgSpec* __restrict__ s
     // ---------------- phase 1: lane = (env el, agent a) ---------------------------------------------------------
     const int el = lane >> apad_log2, a = lane & ((1 << apad_log2) - 1);
     unsigned long long wv = 0ull;
+    uint32_t skip_mask = 0u;          // bit (el << apad_log2): env el of this pass is skipped
     {
       const int64_t e = env0 + el;
       const int eb = sub * EPW + el;
-      if (a < A && e < st.N && !(skip && skip[e])) {      // skipped envs (being re-spawned concurrently) are rewritten later
+      // skipped envs (being re-spawned concurrently) are rewritten later; one flag load per lane, shared through a ballot
+      const bool lane_skip = skip != nullptr && e < st.N && skip[e] != 0;
+      skip_mask = __ballot_sync(0xffffffffu, lane_skip);
+      if (a < A && e < st.N && !lane_skip) {
         const BlkPos pos{blk16, eb};
         const unsigned long long dopen = n_doors ? blk_dopen[eb] : 0ull;
         const uint32_t reached = n_dest ? blk_reached[eb] : 0u;
@@ -569,12 +573,12 @@ __global__ void __launch_bounds__(256) k_obs_tiled(const MfgSpec* __restrict__ s
       float* dst = obs + (size_t)eg * total_channels * DD;
       // envs that are being re-spawned concurrently (skip flags) are written by k_obs_redo, not here
       bool any_skip = false;
-      if (skip) for (int ge = 0; ge < ne; ++ge) any_skip |= skip[eg + ge] != 0;
+      for (int ge = 0; ge < ne; ++ge) any_skip |= ((skip_mask >> ((g * GE + ge) << apad_log2)) & 1u) != 0;
       if (any_skip) {
         __syncwarp();
         const int per = total_channels * DD;
         for (int ge = 0; ge < ne; ++ge) {
-          if (skip[eg + ge]) continue;
+          if ((skip_mask >> ((g * GE + ge) << apad_log2)) & 1u) continue;
           for (int i = lane; i < per; i += 32) dst[ge * per + i] = tile[ge * per + i];
         }
         __syncwarp();
