@@ -43,7 +43,7 @@ extern "C" {
 #define MFG_MAX_FIXED 32
 #define MFG_N_TERMS (9 + MFG_MAX_AGENTS)
 #define MFG_RULE_NPARAM 6
-#define MFG_MAX_RAYS 64
+#define MFG_MAX_RAYS 128
 #define MFG_MAX_RAY_LEN 16
 #define MFG_NO_POS 0xFFFFu
 #define MFG_N_STATS 32

@@ -14,7 +14,7 @@ MAX_AGENTS, MAX_ACTIONS, MAX_DOORS, MAX_DIRT = 16, 32, 64, 64
 MAX_RULES, MAX_CHANNELS, MAX_SMALL, MAX_GROUPS, MAX_FIXED = 32, 32, 32, 16, 32
 N_TERMS = 9 + MAX_AGENTS
 RULE_NPARAM = 6
-MAX_RAYS, MAX_RAY_LEN = 64, 16
+MAX_RAYS, MAX_RAY_LEN = 128, 16
 NO_POS = 0xFFFF
 N_STATS = 32
 ENV_BLOCK = 128          # envs per state block (blocked struct-of-arrays layout, include/mfg_b200.h)
@@ -159,7 +159,9 @@ class PackedSpec:
                 s.group_n_fixed[g] = len(grp.coords)
                 for j, p in enumerate(grp.coords):
                     s.group_fixed_pos[g][j] = pos16(p)
-        rays = full_ray_table(es.obs_d)
+        # ray radius = min(observation shape): the window diameter for POMDP, min(H, W) for full observability
+        # (observation_builder.py:244)
+        rays = full_ray_table(min(es.obs_shape))
         if len(rays) > MAX_RAYS or max(len(r) for r in rays) > MAX_RAY_LEN:
             raise ValueError('ray table exceeds the engine limits')
         s.n_rays = len(rays)

@@ -90,8 +90,7 @@ int mfg_create(const MfgSpec* spec, int64_t n_envs, int64_t env_id_offset, MfgHa
   }
   h->total_channels = 0;
   for (int a = 0; a < h->sp.n_agents; ++a) h->total_channels += h->sp.n_channels[a];
-  const int D = 2 * h->sp.pomdp_r + 1;
-  h->DD = D * D;
+  h->DD = obs_plane_cells(h->sp);
 
   plan_obs(h);
   *out = h;

@@ -1008,15 +1008,24 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
 // ================================================================================================
 // observation, one (env, agent) per thread, all parity modes (the tiled fast path lives in mfg_kernels.cu)
 // ================================================================================================
-constexpr int RANK_INF = 0xFF;            // first-visit ranks: at most (2*7+1)^2 = 225 distinct cells are ever visited
-constexpr int RANK_CELLS = (2 * 7 + 1) * (2 * 7 + 1);
+// first-visit ranks of the cells of the ray-radius box.  POMDP: radius = window diameter <= 7 (225 cells); full
+// observability (pomdp_r == 0): radius = min(H, W) <= MFG_MAX_RAY_LEN - 1 = 15 (961 cells).
+typedef uint16_t rank_t;
+constexpr int RANK_INF = 0xFFFF;
+constexpr int RANK_RMAX = MFG_MAX_RAY_LEN - 1;
+constexpr int RANK_CELLS = (2 * RANK_RMAX + 1) * (2 * RANK_RMAX + 1);
+
+// observation geometry (observation_builder.py:51, 156-160, 244): egocentric (2r+1)^2 window, or the whole level
+MFG_HD bool obs_full(const MfgSpec& sp) { return sp.pomdp_r == 0; }
+MFG_HD int obs_plane_cells(const MfgSpec& sp) { return obs_full(sp) ? sp.H * sp.W : (2 * sp.pomdp_r + 1) * (2 * sp.pomdp_r + 1); }
+MFG_HD int obs_ray_radius(const MfgSpec& sp) { return obs_full(sp) ? (sp.H < sp.W ? sp.H : sp.W) : 2 * sp.pomdp_r + 1; }
 
 template <int AMAX>
 struct ObsCtx {
   Env<AMAX>& v;
   int a, ax, ay, r, D, R, BW;
-  uint8_t* rank;                          // [(2R+1)^2] first-visit order of every cell of the radius box, RANK_INF = unseen
-  MFG_HD ObsCtx(Env<AMAX>& v_, uint8_t* rank_) : v(v_), rank(rank_) {}
+  rank_t* rank;                           // [(2R+1)^2] first-visit order of every cell of the radius box, RANK_INF = unseen
+  MFG_HD ObsCtx(Env<AMAX>& v_, rank_t* rank_) : v(v_), rank(rank_) {}
   MFG_HD bool blocks_light(int x, int y) const {
     if (!v.in_grid(x, y)) return false;
     return v.tbl(v.tb.wall, x * v.sp.W + y) || v.closed_listed_door(x, y);
@@ -1060,12 +1069,13 @@ enum { OK_INT = 0, OK_STORE = 1, OK_DOOR = 2, OK_DIRT = 3 };
 //                             sink.scalar(channel, flat_index, v)   Battery / GlobalPosition values
 // Call order: walls, agents, integer-valued groups, doors, dirt, scalars (fractional encodings last).
 template <int AMAX, typename Sink>
-MFG_HDN void obs_agent_exact(const MfgSpec& sp, const Tables& tb, const State& st, int64_t e, int a, uint8_t* rank,
+MFG_HDN void obs_agent_exact(const MfgSpec& sp, const Tables& tb, const State& st, int64_t e, int a, rank_t* rank,
                              Sink& sink) {
   Env<AMAX> v(sp, tb, st, e);
   v.load();
   ObsCtx<AMAX> o(v, rank);
-  const int r = sp.pomdp_r, D = 2 * r + 1, R = D, BW = 2 * R + 1;
+  const bool full = obs_full(sp);
+  const int r = sp.pomdp_r, D = 2 * r + 1, R = obs_ray_radius(sp), BW = 2 * R + 1;
   o.a = a; o.ax = px(v.apos[a]); o.ay = py(v.apos[a]); o.r = r; o.D = D; o.R = R; o.BW = BW;
   for (int i = 0; i < BW * BW; ++i) rank[i] = RANK_INF;
 
@@ -1080,8 +1090,8 @@ MFG_HDN void obs_agent_exact(const MfgSpec& sp, const Tables& tb, const State& s
       bool hits = o.blocks_light(x, y);
       bool diag = (cx != 0 && cy != 0) && o.blocks_light(x, y - cy) && o.blocks_light(x - cx, y);
       if (!diag) {
-        uint8_t& rk = rank[(dx + R) * BW + (dy + R)];
-        if (rk == RANK_INF) rk = (uint8_t)visit++;
+        rank_t& rk = rank[(dx + R) * BW + (dy + R)];
+        if (rk == RANK_INF) rk = (rank_t)visit++;
       }
       if (hits || diag) break;
       pxr = x; pyr = y;
@@ -1090,6 +1100,7 @@ MFG_HDN void obs_agent_exact(const MfgSpec& sp, const Tables& tb, const State& s
 
   const uint32_t* chm = sp.term_chmask[a];
   auto in_window = [&](uint16_t p, int& cell) {
+    if (full) { cell = px(p) * sp.W + py(p); return true; }          // the plane is the whole level, absolute coordinates
     int dx = px(p) - o.ax + r, dy = py(p) - o.ay + r;
     if (dx < 0 || dy < 0 || dx >= D || dy >= D) return false;
     cell = dx * D + dy;
@@ -1098,7 +1109,8 @@ MFG_HDN void obs_agent_exact(const MfgSpec& sp, const Tables& tb, const State& s
 
   // ---- walls (uid = row-major wall index)
   if (chm[MFG_G_WALLS]) {
-    for (int dx = -r; dx <= r; ++dx) for (int dy = -r; dy <= r; ++dy) {
+    const int wr = full ? R : r;                 // walls can only be seen inside the ray radius
+    for (int dx = -wr; dx <= wr; ++dx) for (int dy = -wr; dy <= wr; ++dy) {
       int x = o.ax + dx, y = o.ay + dy;
       if (!v.in_grid(x, y) || !v.tbl(tb.wall, x * sp.W + y)) continue;
       int rk = rank[(dx + R) * BW + (dy + R)];
@@ -1115,7 +1127,7 @@ MFG_HDN void obs_agent_exact(const MfgSpec& sp, const Tables& tb, const State& s
           sh = uid < v.cls_count(c) && ((v.at(v.cls_listed(c), 0) >> uid) & 1) && o.rank_of(v.at(v.cls_pos(c), uid)) < rk;
         if (sh) continue;
       }
-      sink.wall((dx + r) * D + (dy + r));
+      sink.wall(full ? x * sp.W + y : (dx + r) * D + (dy + r));
     }
   }
   // ---- agents (string identifiers: never shadowed)
@@ -1200,10 +1212,10 @@ struct FloatSink {
 
 template <int AMAX>
 MFG_HDN void obs_agent_direct(const MfgSpec& sp, const Tables& tb, const State& st, int64_t e, int a, float* out) {
-  const int D = 2 * sp.pomdp_r + 1, DD = D * D;
+  const int DD = obs_plane_cells(sp);
   const int C = sp.n_channels[a];
   for (int i = 0; i < C * DD; ++i) out[i] = 0.0f;
-  uint8_t rank[RANK_CELLS];
+  rank_t rank[RANK_CELLS];
   FloatSink sink{out, DD, sp.term_chmask[a][MFG_G_WALLS]};
   obs_agent_exact<AMAX>(sp, tb, st, e, a, rank, sink);
 }

@@ -154,7 +154,9 @@ inline std::string build_tables(const MfgSpec& sp, HostTables& t) {
 
 inline std::string validate_spec(const MfgSpec& sp) {
   if (sp.n_agents < 1 || sp.n_agents > MFG_MAX_AGENTS) return "n_agents out of range";
-  if (sp.pomdp_r < 1 || sp.pomdp_r > 3) return "pomdp_r must be 1..3 (full observability is not supported yet)";
+  if (sp.pomdp_r < 0 || sp.pomdp_r > 3) return "pomdp_r must be 0 (full observability) or 1..3";
+  if (sp.pomdp_r == 0 && (sp.H < sp.W ? sp.H : sp.W) > MFG_MAX_RAY_LEN - 1)
+    return "full observability needs min(H, W) <= 15 (ray length limit)";
   if (sp.n_doors < 0 || sp.n_doors > MFG_MAX_DOORS) return "n_doors out of range";
   if (sp.has_dirt && (sp.dirt_slots < 1 || sp.dirt_slots > MFG_MAX_DIRT)) return "dirt_slots out of range";
   if (sp.n_rules < 0 || sp.n_rules > MFG_MAX_RULES) return "n_rules out of range";

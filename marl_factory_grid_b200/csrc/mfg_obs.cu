@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(128) k_obs_direct(const MfgSpec* __restrict__ 
   if (t >= st.N * A) return;
   int a = (int)(t / st.N);
   int64_t e = t - (int64_t)a * st.N;
-  const int DD = (2 * sp->pomdp_r + 1) * (2 * sp->pomdp_r + 1);
+  const int DD = obs_plane_cells(*sp);
   obs_agent_direct<AMAX>(*sp, tb, st, e, a, obs + ((size_t)e * total_channels + sp->ch_offset[a]) * DD);
 }
 
@@ -119,7 +119,7 @@ template <int AMAX>
 __global__ void __launch_bounds__(128) k_obs_redo(const MfgSpec* __restrict__ sp, Tables tb, State st, float* obs, int total_channels,
                                                   const uint32_t* __restrict__ list, const uint32_t* __restrict__ count) {
   const int A = sp->n_agents;
-  const int DD = (2 * sp->pomdp_r + 1) * (2 * sp->pomdp_r + 1);
+  const int DD = obs_plane_cells(*sp);
   const uint32_t n = *count * (uint32_t)A;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int64_t e = list[i / A];

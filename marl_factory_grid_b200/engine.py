@@ -113,7 +113,7 @@ class Engine:
                                                  (f.block_bytes // f.elem_size, ENV_BLOCK, 1), f.offset // f.elem_size)
         A = es.n_agents
         self.n_rew = A if es.individual_rewards else 1
-        self.obs = torch.zeros((self.N, es.total_channels, es.obs_d, es.obs_d), dtype=torch.float32, device=self.device)
+        self.obs = torch.zeros((self.N, es.total_channels) + tuple(es.obs_shape), dtype=torch.float32, device=self.device)
         self.reward = torch.zeros((self.N, self.n_rew), dtype=torch.float32, device=self.device)
         self.done = torch.zeros(self.N, dtype=torch.uint8, device=self.device)
         self._stats = torch.zeros(N_STATS, dtype=torch.int64, device=self.device)

@@ -77,8 +77,8 @@ class Factory:
 
     @property
     def observation_space(self):
-        d = self.spec.obs_d
-        boxes = [Box(0, 1, (c, d, d), np.float32) for c in self.spec.channels_per_agent]
+        shape = tuple(self.spec.obs_shape)
+        boxes = [Box(0, 1, (c,) + shape, np.float32) for c in self.spec.channels_per_agent]
         return boxes[0] if len(boxes) == 1 else boxes
 
     @property

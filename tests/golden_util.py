@@ -10,8 +10,9 @@ from marl_factory_grid_b200 import FactoryConfigParser
 ROOT = Path(__file__).resolve().parent.parent
 GOLDEN = ROOT / 'tests' / 'golden'
 CONFIGS = ROOT / 'marl_factory_grid_b200' / 'configs'
-ALL_CFGS = ['cfg1', 'cfg2', 'cfg3', 'cfg4', 'stress', 'stress2']      # POMDP configs: oracle AND engine
-ORACLE_ONLY_CFGS = ['obs_test']                                        # pomdp_r = 0 (full observability): oracle only
+ALL_CFGS = ['cfg1', 'cfg2', 'cfg3', 'cfg4', 'stress', 'stress2']      # POMDP configs: oracle, direct AND tiled observation kernels
+FULL_OBS_CFGS = ['obs_test']                                          # pomdp_r = 0 (full observability): oracle and the direct kernel
+ORACLE_ONLY_CFGS = []
 
 SNAP_KEYS = ['agent_pos', 'door_open', 'door_timer', 'door_listed', 'dirt_n', 'dirt_pos', 'dirt_amt', 'dirt_uid',
              'dirt_listed', 'item_pos', 'item_listed', 'pod_pos', 'pod_listed', 'dest_pos', 'dest_listed', 'drop_pos',
@@ -41,7 +42,7 @@ def episodes(cfg):
 
 
 def episode_ids(include_oracle_only=False):
-    cfgs = ALL_CFGS + (ORACLE_ONLY_CFGS if include_oracle_only else [])
+    cfgs = ALL_CFGS + FULL_OBS_CFGS + (ORACLE_ONLY_CFGS if include_oracle_only else [])
     return [(cfg, k) for cfg in cfgs for k in range(len(_load(cfg)))]
 
 

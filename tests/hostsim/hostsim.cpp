@@ -81,7 +81,7 @@ void hs_step(HsHandle* h, const int32_t* actions, const uint8_t* maint_act, cons
   });
 }
 void hs_observe(HsHandle* h, float* obs) {
-  const int DD = (2 * h->sp.pomdp_r + 1) * (2 * h->sp.pomdp_r + 1);
+  const int DD = obs_plane_cells(h->sp);
   int total = 0;
   for (int a = 0; a < h->sp.n_agents; ++a) total += h->sp.n_channels[a];
   dispatch(h->sp.n_agents, [&](auto amax) {

@@ -77,7 +77,7 @@ class HostSim:
         self.n_rew = A if es.individual_rewards else 1
         self.reward = np.zeros((n_envs, self.n_rew), np.float32)
         self.done = np.zeros(n_envs, np.uint8)
-        self.obs = np.zeros((n_envs, es.total_channels, es.obs_d, es.obs_d), np.float32)
+        self.obs = np.zeros((n_envs, es.total_channels) + tuple(es.obs_shape), np.float32)
 
     def __del__(self):
         if getattr(self, 'h', None):

@@ -8,7 +8,7 @@ compared bit-exactly; rewards (emitted as f32) within rtol 1e-6 of the reference
 import numpy as np
 import pytest
 
-from golden_util import ALL_CFGS, episodes, snap_at, spec_for
+from golden_util import ALL_CFGS, FULL_OBS_CFGS, episodes, snap_at, spec_for
 from hostsim_util import HostSim, tape_respawn
 
 torch = pytest.importorskip('torch')
@@ -83,6 +83,14 @@ def test_replay_untouched_reference(cfg):
 def test_replay_identity_reference(cfg):
     """identity mode == identity-patched reference; BOTH observation kernels (direct and tiled)."""
     _replay_batch(cfg, 'I', obs_kernels=[1, 2])
+
+
+@pytest.mark.parametrize('mode', ['U', 'I'])
+@pytest.mark.parametrize('cfg', FULL_OBS_CFGS)
+def test_replay_full_observability(cfg, mode):
+    """pomdp_r = 0 (the reference's own `_obs_test.yaml` fixture): whole-level observation planes, ray radius min(H, W);
+    served by the direct per-agent kernel."""
+    _replay_batch(cfg, mode, obs_kernels=[0])
 
 
 @pytest.mark.parametrize('cfg', ['cfg1', 'cfg2', 'cfg3', 'cfg4', 'stress2'])
