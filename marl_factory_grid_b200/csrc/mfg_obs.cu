@@ -148,7 +148,7 @@ __device__ __forceinline__ void mbar_wait0(unsigned long long* bar) {
 // rounded up to a power of two): lane = (env, agent) in phase 1, the same warp expands the tiles of those envs in phase 2,
 // so after the prefix has landed no CTA-wide barrier is needed and warps in different phases overlap on the SM.
 template <int R, bool FAITHFUL>
-__global__ void __launch_bounds__(256) k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st, ObsSlots sl, WallPlanes wp,
+__global__ void __launch_bounds__(256, 2) k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st, ObsSlots sl, WallPlanes wp,
                                                     float* __restrict__ obs, int total_channels, int cap, int apad_log2,
                                                     int GE, int bulk, uint32_t* __restrict__ redo,
                                                     const uint8_t* __restrict__ skip) {
@@ -527,12 +527,18 @@ __global__ void __launch_bounds__(256) k_obs_tiled(const MfgSpec* __restrict__ s
         if (ge == 0) clear_tile();
         // wall planes: 1.0 where a visible wall is.  Nothing else can be on a wall cell, so the (predicated) store has
         // a unique writer and needs no ordering against the sprite adds below.
-        for (int w = 0; w < wp.n; ++w) {
-          const int src = (elx << apad_log2) + wp.agent[w];
+        // Lane = (plane slot, window row): four planes per round, each lane writes the (at most D) wall cells of one row.
+        for (int w0 = 0; w0 < wp.n; w0 += 4) {
+          const int w = w0 + (lane >> 3), row = lane & 7;
+          const bool mine = w < wp.n && row < D;
+          const int src = (elx << apad_log2) + (mine ? (int)wp.agent[w] : 0);
           const uint32_t m_lo = __shfl_sync(0xffffffffu, wv_lo, src), m_hi = __shfl_sync(0xffffffffu, wv_hi, src);
-          float* plane = te + (int)wp.plane[w] * DD;
-          if ((m_lo >> lane) & 1u) plane[lane] = 1.0f;
-          if (lane + 32 < DD && ((m_hi >> lane) & 1u)) plane[lane + 32] = 1.0f;
+          if (mine) {
+            const uint32_t bits = (uint32_t)((((unsigned long long)m_hi << 32) | m_lo) >> (row * D)) & ((1u << D) - 1u);
+            float* cells = te + (int)wp.plane[w] * DD + row * D;
+#pragma unroll
+            for (int c = 0; c < D; ++c) if ((bits >> c) & 1u) cells[c] = 1.0f;
+          }
         }
         // pass A: integer-valued sprites (stacks add up exactly) and direct stores
         if (k0 == SK_INT) atomicAdd(&te[s0.w & 0xFFFF], s0.val);
