@@ -306,6 +306,11 @@ int64_t mfg_get_info(const MfgHandle* h, const char* name) {
   if (strcmp(name, "obs_ns") == 0) return drain_ns(const_cast<MfgHandle*>(h)->t_obs);
   if (strcmp(name, "reset_ns") == 0) return drain_ns(const_cast<MfgHandle*>(h)->t_reset);
   if (strcmp(name, "tiled_ok") == 0) return h->plan.ok ? 1 : 0;
+  if (strcmp(name, "obs_redo_count") == 0) {          // envs the last tiled launch handed to the exact path (synchronises)
+    uint32_t n = 0;
+    if (!h->d_redo || cudaDeviceSynchronize() != cudaSuccess || cudaMemcpy(&n, h->d_redo, sizeof(n), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    return n;
+  }
   if (strcmp(name, "obs_ctas_per_sm") == 0) return obs_ctas_per_sm(h);
   if (strcmp(name, "obs_smem") == 0) return (int64_t)h->plan.smem;
   if (strcmp(name, "obs_threads") == 0) return h->plan.nw * 32;
