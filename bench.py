@@ -272,7 +272,7 @@ def run_engine(args):
     other = None
     if not args.no_other_mode:
         other_parity = 'identity' if args.parity == 'faithful' else 'faithful'
-        other = measure(args, other_parity, min(args.steps, 50), min(args.warmup, 5), dev, rank, world, local, with_e2e=False)
+        other = measure(args, other_parity, min(args.steps, 200), args.warmup, dev, rank, world, local, with_e2e=False)
 
     if rank != 0:
         if world > 1:
@@ -326,7 +326,7 @@ def main():
     ap.add_argument('--obs-kernel', type=int, default=0, help='0 auto, 1 direct, 2 tiled')
     ap.add_argument('--obs-store', type=int, default=1, help='1 TMA bulk store of the tile, 0 LDS/STG loop')
     ap.add_argument('--e2e-steps', type=int, default=5)
-    ap.add_argument('--cpu-steps', type=int, default=3000, help='env-steps per CPU worker for the baseline sample')
+    ap.add_argument('--cpu-steps', type=int, default=12000, help='env-steps per CPU worker for the baseline sample')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-other-mode', action='store_true', help='skip the short second pass in the other parity mode')
