@@ -194,29 +194,36 @@ def measure(args, parity, steps, warmup, dev, rank, world, local, with_e2e):
     e2e = None
     if with_e2e:
         k2 = max(1, min(steps, args.e2e_steps))
-        h_act = torch.zeros((n_local, A), dtype=torch.int32).pin_memory()
-        h_rew = torch.zeros((n_local, eng.n_rew), dtype=torch.float32).pin_memory()
-        h_done = torch.zeros(n_local, dtype=torch.uint8).pin_memory()
-        h_obs = torch.zeros((n_local, es.total_channels, es.obs_d, es.obs_d), dtype=torch.float32).pin_memory()
-        gen = torch.Generator().manual_seed(rank)
-        pool = [torch.stack([torch.randint(0, n, (n_local,), generator=gen, dtype=torch.int32) for n in es.n_actions], 1)
-                for _ in range(2)]
-        eng.step_host(h_act, h_rew, h_done, h_obs, auto_reset=True)       # warm-up (allocates the staging buffers)
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(k2):
-            h_act.copy_(pool[i % 2])                                        # the caller's host-side actions
-            eng.step_host(h_act, h_rew, h_done, h_obs, auto_reset=True)
-        barrier()
-        t_e2e = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-        e2e = {'value': world * n_local * A * k2 / float(t_e2e[0]), 'unit': UNIT, 'steps': k2,
-               'h2d_bytes_per_step': int(h_act.numel() * 4) * world,
-               'd2h_bytes_per_step': int(h_rew.numel() * 4 + h_done.numel() + h_obs.numel() * 4) * world,
-               'note': 'mfg_step_host: pinned host actions in, reward + done + full observation tensor out, synchronous '
-                       '(PCIe-bound: the dense f32 observation tensor is 7 KB per env)'}
-        del h_obs
+        try:                             # pinned staging buffers: 7.4 GB of observations per rank
+            h_act = torch.zeros((n_local, A), dtype=torch.int32).pin_memory()
+            h_rew = torch.zeros((n_local, eng.n_rew), dtype=torch.float32).pin_memory()
+            h_done = torch.zeros(n_local, dtype=torch.uint8).pin_memory()
+            h_obs = torch.zeros((n_local, es.total_channels) + tuple(es.obs_shape), dtype=torch.float32).pin_memory()
+            ok = 1.0
+        except Exception:                # e.g. not enough lockable host memory for 8 ranks on one box
+            ok = 0.0
+        if allreduce_max(-ok, dev) < 0:  # every rank got its buffers
+            gen = torch.Generator().manual_seed(rank)
+            pool = [torch.stack([torch.randint(0, n, (n_local,), generator=gen, dtype=torch.int32) for n in es.n_actions], 1)
+                    for _ in range(2)]
+            eng.step_host(h_act, h_rew, h_done, h_obs, auto_reset=True)       # warm-up (allocates the staging buffers)
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(k2):
+                h_act.copy_(pool[i % 2])                                        # the caller's host-side actions
+                eng.step_host(h_act, h_rew, h_done, h_obs, auto_reset=True)
+            barrier()
+            t_e2e = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+            e2e = {'value': world * n_local * A * k2 / float(t_e2e[0]), 'unit': UNIT, 'steps': k2,
+                   'h2d_bytes_per_step': int(h_act.numel() * 4) * world,
+                   'd2h_bytes_per_step': int(h_rew.numel() * 4 + h_done.numel() + h_obs.numel() * 4) * world,
+                   'note': 'mfg_step_host: pinned host actions in, reward + done + full observation tensor out, synchronous '
+                           '(PCIe-bound: the dense f32 observation tensor is 7 KB per env)'}
+            del h_obs
+        else:
+            e2e = {'value': None, 'unit': UNIT, 'note': 'pinned host buffers could not be allocated on every rank'}
 
     total_envs = world * n_local
     env_steps_per_s = total_envs * steps / (elapsed_ms * 1e-3)
