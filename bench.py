@@ -30,6 +30,12 @@ sys.path.insert(0, str(ROOT))
 METRIC = 'agent-steps/sec incl. obs'
 UNIT = 'agent-steps/s'
 CONFIGS = ROOT / 'marl_factory_grid_b200' / 'configs'
+WORKLOADS = {          # BASELINE.json configs[0..3] as restated in SURVEY.md App. D; cfg4 at 1M envs per GPU = configs[4]
+    'cfg1': 'single-agent dirt clean-up (level simple, POMDP r=3)',
+    'cfg2': '2-agent item pick-up / drop-off with doors (level rooms, POMDP r=3)',
+    'cfg3': '4-agent batteries + charge pods + destinations (level large, POMDP r=3)',
+    'cfg4': 'all-modules incl. machines + maintainer (level large, 4 agents, POMDP r=3)',
+}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -291,7 +297,7 @@ def run_engine(args):
         'metric': METRIC, 'value': m['value'], 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': m['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'u16/f64 state, f32 obs', 'data': 'synthetic',
-        'config': {'workload': f'{args.config} all-modules (level large, 4 agents, POMDP r=3), {n_local} envs per GPU',
+        'config': {'workload': f'{args.config} {WORKLOADS.get(args.config, "")}, {n_local} envs per GPU',
                    'envs_total': world * n_local, 'agents': A, 'parity': m['parity'],
                    'parity_note': 'faithful = the untouched reference incl. its uid-equality artefact (bit-exact vs oracle-U traces); '
                                   'identity = the identity-patched reference (oracle-I), reported under other_parity_mode',

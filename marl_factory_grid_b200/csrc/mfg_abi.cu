@@ -107,6 +107,7 @@ void mfg_destroy(MfgHandle* h) {
   if (h->d_reset_list) cudaFree(h->d_reset_list);
   if (h->d_reset_count) cudaFree(h->d_reset_count);
   if (h->d_redo) cudaFree(h->d_redo);
+  if (h->d_row_tab) cudaFree(h->d_row_tab);
   drain_ns(h->t_step); drain_ns(h->t_obs); drain_ns(h->t_reset);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -127,6 +128,22 @@ int mfg_bind_state(MfgHandle* h, void* d_state) {
   if (!h || !d_state) return fail(MFG_E_INVALID, "mfg_bind_state: bad arguments");
   if (reinterpret_cast<uintptr_t>(d_state) % 256) return fail(MFG_E_INVALID, "mfg_bind_state: buffer must be 256-byte aligned");
   bind_state(h->sp, h->N, d_state, h->st);
+  if (!h->d_row_tab) {               // rows of the integer region (ColTab): offsets do not depend on the buffer address
+    std::vector<uint32_t> rows;
+    const MfgSpec& sp = h->sp;
+#define F(type, name, rows_expr)                                                                                    \
+    if (!std::is_same<type, double>::value) {                                                                        \
+      const uint32_t off = (uint32_t)(reinterpret_cast<const char*>(h->st.name) - h->st.base_i);                     \
+      const uint32_t lg = sizeof(type) == 1 ? 0u : sizeof(type) == 2 ? 1u : sizeof(type) == 4 ? 2u : 3u;             \
+      for (int r = 0; r < (int)(rows_expr); ++r) rows.push_back((off + (uint32_t)(r * ENV_BLOCK * sizeof(type))) | (lg << 28)); \
+    }
+    MFG_STATE_FIELDS(F)
+#undef F
+    h->n_row_tab = (int)rows.size();
+    h->row_tab_host = rows;
+    CUDA_TRY(cudaMalloc(&h->d_row_tab, rows.size() * sizeof(uint32_t)));
+    CUDA_TRY(cudaMemcpy(h->d_row_tab, rows.data(), rows.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  }
   h->bound = true;
   return MFG_OK;
 }
@@ -223,14 +240,14 @@ int mfg_step_observe(MfgHandle* h, const int32_t* d_actions, const MfgTape* tape
     Timed t(h, h->t_reset, h->side);
     CUDA_TRY(launch_reset_list(h, io, h->side));
   }
-  CUDA_TRY(launch_obs_list(h, d_obs, h->side, h->d_reset_list, h->d_reset_count));
+  CUDA_TRY(launch_obs_tiled_list(h, d_obs, h->side, h->d_reset_list, h->d_reset_count));   // tiled kernel in list mode (+ its redo pass)
   CUDA_TRY(cudaEventRecord(h->ev_join, h->side));
   {
     Timed t(h, h->t_obs, s);
     CUDA_TRY(launch_obs_tiled(h, d_obs, s, d_done));
   }
   CUDA_TRY(cudaStreamWaitEvent(s, h->ev_join, 0));
-  h->launches += 4;                   // reset list, tiled observation + its redo pass, observation of the re-spawned envs
+  h->launches += 5;                   // reset list, tiled observation + its redo pass, the same pair over the re-spawned envs
   return MFG_OK;
 }
 

@@ -1070,8 +1070,8 @@ enum { OK_INT = 0, OK_STORE = 1, OK_DOOR = 2, OK_DIRT = 3 };
 // Call order: walls, agents, integer-valued groups, doors, dirt, scalars (fractional encodings last).
 template <int AMAX, typename Sink>
 MFG_HDN void obs_agent_exact(const MfgSpec& sp, const Tables& tb, const State& st, int64_t e, int a, rank_t* rank,
-                             Sink& sink) {
-  Env<AMAX> v(sp, tb, st, e);
+                             Sink& sink, int64_t eg = -1) {
+  Env<AMAX> v(sp, tb, st, e, eg);      // eg: global env id when `st` is a staged image (f64 fields are never staged)
   v.load();
   ObsCtx<AMAX> o(v, rank);
   const bool full = obs_full(sp);
@@ -1211,13 +1211,14 @@ struct FloatSink {
 };
 
 template <int AMAX>
-MFG_HDN void obs_agent_direct(const MfgSpec& sp, const Tables& tb, const State& st, int64_t e, int a, float* out) {
+MFG_HDN void obs_agent_direct(const MfgSpec& sp, const Tables& tb, const State& st, int64_t e, int a, float* out,
+                              int64_t eg = -1) {
   const int DD = obs_plane_cells(sp);
   const int C = sp.n_channels[a];
   for (int i = 0; i < C * DD; ++i) out[i] = 0.0f;
   rank_t rank[RANK_CELLS];
   FloatSink sink{out, DD, sp.term_chmask[a][MFG_G_WALLS]};
-  obs_agent_exact<AMAX>(sp, tb, st, e, a, rank, sink);
+  obs_agent_exact<AMAX>(sp, tb, st, e, a, rank, sink, eg);
 }
 
 }  // namespace mfg

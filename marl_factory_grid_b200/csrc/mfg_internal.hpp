@@ -50,6 +50,69 @@ struct ObsPlan {
 
 }  // namespace mfg
 
+namespace mfg {
+// Rows of the integer region of a state block: byte offset of the row's [128] slab inside the block | log2(element size) << 28.
+// Lets a CTA copy the columns of arbitrary envs into a shared-memory block image (and back) with independent loads.
+struct ColTab {
+  const uint32_t* rows;
+  int n;
+};
+// list mode of the tiled observation kernel: ids of the envs to observe, the prefix rows to gather
+struct ObsList {
+  const uint32_t* ids;
+  const uint32_t* count;
+  const uint32_t* rows;
+  int n_rows;
+};
+
+#if defined(__CUDACC__)
+// column j of the image <- env list[base + j], for j < n_here; all threads of the CTA take part
+__device__ __forceinline__ void gather_columns(const State& st, unsigned char* stage, ColTab ct, const uint32_t* __restrict__ list,
+                                               uint32_t base, int n_here) {
+  const int total = ct.n * n_here;
+#pragma unroll 4
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int r = idx / n_here, j = idx - r * n_here;
+    const uint32_t rec = ct.rows[r], off = rec & 0x0FFFFFFFu, lg = rec >> 28;
+    const int64_t e = list[base + j];
+    const char* src = st.base_i + (size_t)(e >> 7) * st.blk_i + off + ((size_t)(e & (ENV_BLOCK - 1)) << lg);
+    unsigned char* dst = stage + off + ((size_t)j << lg);
+    if (lg == 0) *dst = __ldg(reinterpret_cast<const unsigned char*>(src));
+    else if (lg == 1) *reinterpret_cast<uint16_t*>(dst) = __ldg(reinterpret_cast<const uint16_t*>(src));
+    else if (lg == 2) *reinterpret_cast<uint32_t*>(dst) = __ldg(reinterpret_cast<const uint32_t*>(src));
+    else *reinterpret_cast<unsigned long long*>(dst) = __ldg(reinterpret_cast<const unsigned long long*>(src));
+  }
+}
+__device__ __forceinline__ void scatter_columns(const State& st, const unsigned char* stage, ColTab ct, const uint32_t* __restrict__ list,
+                                                uint32_t base, int n_here) {
+  const int total = ct.n * n_here;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int r = idx / n_here, j = idx - r * n_here;
+    const uint32_t rec = ct.rows[r], off = rec & 0x0FFFFFFFu, lg = rec >> 28;
+    const int64_t e = list[base + j];
+    char* dst = st.base_i + (size_t)(e >> 7) * st.blk_i + off + ((size_t)(e & (ENV_BLOCK - 1)) << lg);
+    const unsigned char* src = stage + off + ((size_t)j << lg);
+    if (lg == 0) *reinterpret_cast<unsigned char*>(dst) = *src;
+    else if (lg == 1) *reinterpret_cast<uint16_t*>(dst) = *reinterpret_cast<const uint16_t*>(src);
+    else if (lg == 2) *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(src);
+    else *reinterpret_cast<unsigned long long*>(dst) = *reinterpret_cast<const unsigned long long*>(src);
+  }
+}
+// view of a shared-memory block image: same field offsets as `st`, block 0 == the image
+__device__ __forceinline__ State staged_view(const State& st, unsigned char* stage) {
+  State ss = st;
+  ss.N = ENV_BLOCK;
+  ss.base_i = reinterpret_cast<char*>(stage);
+  const char* g0 = st.base_i;
+#define F(type, name, rows_expr) \
+  if constexpr (!std::is_same<type, double>::value) ss.name = reinterpret_cast<type*>(stage + (reinterpret_cast<const char*>(st.name) - g0));
+  MFG_STATE_FIELDS(F)
+#undef F
+  return ss;
+}
+#endif
+}  // namespace mfg
+
 struct MfgHandle {
   MfgSpec sp;                  // host copy (level pointers nulled)
   MfgSpec* d_sp = nullptr;
@@ -69,6 +132,9 @@ struct MfgHandle {
   int64_t launches = 0;
   uint32_t* d_reset_list = nullptr;   // [N] ids of envs that finished in the current step
   uint32_t* d_reset_count = nullptr;
+  uint32_t* d_row_tab = nullptr;      // ColTab rows (built at mfg_bind_state)
+  int n_row_tab = 0;
+  std::vector<uint32_t> row_tab_host;
   uint32_t* d_redo = nullptr;         // [1 + N] observation redo list: count, env ids (tiled kernel's rare exact path)
   int defer_reset = 1;
   // mfg_step_observe overlaps the packed re-spawn (side stream) with the observation kernel (caller's stream)
@@ -94,4 +160,5 @@ void build_vis_tables(const MfgSpec& sp, HostTables& t);
 cudaError_t launch_obs_direct(MfgHandle* h, float* d_obs, cudaStream_t s);
 cudaError_t launch_obs_tiled(MfgHandle* h, float* d_obs, cudaStream_t s, const uint8_t* skip = nullptr);
 cudaError_t launch_obs_list(MfgHandle* h, float* d_obs, cudaStream_t s, const uint32_t* d_list, const uint32_t* d_count);
+cudaError_t launch_obs_tiled_list(MfgHandle* h, float* d_obs, cudaStream_t s, const uint32_t* d_list, const uint32_t* d_count);
 }  // namespace mfg

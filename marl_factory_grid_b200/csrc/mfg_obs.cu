@@ -115,16 +115,26 @@ __device__ __forceinline__ void bulk_store_tile(float* dst, const float* src_sme
 
 // Envs whose sprite list overflowed (any mode) or that have more uid conflicts than the packed list holds (faithful mode)
 // are appended to a redo list; this kernel rewrites their observations with the exact per-agent path of mfg_core.cuh.
+constexpr int REDO_ENVS = 32;       // envs per CTA round of k_obs_redo (columns of the block image in use)
 template <int AMAX>
-__global__ void __launch_bounds__(128) k_obs_redo(const MfgSpec* __restrict__ sp, Tables tb, State st, float* obs, int total_channels,
-                                                  const uint32_t* __restrict__ list, const uint32_t* __restrict__ count) {
+__global__ void __launch_bounds__(128) k_obs_redo(const MfgSpec* __restrict__ sp, Tables tb, State st, ColTab ct, float* obs,
+                                                  int total_channels, const uint32_t* __restrict__ list,
+                                                  const uint32_t* __restrict__ count) {
+  extern __shared__ __align__(128) unsigned char stage[];
   const int A = sp->n_agents;
   const int DD = obs_plane_cells(*sp);
-  const uint32_t n = *count * (uint32_t)A;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int64_t e = list[i / A];
-    const int a = (int)(i % A);
-    obs_agent_direct<AMAX>(*sp, tb, st, e, a, obs + ((size_t)e * total_channels + sp->ch_offset[a]) * DD);
+  const uint32_t n = *count;
+  const State ss = staged_view(st, stage);
+  for (uint32_t base = blockIdx.x * REDO_ENVS; base < n; base += gridDim.x * REDO_ENVS) {
+    const int n_here = (int)(n - base < (uint32_t)REDO_ENVS ? n - base : (uint32_t)REDO_ENVS);
+    gather_columns(st, stage, ct, list, base, n_here);          // the envs' integer columns -> shared-memory image
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_here * A; i += blockDim.x) {
+      const int j = i / A, a = i - j * A;
+      const int64_t e = list[base + j];
+      obs_agent_direct<AMAX>(*sp, tb, ss, j, a, obs + ((size_t)e * total_channels + sp->ch_offset[a]) * DD, e);
+    }
+    __syncthreads();
   }
 }
 
@@ -151,7 +161,7 @@ template <int R, bool FAITHFUL>
 __global__ void __launch_bounds__(256, 2) k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st, ObsSlots sl, WallPlanes wp,
                                                     float* __restrict__ obs, int total_channels, int cap, int apad_log2,
                                                     int GE, int bulk, uint32_t* __restrict__ redo,
-                                                    const uint8_t* __restrict__ skip) {
+                                                    const uint8_t* __restrict__ skip, ObsList ol) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long bar;
   // per-agent channel program (lanes of one warp belong to different agents, so it is read with per-lane indices)
@@ -164,6 +174,10 @@ __global__ void __launch_bounds__(256, 2) k_obs_tiled(const MfgSpec* __restrict_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int EPW = 32 >> apad_log2;                                 // envs per warp pass
   const int64_t blk0 = (int64_t)blockIdx.x * ENV_BLOCK;
+  // list mode (ol.ids != null): the CTA's 128 "envs" are entries of a device-side id list (the envs re-spawned in this step);
+  // their columns are gathered into the same shared-memory image the block mode fills with one bulk copy
+  const bool lmode = ol.ids != nullptr;
+  const uint32_t n_listed = lmode ? *ol.count : 0u;
   const int tile_floats = GE * total_channels * DD;
 
   // shared memory carve-up (every region start stays 16-byte aligned): prefix | per warp: tile, sprite lists, counters
@@ -180,7 +194,19 @@ __global__ void __launch_bounds__(256, 2) k_obs_tiled(const MfgSpec* __restrict_
   float* s_gx = reinterpret_cast<float*>(s_chm + ((A * MFG_N_TERMS + 3) & ~3));                               // x / H, y / W (entity/util.py:56-66)
   float* s_gy = s_gx + ((sp->H + 3) & ~3);
   // ---- stage the positional prefix of this block: one TMA bulk copy (dirt/item/.../agent positions, door + dest masks)
-  if (threadIdx.x == 0) {
+  // block mode: one pass; list mode: grid-stride over chunks of 128 listed envs
+  for (uint32_t lbase = blockIdx.x * ENV_BLOCK;; lbase += gridDim.x * ENV_BLOCK) {
+  int n_live;
+  if (lmode) {
+    if (lbase >= n_listed) break;
+    n_live = (int)(n_listed - lbase < (uint32_t)ENV_BLOCK ? n_listed - lbase : (uint32_t)ENV_BLOCK);
+  } else {
+    n_live = (int)(st.N - blk0 < ENV_BLOCK ? st.N - blk0 : ENV_BLOCK);
+  }
+  auto env_of = [&](int eb) -> int64_t { return lmode ? (int64_t)ol.ids[lbase + eb] : blk0 + eb; };
+  if (lmode) {
+    gather_columns(st, s_blk, ColTab{ol.rows, ol.n_rows}, ol.ids, lbase, n_live);
+  } else if (threadIdx.x == 0) {
     mbar_init1(&bar);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(&bar)), "r"((uint32_t)sl.prefix_bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(s_blk)),
@@ -201,7 +227,7 @@ __global__ void __launch_bounds__(256, 2) k_obs_tiled(const MfgSpec* __restrict_
   for (int i = threadIdx.x; i < sp->W; i += blockDim.x) s_gy[i] = (float)((double)i / (double)sp->W);
   const int spW = sp->W, n_doors = sp->n_doors, n_dest = sp->n_dest, has_dirt = sp->has_dirt, n_walls = sp->n_walls;
   __syncthreads();
-  mbar_wait0(&bar);
+  if (!lmode) mbar_wait0(&bar);
   const uint16_t* blk16 = reinterpret_cast<const uint16_t*>(s_blk);
   const unsigned long long* blk_dopen = reinterpret_cast<const unsigned long long*>(s_blk + sl.off_dopen);
   const uint32_t* blk_reached = reinterpret_cast<const uint32_t*>(s_blk + sl.off_reached);
@@ -212,8 +238,7 @@ __global__ void __launch_bounds__(256, 2) k_obs_tiled(const MfgSpec* __restrict_
   const int hi[6] = {sl.pod0, sl.dest0, sl.drop0, sl.mach0, sl.maint0, sl.agent0};
 
   for (int sub = warp; sub * EPW < ENV_BLOCK; sub += NW) {
-    const int64_t env0 = blk0 + (int64_t)sub * EPW;
-    if (env0 >= st.N) break;
+    if (sub * EPW >= n_live) break;
     if (lane < EPW) s_cnt[lane] = 0;
     __syncwarp();
 
@@ -222,12 +247,13 @@ __global__ void __launch_bounds__(256, 2) k_obs_tiled(const MfgSpec* __restrict_
     unsigned long long wv = 0ull;
     uint32_t skip_mask = 0u;          // bit (el << apad_log2): env el of this pass is skipped
     {
-      const int64_t e = env0 + el;
       const int eb = sub * EPW + el;
+      const bool in_range = eb < n_live;
+      const int64_t e = in_range ? env_of(eb) : 0;
       // skipped envs (being re-spawned concurrently) are rewritten later; one flag load per lane, shared through a ballot
-      const bool lane_skip = skip != nullptr && e < st.N && skip[e] != 0;
+      const bool lane_skip = skip != nullptr && in_range && skip[e] != 0;
       skip_mask = __ballot_sync(0xffffffffu, lane_skip);
-      if (a < A && e < st.N && !lane_skip) {
+      if (a < A && in_range && !lane_skip) {
         const BlkPos pos{blk16, eb};
         const unsigned long long dopen = n_doors ? blk_dopen[eb] : 0ull;
         const uint32_t reached = n_dest ? blk_reached[eb] : 0u;
@@ -486,8 +512,8 @@ __global__ void __launch_bounds__(256, 2) k_obs_tiled(const MfgSpec* __restrict_
     // ---------------- phase 2: the warp expands its EPW envs, one tile of GE envs at a time ----------------------
     const uint32_t wv_lo = (uint32_t)wv, wv_hi = (uint32_t)(wv >> 32);
     for (int g = 0; g * GE < EPW; ++g) {
-      const int64_t eg = env0 + (int64_t)g * GE;
-      if (eg >= st.N) break;
+      const int eb0 = sub * EPW + g * GE;            // first env of this tile inside the CTA's 128
+      if (eb0 >= n_live) break;
       // Each lane keeps (up to) two sprites of the env in registers across the three passes; further rounds only exist
       // with a raised sprite capacity.  Dirt amounts (f64, uncoalesced) are requested as soon as the sprite is decoded
       // so that their latency overlaps the integer pass.
@@ -505,8 +531,8 @@ __global__ void __launch_bounds__(256, 2) k_obs_tiled(const MfgSpec* __restrict_
       };
       for (int ge = 0; ge < GE; ++ge) {
         const int elx = g * GE + ge;
-        const int64_t e = env0 + elx;
-        if (elx >= EPW || e >= st.N) break;
+        if (elx >= EPW || sub * EPW + elx >= n_live) break;
+        const int64_t e = env_of(sub * EPW + elx);
         float* te = tile + (size_t)ge * total_channels * DD;
         const int cnt = s_cnt[elx];
         if (cnt > cap) {                      // sprite list overflowed (or too many uid conflicts): k_obs_redo rewrites this env
@@ -579,17 +605,19 @@ __global__ void __launch_bounds__(256, 2) k_obs_tiled(const MfgSpec* __restrict_
       }
       // ---- stream the tile out
       int ne = EPW - g * GE < GE ? EPW - g * GE : GE;
-      if (st.N - eg < ne) ne = (int)(st.N - eg);
-      float* dst = obs + (size_t)eg * total_channels * DD;
-      // envs that are being re-spawned concurrently (skip flags) are written by k_obs_redo, not here
-      bool any_skip = false;
-      for (int ge = 0; ge < ne; ++ge) any_skip |= ((skip_mask >> ((g * GE + ge) << apad_log2)) & 1u) != 0;
-      if (any_skip) {
+      if (n_live - eb0 < ne) ne = n_live - eb0;
+      float* dst = obs + (size_t)env_of(eb0) * total_channels * DD;
+      // envs that are being re-spawned concurrently (skip flags) are written by the list-mode launch, not here; in list
+      // mode the envs of a multi-env tile are not neighbours in the output tensor
+      bool per_env = lmode && GE > 1;
+      for (int ge = 0; ge < ne; ++ge) per_env |= ((skip_mask >> ((g * GE + ge) << apad_log2)) & 1u) != 0;
+      if (per_env) {
         __syncwarp();
         const int per = total_channels * DD;
         for (int ge = 0; ge < ne; ++ge) {
           if ((skip_mask >> ((g * GE + ge) << apad_log2)) & 1u) continue;
-          for (int i = lane; i < per; i += 32) dst[ge * per + i] = tile[ge * per + i];
+          float* d1 = obs + (size_t)env_of(eb0 + ge) * per;
+          for (int i = lane; i < per; i += 32) d1[i] = tile[ge * per + i];
         }
         __syncwarp();
       } else if (bulk && ne == GE) {
@@ -610,6 +638,9 @@ __global__ void __launch_bounds__(256, 2) k_obs_tiled(const MfgSpec* __restrict_
         __syncwarp();
       }
     }
+  }
+  if (!lmode) break;
+  __syncthreads();                   // every warp is done with the image before the next chunk is staged
   }
   if (bulk && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // smem must outlive the copies
 }
@@ -851,44 +882,68 @@ void plan_obs(MfgHandle* h) {
 
 // exact per-agent observation of the envs in a device-side list (k_obs_redo)
 cudaError_t launch_obs_list(MfgHandle* h, float* d_obs, cudaStream_t s, const uint32_t* d_list, const uint32_t* d_count) {
-  const unsigned blocks = (unsigned)((h->N + ENV_BLOCK - 1) / ENV_BLOCK);
-  const unsigned rblocks = blocks < 296u ? blocks : 296u;
-  if (h->sp.n_agents <= 4) k_obs_redo<4><<<rblocks, 128, 0, s>>>(h->d_sp, h->tb, h->st, d_obs, h->total_channels, d_list, d_count);
-  else k_obs_redo<16><<<rblocks, 128, 0, s>>>(h->d_sp, h->tb, h->st, d_obs, h->total_channels, d_list, d_count);
-  return cudaGetLastError();
+  const unsigned blocks = (unsigned)((h->N + REDO_ENVS - 1) / REDO_ENVS);
+  const unsigned rblocks = blocks < 96u ? blocks : 96u;
+  const size_t smem = h->st.blk_i;
+  const ColTab ct{h->d_row_tab, h->n_row_tab};
+  cudaError_t err = cudaSuccess;
+  if (h->sp.n_agents <= 4) {
+    if (smem > 48 * 1024) err = cudaFuncSetAttribute(k_obs_redo<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err == cudaSuccess) k_obs_redo<4><<<rblocks, 128, smem, s>>>(h->d_sp, h->tb, h->st, ct, d_obs, h->total_channels, d_list, d_count);
+  } else {
+    if (smem > 48 * 1024) err = cudaFuncSetAttribute(k_obs_redo<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err == cudaSuccess) k_obs_redo<16><<<rblocks, 128, smem, s>>>(h->d_sp, h->tb, h->st, ct, d_obs, h->total_channels, d_list, d_count);
+  }
+  return err != cudaSuccess ? err : cudaGetLastError();
 }
 
 template <int R, bool FAITHFUL>
-static cudaError_t launch_tiled_f(MfgHandle* h, float* d_obs, cudaStream_t s, const uint8_t* skip) {
+static cudaError_t launch_tiled_f(MfgHandle* h, float* d_obs, cudaStream_t s, const uint8_t* skip, const ObsList& ol) {
   auto kern = k_obs_tiled<R, FAITHFUL>;
   const ObsPlan& p = h->plan;
   if (p.smem > 40 * 1024) {         // (static shared memory counts against the 48 KB default limit too)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return e;
   }
-  if (!h->d_redo) {                  // [0] = count, [1..N] = env ids
-    cudaError_t e = cudaMalloc(&h->d_redo, ((size_t)h->N + 1) * sizeof(uint32_t));
+  if (!h->d_redo) {                  // two lists (block-mode launch, list-mode launch), each: [0] = count, [1..N] = env ids
+    cudaError_t e = cudaMalloc(&h->d_redo, 2 * ((size_t)h->N + 1) * sizeof(uint32_t));
     if (e != cudaSuccess) return e;
   }
-  cudaError_t e = cudaMemsetAsync(h->d_redo, 0, sizeof(uint32_t), s);
+  uint32_t* redo = h->d_redo + (ol.ids ? (size_t)h->N + 1 : 0);
+  cudaError_t e = cudaMemsetAsync(redo, 0, sizeof(uint32_t), s);
   if (e != cudaSuccess) return e;
-  const unsigned blocks = (unsigned)((h->N + ENV_BLOCK - 1) / ENV_BLOCK);
+  unsigned blocks = (unsigned)((h->N + ENV_BLOCK - 1) / ENV_BLOCK);
+  if (ol.ids && blocks > 96u) blocks = 96u;          // list mode: grid-stride over the list inside the kernel
   kern<<<blocks, p.nw * 32, p.smem, s>>>(h->d_sp, h->tb, h->st, p.slots, p.walls, d_obs, h->total_channels, p.cap, p.apad_log2,
-                                         p.ge, h->obs_store != 0 ? 1 : 0, h->d_redo, skip);
+                                         p.ge, h->obs_store != 0 ? 1 : 0, redo, skip, ol);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  return launch_obs_list(h, d_obs, s, h->d_redo + 1, h->d_redo);
+  return launch_obs_list(h, d_obs, s, redo + 1, redo);
 }
 
 template <int R>
-static cudaError_t launch_tiled_r(MfgHandle* h, float* d_obs, cudaStream_t s, const uint8_t* skip) {
-  return h->sp.faithful ? launch_tiled_f<R, true>(h, d_obs, s, skip) : launch_tiled_f<R, false>(h, d_obs, s, skip);
+static cudaError_t launch_tiled_r(MfgHandle* h, float* d_obs, cudaStream_t s, const uint8_t* skip, const ObsList& ol) {
+  return h->sp.faithful ? launch_tiled_f<R, true>(h, d_obs, s, skip, ol) : launch_tiled_f<R, false>(h, d_obs, s, skip, ol);
+}
+
+// tiled observation of the envs in a device-side list (list mode of k_obs_tiled)
+cudaError_t launch_obs_tiled_list(MfgHandle* h, float* d_obs, cudaStream_t s, const uint32_t* d_list, const uint32_t* d_count) {
+  ObsList ol{d_list, d_count, h->d_row_tab, 0};
+  // the staged prefix = the first rows of the block image
+  for (int i = 0; i < h->n_row_tab && (h->row_tab_host[i] & 0x0FFFFFFFu) < (uint32_t)h->plan.slots.prefix_bytes; ++i) ol.n_rows = i + 1;
+  switch (h->sp.pomdp_r) {
+    case 1: return launch_tiled_r<1>(h, d_obs, s, nullptr, ol);
+    case 2: return launch_tiled_r<2>(h, d_obs, s, nullptr, ol);
+    case 3: return launch_tiled_r<3>(h, d_obs, s, nullptr, ol);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 cudaError_t launch_obs_tiled(MfgHandle* h, float* d_obs, cudaStream_t s, const uint8_t* skip) {
+  const ObsList ol{nullptr, nullptr, nullptr, 0};
   switch (h->sp.pomdp_r) {
-    case 1: return launch_tiled_r<1>(h, d_obs, s, skip);
-    case 2: return launch_tiled_r<2>(h, d_obs, s, skip);
-    case 3: return launch_tiled_r<3>(h, d_obs, s, skip);
+    case 1: return launch_tiled_r<1>(h, d_obs, s, skip, ol);
+    case 2: return launch_tiled_r<2>(h, d_obs, s, skip, ol);
+    case 3: return launch_tiled_r<3>(h, d_obs, s, skip, ol);
     default: return cudaErrorInvalidValue;
   }
 }

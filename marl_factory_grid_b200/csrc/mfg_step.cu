@@ -27,42 +27,24 @@ constexpr int STEP_ENVS_R = ENV_BLOCK;   // threads (= private columns) per CTA 
 // env's integer column into a private column of a shared-memory block image (independent loads), re-spawns against
 // that copy (hundreds of dependent look-ups stay on chip) and scatters the column back.
 template <int AMAX>
-__global__ void __launch_bounds__(STEP_ENVS_R) k_reset_list(const MfgSpec* __restrict__ sp, Tables tb, State st,
+__global__ void __launch_bounds__(STEP_ENVS_R) k_reset_list(const MfgSpec* __restrict__ sp, Tables tb, State st, ColTab ct,
                                                             const uint32_t* __restrict__ list, const uint32_t* __restrict__ count) {
   extern __shared__ __align__(128) unsigned char stage[];
   const uint32_t n = *count;
   const int t = threadIdx.x;
-  State ss = st;
-  ss.N = STEP_ENVS_R;
-  ss.base_i = reinterpret_cast<char*>(stage);
-  {
-    const char* g0 = st.base_i;
-#define F(type, name, rows_expr) \
-  if constexpr (!std::is_same<type, double>::value) ss.name = reinterpret_cast<type*>(stage + (reinterpret_cast<const char*>(st.name) - g0));
-    MFG_STATE_FIELDS(F)
-#undef F
-  }
+  const State ss = staged_view(st, stage);
   const MfgSpec& spr = *sp;
-  for (uint32_t i = blockIdx.x * blockDim.x + t; i < n; i += gridDim.x * blockDim.x) {
-    const int64_t e = list[i];
-    const uint32_t episode = field_at(st, st.episode, 0, e) + 1;
-#define F(type, name, rows_expr)                                                                       \
-  if constexpr (!std::is_same<type, double>::value) {                                                  \
-    const MfgSpec& sp = spr; (void)sp;                                                                 \
-    const int rows = (int)(rows_expr);                                                                 \
-    for (int r = 0; r < rows; ++r) ss.name[r * ENV_BLOCK + t] = field_at(st, st.name, r, e);           \
-  }
-    MFG_STATE_FIELDS(F)
-#undef F
-    env_reset<AMAX>(spr, tb, ss, t, episode, e);
-#define F(type, name, rows_expr)                                                                       \
-  if constexpr (!std::is_same<type, double>::value) {                                                  \
-    const MfgSpec& sp = spr; (void)sp;                                                                 \
-    const int rows = (int)(rows_expr);                                                                 \
-    for (int r = 0; r < rows; ++r) field_at(st, st.name, r, e) = ss.name[r * ENV_BLOCK + t];           \
-  }
-    MFG_STATE_FIELDS(F)
-#undef F
+  for (uint32_t base = blockIdx.x * STEP_ENVS_R; base < n; base += gridDim.x * STEP_ENVS_R) {
+    const int n_here = (int)(n - base < (uint32_t)STEP_ENVS_R ? n - base : (uint32_t)STEP_ENVS_R);
+    gather_columns(st, stage, ct, list, base, n_here);          // all threads: (row, env) pairs, loads in flight together
+    __syncthreads();
+    if (t < n_here) {
+      const int64_t e = list[base + t];
+      env_reset<AMAX>(spr, tb, ss, t, field_at(ss, ss.episode, 0, t) + 1, e);
+    }
+    __syncthreads();
+    scatter_columns(st, stage, ct, list, base, n_here);
+    __syncthreads();
   }
 }
 
@@ -215,7 +197,7 @@ cudaError_t launch_reset_list(MfgHandle* h, const StepIO& io, cudaStream_t s) {
     const unsigned rblocks = blocks < 48 ? blocks : 48;
     auto rk = k_reset_list<AMAX>;
     if (h->st.blk_i > 48 * 1024) err = cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->st.blk_i);
-    if (err == cudaSuccess) rk<<<rblocks, STEP_ENVS_R, h->st.blk_i, s>>>(h->d_sp, h->tb, h->st, io.reset_list, io.reset_count);
+    if (err == cudaSuccess) rk<<<rblocks, STEP_ENVS_R, h->st.blk_i, s>>>(h->d_sp, h->tb, h->st, ColTab{h->d_row_tab, h->n_row_tab}, io.reset_list, io.reset_count);
   });
   return err != cudaSuccess ? err : cudaGetLastError();
 }
