@@ -493,8 +493,15 @@ MFG_HD void stat_add_f64(const Tables& tb, int idx, double v) {
 // reset: Factory.reset with a fresh Factory: SpawnAgents, then the groups in Entities order
 // ================================================================================================
 template <int AMAX>
+MFG_HD void env_reset_inl(const MfgSpec& sp, const Tables& tb, const State& st, int64_t e, uint32_t episode, int64_t eg = -1);
+// out-of-line form: kept out of the instruction stream of kernels that only re-spawn on a rare path (k_step)
+template <int AMAX>
 MFG_HDNI void env_reset(const MfgSpec& sp, const Tables& tb, const State& st, int64_t e, uint32_t episode,
                        int64_t eg = -1) {
+  env_reset_inl<AMAX>(sp, tb, st, e, episode, eg);
+}
+template <int AMAX>
+MFG_HD void env_reset_inl(const MfgSpec& sp, const Tables& tb, const State& st, int64_t e, uint32_t episode, int64_t eg) {
   Env<AMAX> v(sp, tb, st, e, eg);
   const int A = v.A;
   Philox rng;

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(STEP_ENVS_R) k_reset_list(const MfgSpec* __res
     __syncthreads();
     if (t < n_here) {
       const int64_t e = list[base + t];
-      env_reset<AMAX>(spr, tb, ss, t, field_at(ss, ss.episode, 0, t) + 1, e);
+      env_reset_inl<AMAX>(spr, tb, ss, t, field_at(ss, ss.episode, 0, t) + 1, e);     // inlined: State / Tables stay in registers
     }
     __syncthreads();
     scatter_columns(st, stage, ct, list, base, n_here);
