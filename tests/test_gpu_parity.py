@@ -161,6 +161,37 @@ def test_tiled_observation_kernel_equals_direct_kernel_at_scale(cfg, faithful):
     eng.close()
 
 
+@pytest.mark.parametrize('faithful', [False, True])
+def test_full_size_properties_all_modules_262144_envs(faithful):
+    """BASELINE configs[3] at its full size (all modules, 262 144 envs), through size-independent properties: the fused
+    step_observe pipeline (side-stream re-spawn, list-mode observation) is deterministic, its observations equal the
+    direct per-agent kernel on the whole batch, finished envs restart at step 0, agents never stand on walls."""
+    es = spec_for('cfg4')
+    N = 262144
+    a, b = _engine(es, N, faithful=faithful, seed=21), _engine(es, N, faithful=faithful, seed=21)
+    a.reset()
+    b.reset()
+    acts = torch.zeros((N, es.n_agents), dtype=torch.int32, device='cuda:0')
+    walls = torch.as_tensor(es.walls, device='cuda:0')
+    for t in range(24):
+        a.random_actions(acts, seed=5, step_index=t)
+        o1, r1, d1 = a.step_observe(acts, auto_reset=True)
+        o2, r2, d2 = b.step_observe(acts, auto_reset=True)
+        if t % 8 == 7:
+            assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2), t
+            assert int(d1.sum()) > 0
+            assert int(a.field('step')[0][d1.bool()].max()) == 0          # finished envs were re-spawned in the same call
+            o1 = o1.clone()
+            a.set_option('obs_kernel', 1)
+            assert torch.equal(o1, a.observe()), f't={t}: fused pipeline != direct kernel'
+            a.set_option('obs_kernel', 0)
+            apos = a.field('apos').to(torch.int64) & 0xFFFF
+            assert not walls[apos >> 8, apos & 255].any()
+    np.testing.assert_array_equal(a.stats()[:11], b.stats()[:11])
+    a.close()
+    b.close()
+
+
 def test_inline_and_deferred_auto_reset_agree():
     """Three forms of auto-reset give identical results: the packed reset kernel overlapped with the observation kernel
     on a side stream (default of mfg_step_observe), the same kernel serialised, and the in-line reset inside k_step."""
