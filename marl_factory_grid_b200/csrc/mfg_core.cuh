@@ -771,15 +771,21 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
         MFG_NOUNROLL
         for (int k = 0; k < n; ++k) if ((l >> k) & 1) add(v.at(v.cls_pos(c), k));
       }
-      MFG_NOUNROLL
-      for (int d = 0; d < sp.n_doors; ++d) {
-        int n = (int)((c0 >> d) & 1) + 2 * (int)((c1 >> d) & 1);
-        if (n <= 2) {
-          if ((v.dopen >> d) & 1) {
-            uint8_t t = v.at(st.door_timer, d);
-            if (t) v.at(st.door_timer, d) = (uint8_t)(t - 1);
-            else v.dopen &= ~(1ull << d);
-          }
+      // count n = c0 + 2 c1 (saturating at 3).  Only open doors (count down / close) and crowded tiles (n = 3: timer
+      // reset) change state, so only those doors are visited.
+      const uint64_t all = sp.n_doors >= 64 ? ~0ull : ((1ull << sp.n_doors) - 1ull);
+      const uint64_t crowded = c0 & c1 & all;
+      for (uint64_t m = (v.dopen | crowded) & all; m; m &= m - 1) {
+#if defined(__CUDA_ARCH__)
+        const int d = __ffsll((long long)m) - 1;
+#else
+        int d = 0;
+        while (!((m >> d) & 1)) ++d;
+#endif
+        if (!((crowded >> d) & 1)) {
+          uint8_t t = v.at(st.door_timer, d);
+          if (t) v.at(st.door_timer, d) = (uint8_t)(t - 1);
+          else v.dopen &= ~(1ull << d);
         } else {
           v.at(st.door_timer, d) = DOOR_INTERVAL;
         }
