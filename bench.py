@@ -256,7 +256,7 @@ def measure(args, parity, steps, warmup, dev, rank, world, local, with_e2e):
                                     'frac': step_bytes * env_steps_per_s / world / 1e9 / peak}},
         'gpu_launches': launches,
         'obs_launch': {'threads': eng.info('obs_threads'), 'dyn_smem': eng.info('obs_smem'), 'ctas_per_sm': eng.info('obs_ctas_per_sm')},
-        'kernel_ms': {'k_step': step_ms, 'k_obs_tiled+redo': obs_ms, 'k_reset_list+k_obs_redo (side stream, overlaps k_obs_tiled)': reset_ms,
+        'kernel_ms': {'k_step': step_ms, 'k_obs_tiled+redo': obs_ms, 'k_reset_list (side stream, followed there by k_obs_tiled in list mode; overlaps the main k_obs_tiled)': reset_ms,
                       'rest (k_random_actions, joins, gaps)': rest_ms},
         'clocks': clocks.summary(),
         'episode_stats': {'episodes': int(stats[0]), 'env_steps_in_finished_episodes': int(stats[1]),
