@@ -125,6 +125,39 @@ def test_freerun_matches_host_build_of_device_code(cfg, faithful):
 
 
 @pytest.mark.parametrize('faithful', [False, True])
+@pytest.mark.parametrize('cfg', ['cfg4', 'stress'])
+def test_freerun_steady_state_matches_host_build(cfg, faithful):
+    """Long free run (several episodes per env: dirt respawns and compaction, un-listed entities, door traffic, re-spawns
+    through the side-stream pipeline): CUDA kernels == g++ build of the per-env code, every field / reward / done /
+    observation, checked every few steps."""
+    es = spec_for(cfg)           # `stress`: max_steps 200 => every env is re-spawned in the same step twice (full-size lists)
+    N, steps = 160, 420
+    eng = _engine(es, N, faithful=faithful, seed=77)
+    sim = HostSim(es, N, faithful=faithful, seed=77)
+    eng.reset()
+    sim.reset()
+    acts = torch.zeros((N, es.n_agents), dtype=torch.int32, device='cuda:0')
+    for t in range(steps):
+        eng.random_actions(acts, seed=13, step_index=t)
+        obs, rew, done = eng.step_observe(acts, auto_reset=True)
+        r2, d2 = sim.step(acts.cpu().numpy(), auto_reset=True)
+        np.testing.assert_array_equal(done.cpu().numpy(), d2, err_msg=f't={t} done')
+        np.testing.assert_array_equal(rew.cpu().numpy(), r2, err_msg=f't={t} reward')
+        if t % 7 == 6 or t > steps - 5:
+            f = eng.fields_numpy()
+            for name, arr in sim.fields.items():
+                if name == 'ep_ret':
+                    np.testing.assert_allclose(f[name], arr, rtol=1e-12, atol=1e-12)
+                else:
+                    np.testing.assert_array_equal(f[name], arr, err_msg=f't={t} field {name}')
+            np.testing.assert_array_equal(obs.cpu().numpy(), sim.observe(), err_msg=f't={t} obs')
+    s1, s2 = eng.stats(), sim.stats()
+    np.testing.assert_array_equal(s1[:11], s2[:11])
+    assert s1[0] > (2 * N if cfg == 'stress' else 0)
+    eng.close()
+
+
+@pytest.mark.parametrize('faithful', [False, True])
 @pytest.mark.parametrize('cfg', ['cfg1', 'cfg2', 'cfg4', 'stress'])
 def test_tiled_observation_kernel_equals_direct_kernel_at_scale(cfg, faithful):
     """Size-independent property at a larger batch: both observation kernels produce identical tensors, agents never
