@@ -285,7 +285,7 @@ def run_engine(args):
     other = None
     if not args.no_other_mode:
         other_parity = 'identity' if args.parity == 'faithful' else 'faithful'
-        other = measure(args, other_parity, min(args.steps, 200), args.warmup, dev, rank, world, local, with_e2e=False)
+        other = measure(args, other_parity, args.steps, args.warmup, dev, rank, world, local, with_e2e=False)
 
     if rank != 0:
         if world > 1:
@@ -330,8 +330,8 @@ def run_engine(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
-    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=1000)
+    ap.add_argument('--warmup', type=int, default=100)
     ap.add_argument('--impl', default='engine', choices=['engine', 'reference'])
     ap.add_argument('--config', default='cfg4')
     ap.add_argument('--envs-per-gpu', type=int, default=1 << 20)
