@@ -1,14 +1,15 @@
 #!/usr/bin/env python
 """bench.py - agent-steps/s including observations for the batched marl-factory-grid stepping engine.
 
-One "step" = one pass of the hot path over the whole batch: draw uniform random actions on the device (Philox),
-`mfg_step` (actions, rule hooks, done/reward, in-kernel auto reset) and `mfg_observe` (ray-cast observation
-tensor).  Workload at every N: BASELINE.json configs[3]/[4], the all-modules config (cfg4: level `large`,
-4 heterogeneous agents, POMDP r=3, every module incl. machines + maintainer) with 1,048,576 envs PER GPU
+One "step" = one pass of the hot path over the whole batch: draw uniform random actions on the device (Philox), then ONE
+`mfg_step_observe` call (k_step: actions, rule hooks, done / reward; packed re-spawn of the finished envs on a side stream;
+ray-cast observation tensor).  Workload at every N: BASELINE.json configs[3]/[4], the all-modules config (cfg4: level
+`large`, 4 heterogeneous agents, POMDP r=3, every module incl. machines + maintainer) with 1,048,576 envs PER GPU
 (the 1M..8M sweep of configs[4] => weak scaling; envs shard by global env id, no per-step collective, only the
-episode-statistics vector is all-reduced over NCCL).
+episode-statistics vector is all-reduced over NCCL).  Headline = `faithful` parity mode (the untouched reference); the
+identity-patched mode is measured in a second pass and reported under `other_parity_mode`.
 
-    python bench.py --gpus 1 --steps 50 --warmup 10            # this engine
+    python bench.py --gpus 1 --steps 1000 --warmup 100           # this engine (defaults: SURVEY.md 8d protocol)
     python bench.py --impl reference --gpus 1 --steps 3 --warmup 1   # CPU reference arm (oracle port, all host cores)
 
 Prints ONE JSON line (rank 0).  Extra keys: `roofline` (dominant kernel vs measured HBM peak), `cpu_baseline`

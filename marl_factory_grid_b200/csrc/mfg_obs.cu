@@ -1,17 +1,22 @@
 // mfg_obs.cu - observation kernels: OBSBuilder.build_for_all + RayCaster.visible_entities
 // (marl_factory_grid/utils/observation_builder.py:98-235, utils/ray_caster.py:66-199).
 //
-//   k_obs_tiled   identity parity mode.  CTA = 32 envs.
-//       phase 1  one thread per (env, agent) [warp = agent, lane = env]: 49-bit light-block mask (walls from a
-//                per-tile table + closed doors), ray march over the constexpr window-ray trie (straight-line bit
-//                tests, no table loads), then every visible in-window entity becomes an 8-byte "sprite"
-//                (plane-cell index, kind, value) in shared memory; walls stay a 49-bit mask.
-//       phase 2  one warp per env: zero the env's channel tile in shared memory, expand wall masks, add sprites
-//                (integer stacks first, fractional encodings last => the f64 sums of the reference are reproduced
+//   k_obs_tiled<R, FAITHFUL>   CTA = one 128-env state block (its positional prefix staged by one TMA bulk copy), 8 autonomous
+//                warps; both parity modes.  A list mode observes the envs of a device-side id list (re-spawned envs).
+//       phase 1  lane = (env, agent), 32 / A_pad envs per warp pass: 49-bit light-block mask (walls from a per-tile table +
+//                closed doors), ray march over the constexpr window-ray trie (straight-line bit tests, no table loads),
+//                one pass over the listed entities -> visibility masks per class, then every visible in-window entity
+//                becomes an 8-byte "sprite" (plane-cell index, kind, value) in shared memory; walls stay a 49-bit mask.
+//                Faithful mode adds the uid de-duplication of `set(visible_entities)`: candidate mask of the radius-D box,
+//                uid conflict masks, first-visit ranks on demand (first_visit_rank).
+//       phase 2  the same warp, one env at a time: zero the env's channel tile in shared memory, expand wall masks, add
+//                sprites (integer stacks first, fractional encodings last => the f64 sums of the reference are reproduced
 //                with one rounding), then ONE TMA bulk store (cp.async.bulk shared -> global) of the 16-byte aligned
 //                tile.  The observation write is 87-93 % of the algorithmic bytes of an env-step.
-//   k_obs_direct  one thread per (env, agent), every parity mode incl. the faithful first-visit uid de-duplication
-//                (mfg_core.cuh obs_agent_direct); the checker of the tiled kernel and the faithful-mode path.
+//   k_obs_redo    exact per-agent path over a device-side env list (sprite / conflict list overflow), columns staged in
+//                shared memory.
+//   k_obs_direct  one thread per (env, agent), every parity mode and full observability (mfg_core.cuh obs_agent_direct);
+//                the checker of the tiled kernel.
 #include <utility>
 #include "mfg_internal.hpp"
 #include "mfg_rays_gen.h"
