@@ -392,9 +392,22 @@ struct Env {
     return -1;
   }
   MFG_HD double dirt_sum() const {
+    // left-to-right f64 sum over the live piles (clean_up/groups.py:27-32).  The amounts live in HBM: fetch eight at a
+    // time with independent loads, then add in order (a dependent load per pile made the respawning lane - and with it
+    // the whole CTA - wait ~40 memory round trips).
     double s = 0.0;
     MFG_NOUNROLL
-    for (int k = 0; k < dirt_end; ++k) if (at(st.dirt_pos, k) != NO_POS) s += at(st.dirt_amt, k);
+    for (int k0 = 0; k0 < dirt_end; k0 += 8) {
+      double a[8];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int j = 0; j < 8; ++j) a[j] = (k0 + j < dirt_end) ? at(st.dirt_amt, k0 + j) : 0.0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int j = 0; j < 8; ++j) if (k0 + j < dirt_end && at(st.dirt_pos, k0 + j) != NO_POS) s += a[j];
+    }
     return s;
   }
   MFG_HD void dirt_compact() {
