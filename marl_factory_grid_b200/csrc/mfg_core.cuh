@@ -24,10 +24,12 @@
 #define MFG_HDNI __host__ __device__ __noinline__      // rare, large: kept out of the callers' instruction stream
 // tiny run-time trip counts, inlined at dozens of call sites: unrolling them quadruples the kernel image (icache misses)
 #define MFG_NOUNROLL _Pragma("unroll 1")
+#define MFG_UNROLL _Pragma("unroll")
 #else
 #define MFG_HD inline
 #define MFG_HDN inline
 #define MFG_HDNI inline
+#define MFG_UNROLL
 #define MFG_NOUNROLL
 #endif
 
@@ -343,7 +345,7 @@ struct Env {
       for (int k = 0; k < dirt_end; ++k)
         if (at(st.dirt_pos, k) == p && at(st.dirt_uid, k) == uid && ((dirt_listed >> k) & 1)) { cls = C_DIRT; idx = k; return true; }
     }
-    MFG_NOUNROLL
+    MFG_UNROLL
     for (int c = C_ITEM; c <= C_MAINT; ++c) {
       if (uid < cls_count(c) && at(cls_pos(c), uid) == p && ((at(cls_listed(c), 0) >> uid) & 1)) { cls = c; idx = uid; return true; }
     }
@@ -776,7 +778,7 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
 #pragma unroll
       for (int i = 0; i < AMAX; ++i) if (i < A) add(v.apos[i]);
       if (sp.has_dirt) for (int k = 0; k < v.dirt_end; ++k) if ((v.dirt_listed >> k) & 1) add(v.at(st.dirt_pos, k));
-      MFG_NOUNROLL
+      MFG_UNROLL
       for (int c = C_ITEM; c <= C_MAINT; ++c) {
         int n = v.cls_count(c);
         if (!n) continue;
