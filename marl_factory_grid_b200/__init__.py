@@ -12,11 +12,14 @@ from .config_parser import FactoryConfigParser, named_action_space  # noqa: F401
 from .level_parser import LevelParser  # noqa: F401
 from .spec import EnvSpec  # noqa: F401
 
-__all__ = ['Factory', 'FactoryConfigParser', 'LevelParser', 'EnvSpec', 'named_action_space']
+__all__ = ['Factory', 'EnvMonitor', 'FactoryConfigParser', 'LevelParser', 'EnvSpec', 'named_action_space']
 
 
 def __getattr__(name):
     if name == 'Factory':
         from .factory import Factory
         return Factory
+    if name == 'EnvMonitor':
+        from .monitor import EnvMonitor
+        return EnvMonitor
     raise AttributeError(name)

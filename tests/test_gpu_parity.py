@@ -306,3 +306,38 @@ def test_factory_batched_host_path_and_stats():
     st = f.episode_stats()
     assert st['episodes'] > 0 and st['steps'] >= st['episodes']
     f.close()
+
+
+def test_batched_env_monitor_records_every_finished_episode(tmp_path):
+    """EnvMonitor (utils/logging/envmonitor.py:15-73) over the batched Factory: one row per finished episode, episode
+    lengths and returns equal to what the step stream says, totals equal to the engine's device-side statistics."""
+    import pickle
+    from marl_factory_grid_b200 import EnvMonitor, Factory
+    from golden_util import CONFIGS
+    N = 512
+    f = Factory(CONFIGS / 'stress.yaml', n_envs=N, device='cuda:0', parity='faithful', auto_reset=True, seed=3)
+    m = EnvMonitor(f, filepath=tmp_path / 'monitor.pick')
+    m.reset()
+    A = f.spec.n_agents
+    g = torch.Generator(device='cuda:0').manual_seed(0)
+    hi = torch.tensor(f.spec.n_actions, device='cuda:0')
+    ret = np.zeros((N, A)); length = np.zeros(N, np.int64); want = []
+    for t in range(230):                       # max_steps = 200: every env finishes at least once
+        acts = (torch.rand((N, A), generator=g, device='cuda:0') * hi).to(torch.int32)
+        _, _, r, d, _ = m.step(acts)
+        ret += r.cpu().numpy().astype(np.float64); length += 1
+        for e in np.nonzero(d.cpu().numpy())[0]:
+            want.append((int(e), int(length[e]), ret[e].copy()))
+            ret[e] = 0; length[e] = 0
+    df = m.monitor_df
+    assert len(df) == len(want) >= N and list(df['episode']) == list(range(len(df)))
+    np.testing.assert_array_equal(df['env'].to_numpy(), [w[0] for w in want])
+    np.testing.assert_array_equal(df['steps'].to_numpy(), [w[1] for w in want])
+    np.testing.assert_allclose(df[list(df.columns[4:])].to_numpy(), np.stack([w[2] for w in want]), rtol=0, atol=1e-12)
+    st = f.episode_stats()
+    assert st['episodes'] == len(df) and st['steps'] == int(df['steps'].sum())
+    np.testing.assert_allclose(st['return_sum'], df['step_reward'].sum(), rtol=1e-5)
+    m.save_monitor()
+    back = pickle.load(open(tmp_path / 'monitor.pick', 'rb'))
+    assert len(back) == len(df) and 'index' in back.columns
+    f.close()
