@@ -172,6 +172,21 @@ def measure(args, parity, steps, warmup, dev, rank, world, local, with_e2e):
     for i in range(warmup):
         one_step(i)
     barrier()
+    graph = None
+    if args.graph:
+        # launch-bound batch sizes: the fused call as ONE CUDA-graph launch.  Kernel durations cannot be recorded inside a
+        # graph, so they are taken from a short eager pass first (same state, library event pairs).
+        eng.set_option('timing', 1)
+        for i in range(20):
+            one_step(warmup + i)
+        barrier()
+        eager_ms = {k: eng.info(k) * 1e-6 / 20 for k in ('obs_ns', 'step_ns', 'reset_ns')}
+        eng.set_option('timing', 0)
+        graph = eng.capture_step(acts, auto_reset=True)
+
+        def one_step(i):                      # noqa: F811
+            eng.random_actions(acts, seed=0, step_index=i)
+            graph.replay()
     launches0 = eng.info('launches')
     # per-kernel durations: CUDA event pairs recorded by the library around its launches, on the launching streams,
     # during the timed region below (mfg_set_option "timing"; read back after the region)
@@ -190,6 +205,9 @@ def measure(args, parity, steps, warmup, dev, rank, world, local, with_e2e):
     reset_ms = eng.info('reset_ns') * 1e-6 / max(steps, 1)
     eng.set_option('timing', 0)
     launches = eng.info('launches') - launches0
+    if graph is not None:
+        obs_ms, step_ms, reset_ms = eager_ms['obs_ns'], eager_ms['step_ns'], eager_ms['reset_ns']
+        launches = 8 * steps                  # kernels inside each replayed graph (+ k_random_actions), not counted by the library
 
     # episode statistics: the only cross-GPU exchange of the path (one small all-reduce over NVLink)
     stats = allreduce_stats(eng.stats(), device=dev)
@@ -304,7 +322,8 @@ def run_engine(args):
                                   'identity = the identity-patched reference (oracle-I), reported under other_parity_mode',
                    'obs_kernel': 'tiled' if m['tiled'] else 'direct',
                    'l2': f'per-step working set {m["step_bytes"] * n_local / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed)',
-                   'actions': 'device Philox, regenerated every step (inside the timed region)', 'auto_reset': True},
+                   'actions': 'device Philox, regenerated every step (inside the timed region)', 'auto_reset': True,
+                   'cuda_graph': bool(args.graph)},
         'env_steps_per_s': m['env_steps_per_s'],
         'roofline': m['roofline'], 'gpu_launches': m['gpu_launches'], 'obs_launch': m['obs_launch'], 'kernel_ms': m['kernel_ms'],
         'clocks': m['clocks'], 'episode_stats': m['episode_stats'],
@@ -343,6 +362,7 @@ def main():
     ap.add_argument('--cpu-steps', type=int, default=12000, help='env-steps per CPU worker for the baseline sample')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--graph', action='store_true', help='replay the fused step as one CUDA graph (launch-bound batch sizes)')
     ap.add_argument('--no-other-mode', action='store_true', help='skip the short second pass in the other parity mode')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'engine':

@@ -197,6 +197,32 @@ class Engine:
                                                   self._stream()))
         return self.obs, self.reward, self.done
 
+    def capture_step(self, actions, auto_reset=True):
+        """CUDA-graph form of `step_observe` for launch-bound batch sizes: the whole call (k_step, packed re-spawn on the
+        side stream, tiled + list-mode observation kernels, their memsets and the fork / join events) becomes ONE graph
+        launch.  `actions` must be the int32 [N, A] device tensor the caller refills before every replay; results land
+        in `self.obs / self.reward / self.done`.  Returns the `torch.cuda.CUDAGraph` (call `.replay()`).
+
+        One eager step runs first so that the library's lazy allocations happen outside the capture; the state buffer
+        is restored afterwards (the statistics vector keeps that step)."""
+        t = self.torch
+        a = self._actions(actions)
+        if a.data_ptr() != actions.data_ptr():
+            raise ValueError('capture_step needs a contiguous int32 [N, A] tensor on the engine device')
+        saved = self.state.clone()
+        side = t.cuda.Stream(self.device)
+        side.wait_stream(t.cuda.current_stream(self.device))
+        with t.cuda.stream(side):
+            self.step_observe(a, auto_reset=auto_reset)
+        t.cuda.current_stream(self.device).wait_stream(side)
+        t.cuda.synchronize(self.device)
+        self.state.copy_(saved)
+        graph = t.cuda.CUDAGraph()
+        with t.cuda.graph(graph, stream=side, capture_error_mode='thread_local'):
+            self.step_observe(a, auto_reset=auto_reset)
+        self._graph_keep = (a, side)
+        return graph
+
     def random_actions(self, out, seed: int, step_index: int):
         with self.torch.cuda.device(self.device):
             self._check(self.lib.mfg_random_actions(self.h, out.data_ptr(), int(seed), int(step_index), self._stream()))

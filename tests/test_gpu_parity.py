@@ -341,3 +341,23 @@ def test_batched_env_monitor_records_every_finished_episode(tmp_path):
     back = pickle.load(open(tmp_path / 'monitor.pick', 'rb'))
     assert len(back) == len(df) and 'index' in back.columns
     f.close()
+
+
+def test_cuda_graph_replay_equals_eager_step_observe():
+    """Engine.capture_step: the fused call captured in a CUDA graph (side-stream fork / join included) gives the same
+    observations, rewards, done flags and state as eager calls."""
+    es = spec_for('cfg4')
+    N = 1024
+    a, b = _engine(es, N, faithful=True, seed=4), _engine(es, N, faithful=True, seed=4)
+    a.reset()
+    b.reset()
+    acts = torch.zeros((N, es.n_agents), dtype=torch.int32, device='cuda:0')
+    graph = b.capture_step(acts, auto_reset=True)
+    for t in range(40):
+        a.random_actions(acts, seed=6, step_index=t)
+        o1, r1, d1 = a.step_observe(acts, auto_reset=True)
+        graph.replay()
+        assert torch.equal(o1, b.obs) and torch.equal(r1, b.reward) and torch.equal(d1, b.done), t
+    assert torch.equal(a.state, b.state)
+    a.close()
+    b.close()
