@@ -363,7 +363,9 @@ __global__ void __launch_bounds__(256, 2) k_obs_tiled(const MfgSpec* __restrict_
               const uint32_t uid = blk_dirt_uid[k * ENV_BLOCK + eb];
               bool cf;
               if (uid < 64) {
-                cf = ((seen >> uid) & 1ull) != 0;
+                // another holder of the uid exists, and one of the two is inside the window (the final pruning, applied
+                // before the pile takes a slot of the packed list: on small levels most piles share a uid with some wall)
+                cf = ((seen >> uid) & 1ull) != 0 && (c == 3 || ((win_uids >> uid) & 1ull) != 0);
                 if (c == 3) win_uids |= 1ull << uid;
               } else {
                 cf = uid >= (wrng & 0xFFFFu) && uid <= (wrng >> 16);
