@@ -348,8 +348,8 @@ __global__ void __launch_bounds__(256, 2) k_obs_tiled(const MfgSpec* __restrict_
             }
           seen |= seen32; dup |= dup32; win_uids |= win32;
         }
-        // dirt piles last (their uids are unique among dirt piles): conflicting ones go to an 8-entry packed list
-        unsigned long long dlist = 0ull, dlist2 = 0ull;          // 8 packed entries: uid | slot << 10
+        // dirt piles last (their uids are unique among dirt piles): conflicting ones go to a 12-entry packed list
+        unsigned long long dlist = 0ull, dlist2 = 0ull, dlist3 = 0ull;          // 12 packed entries: uid | slot << 10
         int ndl = 0;
         bool overflow = false;
         {
@@ -377,9 +377,9 @@ __global__ void __launch_bounds__(256, 2) k_obs_tiled(const MfgSpec* __restrict_
               }
               if (cf) {
                 if (uid < 64) dup |= 1ull << uid;
-                if (ndl < 8 && uid < 1024) {
+                if (ndl < 12 && uid < 1024) {
                   const unsigned long long en = (unsigned long long)(uid | ((uint32_t)k << 10)) << (16 * (ndl & 3));
-                  if (ndl < 4) dlist |= en; else dlist2 |= en;
+                  if (ndl < 4) dlist |= en; else if (ndl < 8) dlist2 |= en; else dlist3 |= en;
                   ++ndl;
                 }
                 else overflow = true;
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(256, 2) k_obs_tiled(const MfgSpec* __restrict_
               }
               int r_dirt = INF, k_dirt = -1;
               for (int i = 0; i < ndl; ++i) {
-                const uint32_t en = (uint32_t)((i < 4 ? dlist : dlist2) >> (16 * (i & 3))) & 0xFFFFu;
+                const uint32_t en = (uint32_t)((i < 4 ? dlist : i < 8 ? dlist2 : dlist3) >> (16 * (i & 3))) & 0xFFFFu;
                 if ((int)(en & 1023u) == u) { k_dirt = (int)(en >> 10); r_dirt = rk(pos[k_dirt]); }
               }
               int best = r_wall < r_door ? r_wall : r_door;
@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(256, 2) k_obs_tiled(const MfgSpec* __restrict_
             }
             // dirt piles with uid >= 64 can only meet the wall of that uid
             for (int i = 0; i < ndl; ++i) {
-              const uint32_t en = (uint32_t)((i < 4 ? dlist : dlist2) >> (16 * (i & 3))) & 0xFFFFu;
+              const uint32_t en = (uint32_t)((i < 4 ? dlist : i < 8 ? dlist2 : dlist3) >> (16 * (i & 3))) & 0xFFFFu;
               const int uid = (int)(en & 1023u), k = (int)(en >> 10);
               if (uid < 64 || uid >= n_walls) continue;
               const uint16_t w = tb.wall_pos[uid];

@@ -6,8 +6,8 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 from marl_factory_grid_b200 import FactoryConfigParser
 from marl_factory_grid_b200.engine import Engine
-es = FactoryConfigParser(ROOT / 'marl_factory_grid_b200' / 'configs' / 'cfg4.yaml').compile()
-N = 1 << 20
+es = FactoryConfigParser(ROOT / 'marl_factory_grid_b200' / 'configs' / (sys.argv[1] if len(sys.argv) > 1 else 'cfg4.yaml')).compile()
+N = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 20
 for parity in ('identity', 'faithful'):
     eng = Engine(es, N, device='cuda:0', faithful=parity == 'faithful', seed=es.env_seed)
     acts = torch.zeros((N, es.n_agents), dtype=torch.int32, device='cuda:0')
