@@ -125,6 +125,37 @@ def test_freerun_matches_host_build_of_device_code(cfg, faithful):
 
 
 @pytest.mark.parametrize('faithful', [False, True])
+@pytest.mark.parametrize('cfg', ['crowd', 'crowd12'])
+def test_freerun_wide_agent_mappings_match_host_build(cfg, faithful):
+    """7 and 12 agents per env: the 8- and 16-lane-per-env mappings of the tiled observation kernel (multi-env tiles for
+    the odd channel count of `crowd`), AMAX = 8 / 16 step kernels, re-spawns every 60 steps."""
+    es = spec_for(cfg)
+    N, steps = 70, 130
+    eng = _engine(es, N, faithful=faithful, seed=11)
+    assert eng.info('tiled_ok') == 1
+    sim = HostSim(es, N, faithful=faithful, seed=11)
+    eng.reset()
+    sim.reset()
+    acts = torch.zeros((N, es.n_agents), dtype=torch.int32, device='cuda:0')
+    for t in range(steps):
+        eng.random_actions(acts, seed=17, step_index=t)
+        obs, rew, done = eng.step_observe(acts, auto_reset=True)
+        r2, d2 = sim.step(acts.cpu().numpy(), auto_reset=True)
+        np.testing.assert_array_equal(done.cpu().numpy(), d2, err_msg=f't={t} done')
+        np.testing.assert_array_equal(rew.cpu().numpy(), r2, err_msg=f't={t} reward')
+        if t % 5 == 4:
+            f = eng.fields_numpy()
+            for name, arr in sim.fields.items():
+                if name == 'ep_ret':
+                    np.testing.assert_allclose(f[name], arr, rtol=1e-12, atol=1e-12)
+                else:
+                    np.testing.assert_array_equal(f[name], arr, err_msg=f't={t} field {name}')
+            np.testing.assert_array_equal(obs.cpu().numpy(), sim.observe(), err_msg=f't={t} obs')
+    assert eng.stats()[0] >= 2 * N
+    eng.close()
+
+
+@pytest.mark.parametrize('faithful', [False, True])
 @pytest.mark.parametrize('cfg', ['cfg4', 'stress'])
 def test_freerun_steady_state_matches_host_build(cfg, faithful):
     """Long free run (several episodes per env: dirt respawns and compaction, un-listed entities, door traffic, re-spawns
