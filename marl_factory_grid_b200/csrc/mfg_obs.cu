@@ -920,7 +920,7 @@ static cudaError_t launch_tiled_f(MfgHandle* h, float* d_obs, cudaStream_t s, co
   cudaError_t e = cudaMemsetAsync(redo, 0, sizeof(uint32_t), s);
   if (e != cudaSuccess) return e;
   unsigned blocks = (unsigned)((h->N + ENV_BLOCK - 1) / ENV_BLOCK);
-  if (ol.ids && blocks > 96u) blocks = 96u;          // list mode: grid-stride over the list inside the kernel
+  if (ol.ids && blocks > 592u) blocks = 592u;        // list mode: grid-stride over the list inside the kernel (idle CTAs exit at once)
   kern<<<blocks, p.nw * 32, p.smem, s>>>(h->d_sp, h->tb, h->st, p.slots, p.walls, d_obs, h->total_channels, p.cap, p.apad_log2,
                                          p.ge, h->obs_store != 0 ? 1 : 0, redo, skip, ol);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;

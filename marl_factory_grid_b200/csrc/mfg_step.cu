@@ -192,9 +192,8 @@ cudaError_t launch_reset_list(MfgHandle* h, const StepIO& io, cudaStream_t s) {
   cudaError_t err = cudaSuccess;
   dispatch_amax(h->sp.n_agents, [&](auto amax) {
     constexpr int AMAX = decltype(amax)::value;
-    // few CTAs: ~0.2 % of the envs finish per step, and every resident CTA holds a block image in shared memory that
-    // the concurrently running observation kernel could use (grid-stride loop covers larger lists)
-    const unsigned rblocks = blocks < 48 ? blocks : 48;
+    // ~0.2 % of the envs finish per step (a handful of busy CTAs); the grid-stride loop covers larger lists
+    const unsigned rblocks = blocks < 1184 ? blocks : 1184;      // CTAs beyond the list exit at once; a max-steps boundary can list most envs
     auto rk = k_reset_list<AMAX>;
     if (h->st.blk_i > 48 * 1024) err = cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->st.blk_i);
     if (err == cudaSuccess) rk<<<rblocks, STEP_ENVS_R, h->st.blk_i, s>>>(h->d_sp, h->tb, h->st, ColTab{h->d_row_tab, h->n_row_tab}, io.reset_list, io.reset_count);
