@@ -341,9 +341,14 @@ struct Env {
   MFG_HD bool find_listed(int uid, uint16_t p, int& cls, int& idx) const {
     if (uid < sp.n_doors && tbl(tb.door_pos, uid) == p && ((dlisted >> uid) & 1)) { cls = C_DOOR; idx = uid; return true; }
     if (sp.has_dirt && uid < (int)at(st.dirt_next_uid, 0)) {
+      // slots are in creation order and uids only grow (deleted slots keep theirs, compaction keeps the order), so the
+      // scan can stop at the first larger uid - the uids asked for (maintainers, items, doors ...) are small
       MFG_NOUNROLL
-      for (int k = 0; k < dirt_end; ++k)
-        if (at(st.dirt_pos, k) == p && at(st.dirt_uid, k) == uid && ((dirt_listed >> k) & 1)) { cls = C_DIRT; idx = k; return true; }
+      for (int k = 0; k < dirt_end; ++k) {
+        const int du = at(st.dirt_uid, k);
+        if (du > uid) break;
+        if (du == uid && at(st.dirt_pos, k) == p && ((dirt_listed >> k) & 1)) { cls = C_DIRT; idx = k; return true; }
+      }
     }
     MFG_UNROLL
     for (int c = C_ITEM; c <= C_MAINT; ++c) {
