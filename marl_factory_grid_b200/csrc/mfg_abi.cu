@@ -70,7 +70,7 @@ int mfg_create(const MfgSpec* spec, int64_t n_envs, int64_t env_id_offset, MfgHa
   h->N = n_envs;
   int rc;
 #define UP(field) if ((rc = upload(h, ht.field, &h->tb.field)) != MFG_OK) { mfg_destroy(h); return rc; }
-  UP(wall) UP(door_map) UP(floor_pos) UP(floor_index) UP(wall_uid) UP(wall_pos) UP(door_pos) UP(nexthop) UP(wall_win) UP(wall_box) UP(door_near)
+  UP(wall) UP(door_map) UP(floor_pos) UP(floor_index) UP(wall_uid) UP(wall_pos) UP(door_pos) UP(nexthop) UP(wall_win) UP(wall_box) UP(door_near) UP(door_adj)
   UP(vis_box) UP(wall_cand64) UP(wall_cand_rng) UP(wall_win64)
 #undef UP
   h->tb.env_id_offset = env_id_offset;

@@ -118,6 +118,7 @@ struct Tables {
   const uint8_t* nexthop;      // [F*F] or null
   const uint64_t* wall_win;    // [H*W] (2r+1)^2-bit wall mask of the window centred on the tile (r <= 3)
   const uint64_t* door_near;   // [H*W] doors inside the radius-D box centred on the tile (bit = door index)
+  const uint64_t* door_adj;    // [H*W] doors inside the 3x3 neighbourhood of the tile (DoorUse, doors/actions.py:18-34)
   const uint64_t* wall_box;    // [H*W][4] wall mask of the (2D+1)^2 box (D = 2r+1) centred on the tile, bit = (dx+D)*(2D+1)+(dy+D)
   // faithful observation mode (built by build_vis_tables, mfg_obs.cu): static walls-only visibility
   const uint64_t* vis_box;       // [H*W][4] box cells some full ray reaches when only walls block light (superset of the truth)
@@ -136,6 +137,13 @@ MFG_HD T& field_at(const State& st, T* base, int row, int64_t e) {
   return reinterpret_cast<T*>(b)[row * ENV_BLOCK + (int)(e & (ENV_BLOCK - 1))];
 }
 
+MFG_HD int ctz64(uint64_t m) {            // index of the lowest set bit (m != 0)
+#if defined(__CUDA_ARCH__)
+  return __ffsll((long long)m) - 1;
+#else
+  return __builtin_ctzll(m);
+#endif
+}
 MFG_HD int px(uint16_t p) { return p >> 8; }
 MFG_HD int py(uint16_t p) { return p & 255; }
 MFG_HD uint16_t mkpos(int x, int y) { return (uint16_t)((x << 8) | y); }
@@ -377,17 +385,13 @@ struct Env {
 
   // ---------------------------------------------------------------- doors (doors/actions.py:18-34, entitites.py:97-140)
   MFG_HD bool toggle_near(uint16_t p) {
-    bool valid = false;
-    int x = px(p), y = py(p);
-    MFG_NOUNROLL
-    for (int d = 0; d < sp.n_doors; ++d) {
-      uint16_t q = tbl(tb.door_pos, d);
-      int dx = px(q) - x, dy = py(q) - y;
-      if (((dlisted >> d) & 1) && dx >= -1 && dx <= 1 && dy >= -1 && dy <= 1) {
-        if ((dopen >> d) & 1) dopen &= ~(1ull << d);
-        else { dopen |= (1ull << d); at(st.door_timer, d) = DOOR_INTERVAL; }
-        valid = true;
-      }
+    // doors of the 3x3 neighbourhood (POS_MASK_8 + own tile) from the per-tile table, in door order
+    uint64_t m = tb.door_adj[px(p) * sp.W + py(p)] & dlisted;
+    const bool valid = m != 0;
+    for (; m; m &= m - 1) {
+      const int d = ctz64(m);
+      if ((dopen >> d) & 1) dopen &= ~(1ull << d);
+      else { dopen |= (1ull << d); at(st.door_timer, d) = DOOR_INTERVAL; }
     }
     return valid;
   }
@@ -796,12 +800,7 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
       const uint64_t all = sp.n_doors >= 64 ? ~0ull : ((1ull << sp.n_doors) - 1ull);
       const uint64_t crowded = c0 & c1 & all;
       for (uint64_t m = (v.dopen | crowded) & all; m; m &= m - 1) {
-#if defined(__CUDA_ARCH__)
-        const int d = __ffsll((long long)m) - 1;
-#else
-        int d = 0;
-        while (!((m >> d) & 1)) ++d;
-#endif
+        const int d = ctz64(m);
         if (!((crowded >> d) & 1)) {
           uint8_t t = v.at(st.door_timer, d);
           if (t) v.at(st.door_timer, d) = (uint8_t)(t - 1);

@@ -74,7 +74,7 @@ inline void bind_state(const MfgSpec& sp, int64_t N, void* base, State& st) {
 struct HostTables {
   std::vector<uint8_t> wall, door_map, nexthop;
   std::vector<uint16_t> floor_pos, floor_index, wall_uid, wall_pos, door_pos;
-  std::vector<uint64_t> wall_win, wall_box, door_near, vis_box, wall_cand64, wall_win64;
+  std::vector<uint64_t> wall_win, wall_box, door_near, door_adj, vis_box, wall_cand64, wall_win64;
   std::vector<uint32_t> wall_cand_rng;
 };
 
@@ -143,11 +143,13 @@ inline std::string build_tables(const MfgSpec& sp, HostTables& t) {
   }
   // per-tile mask of the doors inside the radius-D box (the observation kernels only look at those)
   t.door_near.assign((size_t)H * W, 0);
+  t.door_adj.assign((size_t)H * W, 0);
   for (int x = 0; x < H; ++x)
     for (int y = 0; y < W; ++y)
       for (int d = 0; d < sp.n_doors; ++d) {
         const int dx = px(sp.door_pos[d]) - x, dy = py(sp.door_pos[d]) - y;
         if (dx >= -D && dx <= D && dy >= -D && dy <= D) t.door_near[(size_t)x * W + y] |= 1ull << d;
+        if (dx >= -1 && dx <= 1 && dy >= -1 && dy <= 1) t.door_adj[(size_t)x * W + y] |= 1ull << d;
       }
   return "";
 }

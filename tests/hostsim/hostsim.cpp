@@ -53,6 +53,7 @@ const char* hs_create(const MfgSpec* spec, int64_t n_envs, int64_t env_id_offset
   h->tb.door_pos = h->ht.door_pos.data(); h->tb.nexthop = h->ht.nexthop.empty() ? nullptr : h->ht.nexthop.data();
   h->tb.wall_win = h->ht.wall_win.data();
   h->tb.wall_box = h->ht.wall_box.data();
+  h->tb.door_adj = h->ht.door_adj.data();
   h->tb.env_id_offset = env_id_offset; h->tb.stats = h->stats.data();
   h->sp.walls = nullptr; h->sp.floor_pos = nullptr; h->sp.door_pos = nullptr; h->sp.nexthop = nullptr;
   *out = h;
