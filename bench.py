@@ -246,6 +246,20 @@ def measure(args, parity, steps, warmup, dev, rank, world, local, with_e2e):
                    'd2h_bytes_per_step': int(h_rew.numel() * 4 + h_done.numel() + h_obs.numel() * 4) * world,
                    'note': 'mfg_step_host: pinned host actions in, reward + done + full observation tensor out, synchronous '
                            '(PCIe-bound: the dense f32 observation tensor is 7 KB per env)'}
+            # second view: a GPU-resident learner reads the observation tensor in place; only actions go in and reward /
+            # done come out over PCIe (mfg_step_host with h_obs = NULL).  Reported beside e2e, not instead of it.
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(k2 * 4):
+                h_act.copy_(pool[i % 2])
+                eng.step_host(h_act, h_rew, h_done, None, auto_reset=True)
+            barrier()
+            t_dev = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+            e2e['obs_left_on_device'] = {'value': world * n_local * A * k2 * 4 / float(t_dev[0]), 'unit': UNIT, 'steps': k2 * 4,
+                                         'h2d_bytes_per_step': int(h_act.numel() * 4) * world,
+                                         'd2h_bytes_per_step': int(h_rew.numel() * 4 + h_done.numel()) * world}
             del h_obs
         else:
             e2e = {'value': None, 'unit': UNIT, 'note': 'pinned host buffers could not be allocated on every rank'}
