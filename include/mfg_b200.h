@@ -75,7 +75,7 @@ enum { MFG_ST_EPISODES = 0, MFG_ST_STEPS, MFG_ST_DONE_MAX_STEPS, MFG_ST_DONE_ALL
  * yaml + level .txt by the host-side config compiler. */
 typedef struct MfgSpec {
   int32_t H, W, pomdp_r, n_agents;
-  int32_t individual_rewards;
+  int32_t individual_rewards;     /* must be 1: the reference raises TypeError (factory.py:217) on the first step otherwise */
   int32_t faithful;               /* 1: reproduce the reference's uid-equality artefact */
   int32_t n_floor, n_doors, n_walls;
   int32_t has_dirt, dirt_slots, dirt_quantity;
@@ -151,8 +151,8 @@ int mfg_bind_state(MfgHandle* h, void* d_state);
 
 /* Factory.reset: spawn every (masked) env from the engine's counter-based Philox streams. d_env_mask may be NULL. */
 int mfg_reset(MfgHandle* h, const uint8_t* d_env_mask, void* stream);
-/* Gamestate.tick + check_done + reward fold.  d_actions [N][A] int32, d_reward [N][A] float (or [N][1] when rewards
- * are not individual), d_done [N] uint8.  auto_reset != 0 re-spawns finished envs in the same launch. */
+/* Gamestate.tick + check_done + reward fold.  d_actions [N][A] int32, d_reward [N][A] float,
+ * d_done [N] uint8.  auto_reset != 0 re-spawns finished envs in the same launch. */
 int mfg_step(MfgHandle* h, const int32_t* d_actions, const MfgTape* tape, float* d_reward, uint8_t* d_done,
              int auto_reset, void* stream);
 /* OBSBuilder.build_for_all (observation_builder.py:98-235): packed observation tensor [N][sum(C_a)][D][D] float32. */

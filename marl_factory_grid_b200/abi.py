@@ -192,7 +192,7 @@ FIELD_DTYPES = {1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}
 FIELD_VIEW = {'bat': np.float64, 'ep_ret': np.float64, 'dirt_amt': np.float64, 'dirt_next_spawn': np.int16}
 
 STATE_FIELD_NAMES: List[str] = [
-    'step', 'episode', 'clock', 'apos', 'astamp', 'aflag', 'bat', 'ep_ret', 'door_open', 'door_listed', 'door_timer',
+    'step', 'episode', 'clock', 'apos', 'astamp', 'aflag', 'finished', 'bat', 'ep_ret', 'door_open', 'door_listed', 'door_timer',
     'dirt_pos', 'dirt_amt', 'dirt_uid', 'dirt_listed', 'dirt_end', 'dirt_n', 'dirt_next_uid', 'dirt_next_spawn',
     'item_pos', 'pod_pos', 'dest_pos', 'drop_pos', 'mach_pos', 'maint_pos', 'item_listed', 'pod_listed', 'dest_listed',
     'drop_listed', 'mach_listed', 'maint_listed', 'dest_reached', 'maint_target', 'maint_rand', 'maint_remaining',

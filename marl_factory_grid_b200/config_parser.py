@@ -386,6 +386,8 @@ class FactoryConfigParser:
             _require(es.n_maint > 0, name, 'Maintainers')
         elif op == S.R_DONE_MAX_STEPS:          # environment/rules.py:204
             p[0] = float(int(take('max_steps', 500)))
+            if not 0 <= p[0] <= 65535:
+                raise ValueError('DoneAtMaxStepsReached.max_steps must be within 0..65535 (16-bit step counter).')
         if kw:
             raise TypeError(f'{name}.__init__() got unexpected keyword argument(s) {sorted(kw)}.')
         return RuleSpec(name, op, p)

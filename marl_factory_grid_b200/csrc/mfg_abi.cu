@@ -153,6 +153,7 @@ int mfg_bind_state(MfgHandle* h, void* d_state) {
 int mfg_reset(MfgHandle* h, const uint8_t* d_env_mask, void* stream) {
   NEED_BOUND(h);
   CUDA_TRY(launch_reset(h, d_env_mask, static_cast<cudaStream_t>(stream)));
+  if (!d_env_mask) h->ever_reset = true;
   h->launches++;
   return MFG_OK;
 }
@@ -264,7 +265,7 @@ int mfg_step_host(MfgHandle* h, const int32_t* h_actions, float* h_reward, uint8
   NEED_BOUND(h);
   if (!h_actions || !h_reward || !h_done) return fail(MFG_E_INVALID, "mfg_step_host: NULL buffer");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int A = h->sp.n_agents, NR = h->sp.individual_rewards ? A : 1;
+  const int A = h->sp.n_agents, NR = A;
   const size_t obs_bytes = (size_t)h->N * h->total_channels * h->DD * sizeof(float);
   if (!h->d_actions) {
     CUDA_TRY(cudaMalloc(&h->d_actions, (size_t)h->N * A * sizeof(int32_t)));
@@ -308,6 +309,7 @@ int mfg_set_option(MfgHandle* h, const char* name, int64_t value) {
     return MFG_OK;
   }
   if (strcmp(name, "overlap_reset") == 0) { h->overlap_reset = value != 0; return MFG_OK; }
+  if (strcmp(name, "reseed") == 0) { h->ever_reset = false; return MFG_OK; }      // the next full reset starts again at episode 0
   if (strcmp(name, "timing") == 0) { h->timing = value != 0; return MFG_OK; }
   if (strcmp(name, "obs_store") == 0) {        // 1 = TMA bulk store of the tile (default), 0 = LDS/STG loop
     h->obs_store = value != 0;

@@ -79,6 +79,7 @@ enum { C_DOOR = 0, C_DIRT, C_ITEM, C_POD, C_DEST, C_DROP, C_MACH, C_MAINT, C_NON
   F(uint32_t, clock, 1)                                                            \
   F(uint32_t, astamp, sp.n_agents)                                                 \
   F(uint8_t, aflag, sp.n_agents)                                                   \
+  F(uint8_t, finished, 1)      /* episode over and not yet re-spawned: statistics are counted once */ \
   F(double, bat, sp.has_batteries ? sp.n_agents : 0)                               \
   F(double, ep_ret, sp.n_agents)                                                   \
   F(uint8_t, door_timer, sp.n_doors)                                               \
@@ -534,6 +535,7 @@ MFG_HD void env_reset_inl(const MfgSpec& sp, const Tables& tb, const State& st, 
   v.at(st.step, 0) = 0;
   v.at(st.episode, 0) = episode;
   v.at(st.clock, 0) = (uint32_t)A;
+  v.at(st.finished, 0) = 0;
   for (int i = 0; i < A; ++i) {
     v.at(st.astamp, i) = (uint32_t)i;
     v.at(st.aflag, i) = 0;
@@ -632,7 +634,7 @@ struct StepIO {
   const uint8_t* maint_act;   // [N][NM] or null
   const int8_t* respawn_n;    // [N] or null
   const uint16_t* respawn_pos;// [N][8] or null
-  float* reward;              // [N][A] (or [N][1])
+  float* reward;              // [N][A]
   uint8_t* done;              // [N]
   int auto_reset;             // 0 = never, 1 = re-spawn finished envs (inline, or deferred when reset_list is set)
   uint32_t* reset_list;       // deferred reset: finished env ids are appended here and re-spawned by k_reset_list, packed
@@ -693,7 +695,7 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
   double rew[AMAX];
 #pragma unroll
   for (int i = 0; i < AMAX; ++i) rew[i] = 0.0;
-  double glob = 0.0, other = 0.0;
+  double glob = 0.0;
   // The f64 fields live in HBM (never staged): fetch every battery level, episode return and action of this env up
   // front with independent loads (one round trip instead of a dependent one per use) and keep them in registers.
   double bat[AMAX], epr[AMAX];
@@ -701,7 +703,7 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
 #pragma unroll
   for (int i = 0; i < AMAX; ++i) {
     bat[i] = (i < A && sp.has_batteries) ? v.at(st.bat, i) : 1.0;
-    epr[i] = (i < A && (sp.individual_rewards || i == 0)) ? v.at(st.ep_ret, i) : 0.0;
+    epr[i] = i < A ? v.at(st.ep_ret, i) : 0.0;
     act[i] = i < A ? io.actions[(size_t)e * A + i] : 0;
   }
 
@@ -894,26 +896,6 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
       for (int i = 0; i < AMAX; ++i) {
         if (i < A && v.n_coll(px(v.apos[i]), py(v.apos[i])) >= 2) { rew[i] += P[0]; ++n_collisions; }
       }
-      if (!sp.individual_rewards) {
-        // non-agent guests of collision tiles also collect the penalty when rewards are summed (factory.py:256)
-        int n_other = 0;
-        uint32_t seen = 0;
-        if (sp.n_maint) {
-          uint32_t l = v.at(st.maint_listed, 0);
-          for (int k = 0; k < sp.n_maint; ++k) {
-            uint16_t q = v.at(st.maint_pos, k);
-            if (((l >> k) & 1) && v.n_coll(px(q), py(q)) >= 2) { ++n_other; seen |= 1u << k; }
-          }
-        }
-        for (int d = 0; d < sp.n_doors; ++d) {
-          uint16_t q = v.tbl(tb.door_pos, d);
-          if (((v.dlisted >> d) & 1) && !((v.dopen >> d) & 1) && v.n_coll(px(q), py(q)) >= 2) {
-            if (sp.faithful && d < 32 && ((seen >> d) & 1)) continue;   // `x.entity == guest` is uid equality
-            ++n_other;
-          }
-        }
-        other += P[0] * n_other;
-      }
     } else if (op == MFG_R_BATTERY_DECHARGE || op == MFG_R_DONE_BATTERY) {   // batteries/rules.py:66-87
 #pragma unroll
       for (int i = 0; i < AMAX; ++i) {
@@ -982,26 +964,17 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
     done |= fired;
   }
 
-  // ---- reward fold (factory.py:222-259)
-  if (sp.individual_rewards) {
+  // ---- reward fold (factory.py:222-259), individual rewards: agent's own results + the global ones.  The scalar form
+  // (individual_rewards: false) does not exist: the reference raises at factory.py:217 (`sum(reward)` of a float) on the
+  // first step, so mfg_create rejects such a spec.
 #pragma unroll
-    for (int i = 0; i < AMAX; ++i) {
-      if (i < A) {
-        double r = rew[i] + glob;
-        io.reward[(size_t)e * A + i] = (float)r;
-        epr[i] += r;
-        v.at(st.ep_ret, i) = epr[i];
-      }
+  for (int i = 0; i < AMAX; ++i) {
+    if (i < A) {
+      double r = rew[i] + glob;
+      io.reward[(size_t)e * A + i] = (float)r;
+      epr[i] += r;
+      v.at(st.ep_ret, i) = epr[i];
     }
-  } else {
-    double s = 0.0;
-#pragma unroll
-    for (int i = 0; i < AMAX; ++i) if (i < A) s += rew[i];
-    s += other;
-    s += glob;
-    io.reward[e] = (float)s;
-    epr[0] += s;
-    v.at(st.ep_ret, 0) = epr[0];
   }
   io.done[e] = done ? 1 : 0;
   if (sp.has_batteries) {
@@ -1012,15 +985,20 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
 
   // ---- episode statistics + optional in-kernel auto reset
   if (n_collisions) stat_add(tb, MFG_ST_COLLISIONS, (unsigned long long)n_collisions);
-  if (done) {
+  // an env that is stepped on after its episode ended (auto_reset off, like the reference's un-reset Factory) keeps
+  // ticking, but its episode is counted once
+  const bool first_done = done && !v.at(st.finished, 0);
+  if (done) v.at(st.finished, 0) = 1;
+  if (first_done) {
     stat_add(tb, MFG_ST_EPISODES, 1);
     stat_add(tb, MFG_ST_STEPS, (unsigned long long)step);
     if (reason >= 0) stat_add(tb, reason, 1);
     double tot = 0.0;
-    const int nr = sp.individual_rewards ? A : 1;
 #pragma unroll
-    for (int i = 0; i < AMAX; ++i) if (i < nr) { double x = epr[i]; tot += x; stat_add_f64(tb, MFG_ST_RETURN_AGENT0 + i, x); }
+    for (int i = 0; i < AMAX; ++i) if (i < A) { double x = epr[i]; tot += x; stat_add_f64(tb, MFG_ST_RETURN_AGENT0 + i, x); }
     stat_add_f64(tb, MFG_ST_RETURN_SUM, tot);
+  }
+  if (done) {
     if (io.auto_reset) {
 #if defined(__CUDA_ARCH__)
       if (io.reset_list) io.reset_list[atomicAdd(io.reset_count, 1u)] = (uint32_t)v.eg;

@@ -84,6 +84,7 @@ inline std::string build_tables(const MfgSpec& sp, HostTables& t) {
   if (!sp.walls || !sp.floor_pos) return "walls / floor_pos must not be NULL";
   if (sp.n_doors && !sp.door_pos) return "door_pos must not be NULL when n_doors > 0";
   t.wall.assign(sp.walls, sp.walls + (size_t)H * W);
+  const size_t hw_pad = ((size_t)H * W + 3) / 4 * 4;       // k_step copies wall / door_map as 32-bit words
   t.floor_pos.assign(sp.floor_pos, sp.floor_pos + sp.n_floor);
   t.door_pos.assign(sp.door_pos, sp.door_pos + sp.n_doors);
   if (t.door_pos.empty()) t.door_pos.push_back(NO_POS);
@@ -93,6 +94,8 @@ inline std::string build_tables(const MfgSpec& sp, HostTables& t) {
     if (x >= H || y >= W) return "door position outside the level";
     t.door_map[(size_t)x * W + y] = (uint8_t)d;
   }
+  t.wall.resize(hw_pad, 0);
+  t.door_map.resize(hw_pad, 0xFF);
   t.floor_index.assign((size_t)H * W, 0xFFFF);
   for (int f = 0; f < sp.n_floor; ++f) {
     int x = px(sp.floor_pos[f]), y = py(sp.floor_pos[f]);
@@ -156,6 +159,8 @@ inline std::string build_tables(const MfgSpec& sp, HostTables& t) {
 
 inline std::string validate_spec(const MfgSpec& sp) {
   if (sp.n_agents < 1 || sp.n_agents > MFG_MAX_AGENTS) return "n_agents out of range";
+  if (!sp.individual_rewards)
+    return "individual_rewards = 0 is not runnable: the reference raises TypeError at environment/factory.py:217 on the first step";
   if (sp.pomdp_r < 0 || sp.pomdp_r > 3) return "pomdp_r must be 0 (full observability) or 1..3";
   if (sp.pomdp_r == 0 && (sp.H < sp.W ? sp.H : sp.W) > MFG_MAX_RAY_LEN - 1)
     return "full observability needs min(H, W) <= 15 (ray length limit)";
@@ -172,6 +177,9 @@ inline std::string validate_spec(const MfgSpec& sp) {
   }
   for (int r = 0; r < sp.n_rays; ++r) if (sp.ray_len[r] < 1 || sp.ray_len[r] > MFG_MAX_RAY_LEN) return "ray_len out of range";
   if (sp.n_floor < sp.n_agents) return "fewer floor tiles than agents";
+  for (int r = 0; r < sp.n_rules; ++r)
+    if (sp.rule_op[r] == MFG_R_DONE_MAX_STEPS && !(sp.rule_param[r][0] >= 0 && sp.rule_param[r][0] <= 65535))
+      return "DoneAtMaxStepsReached.max_steps must be within 0..65535 (16-bit step counter)";
   return "";
 }
 

@@ -124,6 +124,7 @@ struct MfgHandle {
   int64_t N = 0;
   int total_channels = 0, DD = 0;
   bool bound = false;
+  bool ever_reset = false;     // the first full (unmasked) reset seeds episode 0; later resets advance each env's episode counter
   int obs_kernel = 0;          // 0 = auto (tiled when possible), 1 = direct, 2 = tiled
   int obs_store = 1;           // 1 = TMA bulk store of the tile, 0 = LDS/STG loop
   mfg::ObsPlan plan;

@@ -11,11 +11,13 @@
 using namespace mfg;
 
 template <int AMAX>
-__global__ void __launch_bounds__(128) k_reset(const MfgSpec* __restrict__ sp, Tables tb, State st, const uint8_t* mask) {
+__global__ void __launch_bounds__(128) k_reset(const MfgSpec* __restrict__ sp, Tables tb, State st, const uint8_t* mask, int first) {
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= st.N) return;
   if (mask && !mask[e]) return;
-  uint32_t episode = mask ? field_at(st, st.episode, 0, e) + 1 : 0;
+  // episode = third word of the Philox counter: every reset of an env draws a fresh layout; episode 0 is the first
+  // full reset of a handle (or the first after the "reseed" option)
+  uint32_t episode = first ? 0u : field_at(st, st.episode, 0, e) + 1;
   env_reset<AMAX>(*sp, tb, st, e, episode);
 }
 
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(STEP_ENVS, 5) k_step(const __grid_constant__ H
   uint32_t* s_wall = reinterpret_cast<uint32_t*>(stage + bytes);
   uint32_t* s_dmap = s_wall + HW4;
   uint16_t* s_dpos = reinterpret_cast<uint16_t*>(s_dmap + HW4);
-  {   // 32-bit copies (the device tables are allocated in 256-byte granules, reading the pad word is safe)
+  {   // 32-bit copies (build_tables pads both tables to a multiple of 4 bytes)
     const uint32_t* gw = reinterpret_cast<const uint32_t*>(tb.wall);
     const uint32_t* gd = reinterpret_cast<const uint32_t*>(tb.door_map);
     for (int i = el; i < HW4; i += STEP_ENVS) { s_wall[i] = gw[i]; s_dmap[i] = gd[i]; }
@@ -162,7 +164,7 @@ cudaError_t launch_reset(MfgHandle* h, const uint8_t* d_mask, cudaStream_t s) {
   const int threads = 128;
   const unsigned blocks = (unsigned)((h->N + threads - 1) / threads);
   dispatch_amax(h->sp.n_agents, [&](auto amax) {
-    k_reset<decltype(amax)::value><<<blocks, threads, 0, s>>>(h->d_sp, h->tb, h->st, d_mask);
+    k_reset<decltype(amax)::value><<<blocks, threads, 0, s>>>(h->d_sp, h->tb, h->st, d_mask, (!d_mask && !h->ever_reset) ? 1 : 0);
   });
   return cudaGetLastError();
 }

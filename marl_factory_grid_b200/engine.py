@@ -112,7 +112,7 @@ class Engine:
             self.fields[name] = torch.as_strided(self.state.view(dt), (n_blocks, f.rows, ENV_BLOCK),
                                                  (f.block_bytes // f.elem_size, ENV_BLOCK, 1), f.offset // f.elem_size)
         A = es.n_agents
-        self.n_rew = A if es.individual_rewards else 1
+        self.n_rew = A
         self.obs = torch.zeros((self.N, es.total_channels) + tuple(es.obs_shape), dtype=torch.float32, device=self.device)
         self.reward = torch.zeros((self.N, self.n_rew), dtype=torch.float32, device=self.device)
         self.done = torch.zeros(self.N, dtype=torch.uint8, device=self.device)

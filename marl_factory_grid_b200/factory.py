@@ -52,6 +52,10 @@ class Factory:
         self._config_file = config_file
         self.conf = FactoryConfigParser(config_file, custom_modules_path)
         self.spec: EnvSpec = self.conf.compile(custom_level_path=custom_level_path, dirt_slots=dirt_slots)
+        # `individual_rewards: false` is dead in the reference: construction and reset() work, the first step() raises
+        # TypeError at factory.py:217 (`sum(reward)` of a float).  Mirrored: the engine always folds per agent.
+        self._scalar_reward_defect = not self.spec.individual_rewards
+        self.spec.individual_rewards = True
         self.unbatched = n_envs is None
         self.n_envs = 1 if n_envs is None else int(n_envs)
         self.parity = parity
@@ -106,13 +110,15 @@ class Factory:
         """factory.py:189-220.  Returns (None, [obs per agent], reward, done, info)."""
         if self._needs_reset:
             raise RuntimeError('call reset() before step()')
+        if self._scalar_reward_defect:
+            raise TypeError("'float' object is not iterable")      # factory.py:217 with individual_rewards: false
         if self.unbatched and not hasattr(actions, 'shape'):
             actions = np.asarray(actions if isinstance(actions, (list, tuple)) else [int(actions)], np.int32)[None]
         obs, reward, done = self.engine.step_observe(actions, tape=tape, auto_reset=self.auto_reset)
         per_agent = self._split(obs)
         if self.unbatched:
             r = reward[0].cpu().numpy().astype(np.float64)
-            rew = [float(x) for x in r] if self.spec.individual_rewards else float(r[0])
+            rew = [float(x) for x in r]
             step = int(self.engine.fields['step'][0, 0, 0].item()) & 0xFFFF
             info = dict(step_reward=float(np.sum(r)), step=step)
             return None, [o[0].cpu().numpy() for o in per_agent], rew, bool(done[0].item()), info

@@ -42,6 +42,7 @@ def snapshot_to_columns(es: EnvSpec, snap: dict) -> Dict[str, np.ndarray]:
     col['clock'] = np.array([int(col['astamp'].max()) + 1], np.uint32)
     par = np.asarray(snap['paralysed']).reshape(A) if 'paralysed' in snap else np.zeros(A)
     col['aflag'] = par.astype(np.uint8)
+    col['finished'] = np.array([0], np.uint8)
     col['ep_ret'] = np.zeros(A, np.float64)
     if es.has_batteries:
         col['bat'] = np.asarray(snap['battery'], np.float64).reshape(A)

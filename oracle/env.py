@@ -180,7 +180,6 @@ class OracleEnv:
         self.step_no += 1
         rew = [0.0] * A
         glob = 0.0
-        other = 0.0                                     # rewards of non-agent entities (maintainers, doors)
 
         # ---- agents act sequentially against the live state (states.py:189-198)
         for i in range(A):
@@ -287,7 +286,6 @@ class OracleEnv:
                 for i in range(A):
                     if self.n_coll(self.apos[i]) >= 2:
                         rew[i] += P[0]
-                other += P[0] * self._n_non_agent_colliders()
             elif op in (S.R_BATTERY_DECHARGE, S.R_DONE_BATTERY):    # batteries/rules.py:66-87
                 for i in range(A):
                     if self.bat[i] == 0:
@@ -331,9 +329,11 @@ class OracleEnv:
                     done = True
                     glob += P[2]
         # ---- reward fold (factory.py:222-259)
-        if sp.individual_rewards:
-            return np.array([x + glob for x in rew], np.float64), bool(done)
-        return np.array([sum(rew) + other + glob], np.float64), bool(done)
+        # individual rewards only: with `individual_rewards: false` the reference raises TypeError at factory.py:217
+        # (`sum(reward)` of a float) on the first step, so there is no scalar fold to restate
+        if not sp.individual_rewards:
+            raise TypeError("'float' object is not iterable")
+        return np.array([x + glob for x in rew], np.float64), bool(done)
 
     @staticmethod
     def _remove_identity(lst, e):
@@ -341,15 +341,6 @@ class OracleEnv:
             if x is e:
                 del lst[k]
                 return
-
-    def _n_non_agent_colliders(self):
-        """Non-agent guests of collision tiles (rules.py:291-304); only matters when rewards are not individual.
-        The `x.entity == guest` de-dup uses uid equality in the untouched reference."""
-        keys = set()
-        for e in self.maints + self.doors:
-            if e.listed and (e.cls == 'maint' or not e.open) and self.n_coll(e.pos) >= 2:
-                keys.add(e.uid if self.faithful else (e.cls, e.uid))
-        return len(keys)
 
     def _any_listed_collision(self):
         tiles = [m.pos for m in self.maints if m.listed]

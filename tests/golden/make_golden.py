@@ -229,6 +229,13 @@ PLAN = {
     'stress': [(s, 'U', 200) for s in range(8)] + [(s, 'I', 200) for s in range(8, 12)],
     'obs_test': [(0, 'U', 3), (1, 'I', 3)],
     'stress2': [(s, 'U', 150) for s in range(4)] + [(s, 'I', 150) for s in range(4, 6)],
+    # the reference's own shipped scenarios, unmodified (configs/default_config.yaml, configs/clean_and_bring.yaml)
+    'default_config': [(0, 'U', 150), (1, 'U', 150), (2, 'I', 100)],
+    'clean_and_bring': [(0, 'U', 120), (1, 'U', 120), (2, 'I', 80)],
+    # done rules no other fixture fires: WatchCollisions.done_at_collisions, DoneAtDestinationReach all / simultaneous
+    'stress3': [(s, 'U', 120) for s in range(6)] + [(s, 'I', 120) for s in range(6, 8)],
+    'dest_all': [(s, 'U', 400) for s in range(3)] + [(3, 'I', 400)],
+    'dest_simul': [(s, 'U', 600) for s in range(3)] + [(3, 'I', 600)],
 }
 
 

@@ -20,6 +20,7 @@ struct HsHandle {
   std::vector<FieldInfo> fields;
   size_t bytes;
   std::vector<unsigned long long> stats;
+  bool ever_reset = false;
 };
 
 template <typename Fn>
@@ -71,8 +72,10 @@ void hs_bind_state(HsHandle* h, void* base) { bind_state(h->sp, h->N, base, h->s
 void hs_reset(HsHandle* h, const uint8_t* mask) {
   dispatch(h->sp.n_agents, [&](auto amax) {
     for (int64_t e = 0; e < h->N; ++e)
-      if (!mask || mask[e]) env_reset<decltype(amax)::value>(h->sp, h->tb, h->st, e, mask ? field_at(h->st, h->st.episode, 0, e) + 1 : 0);
+      if (!mask || mask[e])
+        env_reset<decltype(amax)::value>(h->sp, h->tb, h->st, e, (!mask && !h->ever_reset) ? 0u : field_at(h->st, h->st.episode, 0, e) + 1);
   });
+  if (!mask) h->ever_reset = true;
 }
 void hs_step(HsHandle* h, const int32_t* actions, const uint8_t* maint_act, const int8_t* respawn_n,
              const uint16_t* respawn_pos, float* reward, uint8_t* done, int auto_reset) {

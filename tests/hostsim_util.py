@@ -74,7 +74,7 @@ class HostSim:
             self._views[name] = np.lib.stride_tricks.as_strided(
                 typed, shape=(n_blocks, f.rows, ENV_BLOCK), strides=(f.block_bytes, ENV_BLOCK * f.elem_size, f.elem_size))
         A = es.n_agents
-        self.n_rew = A if es.individual_rewards else 1
+        self.n_rew = A
         self.reward = np.zeros((n_envs, self.n_rew), np.float32)
         self.done = np.zeros(n_envs, np.uint8)
         self.obs = np.zeros((n_envs, es.total_channels) + tuple(es.obs_shape), np.float32)

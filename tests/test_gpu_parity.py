@@ -25,8 +25,12 @@ def _engine(es, n, **kw):
     return Engine(es, n, device='cuda:0', **kw)
 
 
-def _replay_batch(cfg, mode, obs_kernels):
-    """All episodes of (cfg, mode) as ONE batch: env i replays episode i; finished episodes idle."""
+def _replay_batch(cfg, mode, obs_kernels, fused=False):
+    """All episodes of (cfg, mode) as ONE batch: env i replays episode i; finished episodes idle.
+
+    fused=True drives the ONE-call form `mfg_step_observe` with the tape and auto_reset on (k_step, packed re-spawn +
+    list-mode observation on the side stream, tiled observation kernel on the caller's stream): an env is compared until
+    the step that ends its episode (reward / done included); after that it is re-spawned from Philox and ignored."""
     es = spec_for(cfg)
     eps = [ep for ep in episodes(cfg) if ep['meta']['mode'] == mode]
     if not eps:
@@ -58,18 +62,27 @@ def _replay_batch(cfg, mode, obs_kernels):
                     ma[i, :NM] = ep['maint_act'][t]
                 rn[i], rp[i] = tape_respawn(ep, t)
         tape = dict(maint_action=ma[:, :NM] if NM else None, respawn_n=rn, respawn_pos=rp)
-        rew, done = eng.step(acts, tape=tape)
+        if fused:
+            obs, rew, done = eng.step_observe(acts, tape=tape, auto_reset=True)
+            obs = obs.cpu().numpy()
+        else:
+            rew, done = eng.step(acts, tape=tape)
         rew, done = rew.cpu().numpy(), done.cpu().numpy()
         fields = eng.fields_numpy()
         for i, ep in enumerate(eps):
             if t >= T[i]:
                 continue
+            np.testing.assert_allclose(rew[i], ep['reward'][t], rtol=1e-6, atol=1e-7, err_msg=f'{cfg}/{mode} env{i} step {t + 1}')
+            assert bool(done[i]) == bool(ep['done'][t]), f'{cfg}/{mode} env{i} step {t + 1} done'
+            if fused and done[i]:
+                continue                      # re-spawned inside the call: the reference episode is over
             got, want = eng.snapshot(i, fields), snap_at(ep, t + 1)
             for key in CMP_KEYS:
                 np.testing.assert_array_equal(got[key], want[key], err_msg=f'{cfg}/{mode} env{i} step {t + 1}: {key}')
-            np.testing.assert_allclose(rew[i], ep['reward'][t], rtol=1e-6, atol=1e-7, err_msg=f'{cfg}/{mode} env{i} step {t + 1}')
-            assert bool(done[i]) == bool(ep['done'][t]), f'{cfg}/{mode} env{i} step {t + 1} done'
-        check_obs(t + 1)
+            if fused:
+                np.testing.assert_array_equal(obs[i], ep['obs'][t + 1], err_msg=f'{cfg}/{mode} env{i} t={t + 1} fused obs')
+        if not fused:
+            check_obs(t + 1)
     eng.close()
 
 
@@ -83,6 +96,13 @@ def test_replay_untouched_reference(cfg):
 def test_replay_identity_reference(cfg):
     """identity mode == identity-patched reference; BOTH observation kernels (direct and tiled)."""
     _replay_batch(cfg, 'I', obs_kernels=[1, 2])
+
+
+@pytest.mark.parametrize('mode', ['U', 'I'])
+@pytest.mark.parametrize('cfg', ALL_CFGS)
+def test_replay_through_fused_step_observe(cfg, mode):
+    """The same reference traces through `mfg_step_observe` (tape + auto_reset): the overlapped side-stream pipeline."""
+    _replay_batch(cfg, mode, obs_kernels=[], fused=True)
 
 
 @pytest.mark.parametrize('mode', ['U', 'I'])

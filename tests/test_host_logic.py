@@ -45,6 +45,21 @@ def test_engine_fails_loudly_without_cuda():
         Engine(spec_for('cfg1'), 4)
 
 
+@pytest.mark.parametrize('cfg', ['cfg1', 'cfg2', 'cfg3', 'cfg4', 'stress', 'stress2', 'default_config', 'clean_and_bring',
+                                 'stress3', 'dest_all', 'dest_simul', 'obs_test'])
+def test_named_spaces_equal_the_reference(cfg):
+    """Agent names, named action space, action counts and the per-agent observation layer names recorded from the
+    reference's own `Factory` (meta of the golden traces) == what the config compiler derives (no GPU needed)."""
+    from marl_factory_grid_b200.config_parser import named_action_space
+    meta, es = episodes(cfg)[0]['meta'], spec_for(cfg)
+    assert [a.name for a in es.agents] == meta['agent_names']
+    assert named_action_space(es) == meta['named_action_space']
+    assert list(es.n_actions) == meta['n_actions']
+    assert [[act.name for act in a.actions] for a in es.agents] == meta['action_names']
+    assert [[ch.name for ch in a.channels] for a in es.agents] == meta['obs_layers']      # == Factory.named_observation_space
+    assert [es.H, es.W] == meta['level_shape']
+
+
 def test_ray_table_matches_survey_appendix_c():
     full = full_ray_table(7)
     assert len(full) == 44 and sum(len(r) for r in full) == 320
@@ -165,3 +180,61 @@ def test_freerun_invariants_host_build(cfg):
     assert st[9] == 0 and st[10] == 0                      # no dirt overflow; no spawn failure
     if cfg in ('stress', 'cfg3', 'cfg4'):
         assert st[0] > 0 and st[1] >= st[0]                # some episodes finished and were re-spawned in place
+
+
+def test_every_reset_draws_a_fresh_layout_host_build():
+    """a second full `reset()` must not replay episode 0.  Two consecutive unmasked resets give different
+    spawn layouts, and reset(mask = all ones) == the second unmasked reset (both advance each env's episode counter)."""
+    from hostsim_util import HostSim
+    es = spec_for('cfg4')
+    N = 40
+    a, b = HostSim(es, N, faithful=True, seed=5), HostSim(es, N, faithful=True, seed=5)
+    a.reset(); b.reset()
+    first = a.fields
+    np.testing.assert_array_equal(first['apos'], b.fields['apos'])
+    assert np.all(first['episode'] == 0)
+    a.reset()
+    b.reset(np.ones(N, np.uint8))
+    second = a.fields
+    assert np.all(second['episode'] == 1)
+    assert np.mean(np.any(second['apos'] != first['apos'], axis=0)) > 0.9          # fresh layouts
+    for name, arr in b.fields.items():
+        np.testing.assert_array_equal(arr, second[name], err_msg=name)
+
+
+def test_finished_envs_are_counted_once_without_auto_reset_host_build():
+    """with auto_reset off (the reference's convention) a finished env may keep being stepped; its episode
+    enters the statistics once, not once per step."""
+    from hostsim_util import HostSim
+    es = spec_for('stress')                  # max_steps = 200, several early done rules
+    N = 16
+    sim = HostSim(es, N, faithful=True, seed=1)
+    sim.reset()
+    rng = np.random.default_rng(3)
+    ever = np.zeros(N, bool)
+    for t in range(230):
+        a = np.stack([rng.integers(0, n, N) for n in es.n_actions], 1).astype(np.int32)
+        _, done = sim.step(a, auto_reset=False)
+        ever |= done.astype(bool)
+    assert ever.all()
+    st = sim.stats()
+    assert st[0] == N and st[1] <= 200 * N
+    assert np.all(sim.fields['finished'][0] == 1)
+    sim.reset()
+    assert np.all(sim.fields['finished'][0] == 0)
+
+
+def test_limits_are_rejected_not_wrapped(tmp_path):
+    from hostsim_util import HostSim
+    with pytest.raises(ValueError):          # 16-bit step counter
+        FactoryConfigParser(_write(tmp_path, lambda c: c['Rules']['DoneAtMaxStepsReached'].update(max_steps=70000))).compile()
+    # individual_rewards: false is dead in the reference (TypeError at environment/factory.py:217 on the first step)
+    es = FactoryConfigParser(_write(tmp_path, lambda c: c['General'].update(individual_rewards=False))).compile()
+    assert es.individual_rewards is False
+    with pytest.raises(RuntimeError, match='individual_rewards'):
+        HostSim(es, 1)                       # the C-side spec validation (shared with mfg_create)
+    from oracle.freerun import FreeRunEnv
+    env = FreeRunEnv(es, faithful=True, seed=0)
+    env.reset()
+    with pytest.raises(TypeError):
+        env.step_free([0] * es.n_agents)
