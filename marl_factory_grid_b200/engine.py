@@ -8,6 +8,7 @@ visible, construction raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 from typing import Dict, Optional
 
@@ -18,7 +19,8 @@ from .abi import (ENV_BLOCK, FIELD_DTYPES, FIELD_VIEW, N_STATS, RESPAWN_TAPE_W, 
 from .spec import EnvSpec
 from .state_io import columns_to_snapshot, snapshot_to_columns
 
-LIB_PATH = Path(__file__).resolve().parent / 'libmfg_b200.so'
+# MFG_B200_LIB: development aid (A/B runs of differently compiled builds); the product loads the in-tree library
+LIB_PATH = Path(os.environ.get('MFG_B200_LIB') or Path(__file__).resolve().parent / 'libmfg_b200.so')
 _lib = None
 
 EXPORTS = ['mfg_create', 'mfg_destroy', 'mfg_last_error', 'mfg_version', 'mfg_state_bytes', 'mfg_state_field',

@@ -412,3 +412,45 @@ def test_cuda_graph_replay_equals_eager_step_observe():
     assert torch.equal(a.state, b.state)
     a.close()
     b.close()
+
+
+def test_consecutive_resets_draw_fresh_layouts_and_match_host_build():
+    """every `reset()` advances the per-env episode counter (Philox counter word), so `env.reset()` per episode
+    (auto_reset off, the reference's usual loop) sees a new layout each time; reset(mask = all) == reset()."""
+    es = spec_for('cfg4')
+    N = 300
+    eng, eng2 = _engine(es, N, faithful=True, seed=5), _engine(es, N, faithful=True, seed=5)
+    sim = HostSim(es, N, faithful=True, seed=5)
+    layouts = []
+    for k in range(3):
+        eng.reset()
+        sim.reset()
+        eng2.reset(None if k == 0 else torch.ones(N, dtype=torch.uint8))
+        f = eng.fields_numpy()
+        for name, arr in sim.fields.items():
+            np.testing.assert_array_equal(f[name], arr, err_msg=f'reset {k} field {name}')
+        for name, arr in eng2.fields_numpy().items():
+            np.testing.assert_array_equal(f[name], arr, err_msg=f'reset {k} masked == unmasked: {name}')
+        assert np.all(f['episode'] == k)
+        layouts.append(f['apos'].copy())
+    assert np.mean(np.any(layouts[0] != layouts[1], axis=0)) > 0.9 and np.mean(np.any(layouts[1] != layouts[2], axis=0)) > 0.9
+    eng.close()
+    eng2.close()
+
+
+def test_factory_scalar_reward_config_raises_like_the_reference(tmp_path):
+    """`individual_rewards: false`: the reference constructs and resets, then raises TypeError at
+    environment/factory.py:217 on the first step."""
+    import yaml
+    from marl_factory_grid_b200 import Factory
+    from golden_util import CONFIGS
+    cfg = yaml.safe_load((CONFIGS / 'cfg2.yaml').read_text())
+    cfg['General']['individual_rewards'] = False
+    p = tmp_path / 'scalar.yaml'
+    p.write_text(yaml.safe_dump(cfg, sort_keys=False))
+    f = Factory(p, device='cuda:0')
+    obs = f.reset()
+    assert len(obs) == 2
+    with pytest.raises(TypeError):
+        f.step([0, 0])
+    f.close()
