@@ -43,19 +43,30 @@ WORKLOADS = {          # BASELINE.json configs[0..3] as restated in SURVEY.md Ap
 # CPU arm: the oracle port of the reference's CPU path, multiprocess over the host cores
 # ---------------------------------------------------------------------------------------------------------------
 class CpuPool:
-    """Persistent multiprocess pool of oracle environments (one per host core)."""
+    """Persistent multiprocess pool of CPU environments, one per host core.
 
-    def __init__(self, cfg: str, faithful: bool, procs: int):
+    kind 'reference' = the UNMODIFIED reference installed into baseline/_ref (baseline/install_ref.sh, SURVEY.md 8d protocol:
+    own Factory per worker, random.seed(worker), 30 warm-up steps, in-place reset on done, stdout suppressed);
+    kind 'port' = the oracle restatement (oracle/freerun.py), used when the reference install is absent."""
+
+    def __init__(self, cfg: str, faithful: bool, procs: int, kind: str = 'auto'):
         import multiprocessing as mp
-        from oracle.freerun import worker_init
-        self.procs = procs
-        self.pool = mp.get_context('spawn').Pool(procs, initializer=worker_init,
-                                                 initargs=(str(CONFIGS / f'{cfg}.yaml'), faithful, 1000))
+        from baseline import ref_worker
+        if kind == 'auto':
+            kind = 'reference' if ref_worker.available() else 'port'
+        self.kind, self.procs = kind, procs
+        cfg_path = str(CONFIGS / f'{cfg}.yaml')
+        if kind == 'reference':
+            self._run = ref_worker.worker_run
+            self.pool = mp.get_context('spawn').Pool(procs, initializer=ref_worker.worker_init, initargs=(cfg_path, 30))
+        else:
+            from oracle.freerun import worker_init, worker_run
+            self._run = worker_run
+            self.pool = mp.get_context('spawn').Pool(procs, initializer=worker_init, initargs=(cfg_path, faithful, 1000))
 
     def run(self, steps_per_worker: int):
         """Every worker advances its env by steps_per_worker; returns (agent_steps, slowest worker seconds)."""
-        from oracle.freerun import worker_run
-        res = self.pool.map(worker_run, [steps_per_worker] * self.procs, chunksize=1)
+        res = self.pool.map(self._run, [steps_per_worker] * self.procs, chunksize=1)
         return sum(r[0] for r in res), max(r[1] for r in res)
 
     def close(self):
@@ -63,14 +74,53 @@ class CpuPool:
         self.pool.join()
 
 
+def cpu_sample(cfg: str, faithful: bool, procs: int, kind: str, seconds: float):
+    """Bounded sample: a short calibration run sizes the timed run to ~`seconds`.  Returns (value, steps per worker, slowest s)."""
+    pool = CpuPool(cfg, faithful, procs, kind)
+    a, t = pool.run(20)
+    per = max(20, int(20 * seconds / max(t, 1e-3)))
+    agent_steps, slowest = pool.run(per)
+    pool.close()
+    return agent_steps / slowest, per, slowest, pool.kind
+
+
+def workload_config(args, world: int):
+    """The `config` object of the JSON line: a function of the arguments only, so that the engine arm and the reference arm
+    print the same one."""
+    from marl_factory_grid_b200 import FactoryConfigParser
+    es = FactoryConfigParser(CONFIGS / f'{args.config}.yaml').compile()
+    n_local = args.envs_per_gpu
+    step_bytes = es.algorithmic_bytes_per_env_step()
+    return {'workload': f'{args.config} {WORKLOADS.get(args.config, "")}, {n_local} envs per GPU',
+            'envs_total': world * n_local, 'agents': es.n_agents, 'parity': args.parity,
+            'parity_note': 'faithful = the untouched reference incl. its uid-equality artefact (bit-exact vs oracle-U traces); '
+                           'identity = the identity-patched reference (oracle-I), reported under other_parity_mode',
+            'l2': f'per-step working set {step_bytes * n_local / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed)',
+            'actions': 'uniform random, regenerated every step (engine: device Philox inside the timed region)', 'auto_reset': True,
+            'aged_steps': aged_steps(args),
+            'aged_note': 'untimed env-steps run before the warm-up so that a short timed region sees the steady-state episode mix'}
+
+
+def aged_steps(args) -> int:
+    """Short runs (the driver's --steps 20) would otherwise time young episodes only: few dirt piles, no un-listed entities.
+    Below 200 timed steps, ageing + warm-up together cover at least 300 env-steps (the SURVEY 8d protocol - 100 + 1000
+    steps - spans the whole episode-age mix by itself)."""
+    if args.age >= 0:
+        return args.age
+    return max(0, 300 - args.warmup) if args.steps < 200 else 0
+
+
 def run_reference(args):
-    """--impl reference: times the CPU path (oracle port; the Python reference itself cannot travel to the GPU box)."""
+    """--impl reference: times the reference's own CPU implementation of the path on the host cores (the unmodified
+    reference from baseline/_ref; the oracle port only if that install is absent).  Each bench "step" is a bounded sample:
+    every worker advances its env by `per_step` env-steps."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     procs = os.cpu_count() or 1
-    per_step = max(20, args.cpu_steps // max(args.steps, 1))     # env-steps per worker per bench "step"
     pool = CpuPool(args.config, args.parity == 'faithful', procs)
+    a, t = pool.run(10)                                           # calibration: size a bench step to ~cpu_seconds / steps
+    per_step = max(5, int(10 * args.cpu_seconds / max(args.steps, 1) / max(t, 1e-3)))
     for _ in range(max(args.warmup, 1)):
         pool.run(per_step)
     tot_steps, tot_time = 0, 0.0
@@ -80,13 +130,14 @@ def run_reference(args):
         tot_time += slowest
     pool.close()
     value = tot_steps / tot_time
-    sample = (f'{procs} procs x {per_step} env-steps of {args.config} per bench step (random actions, obs built every '
-              f'step, in-place reset)')
+    what = 'unmodified reference (baseline/_ref)' if pool.kind == 'reference' else 'oracle port of the reference step+obs'
+    sample = (f'{procs} procs x {per_step} env-steps of {args.config} per bench step, {what} (own Factory per worker, random '
+              f'actions, obs built every step, in-place reset on done)')
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': 1e3 * tot_time / max(args.steps, 1), 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': f'{args.config} all-modules, CPU oracle port of the reference step+obs', 'parity': args.parity},
-            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': procs, 'kind': 'port', 'sample': sample},
+            'config': workload_config(args, int(os.environ.get('WORLD_SIZE', '1'))), 'cpu_arm': what,
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': procs, 'kind': pool.kind, 'sample': sample},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line), flush=True)
 
@@ -129,6 +180,14 @@ class ClockSampler:
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': reasons, 'samples': len(self.rows)}
 
 
+def kernel_source_sha() -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted((ROOT / 'marl_factory_grid_b200' / 'csrc').glob('*.cu*')) + sorted((ROOT / 'marl_factory_grid_b200' / 'csrc').glob('*.h*')):
+        h.update(f.read_bytes())
+    return h.hexdigest()[:16]
+
+
 def hbm_peak():
     p = ROOT / 'MEASURED_PEAKS.json'
     if p.exists():
@@ -169,9 +228,13 @@ def measure(args, parity, steps, warmup, dev, rank, world, local, with_e2e):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for i in range(warmup):
+    n_age = aged_steps(args)
+    for i in range(n_age):                 # untimed, not part of `steps` / `warmup` (config.aged_steps)
         one_step(i)
+    for i in range(warmup):
+        one_step(n_age + i)
     barrier()
+    warmup = n_age + warmup                # step index offset of the timed region
     graph = None
     if args.graph:
         # launch-bound batch sizes: the fused call as ONE CUDA-graph launch.  Kernel durations cannot be recorded inside a
@@ -260,6 +323,20 @@ def measure(args, parity, steps, warmup, dev, rank, world, local, with_e2e):
             e2e['obs_left_on_device'] = {'value': world * n_local * A * k2 * 4 / float(t_dev[0]), 'unit': UNIT, 'steps': k2 * 4,
                                          'h2d_bytes_per_step': int(h_act.numel() * 4) * world,
                                          'd2h_bytes_per_step': int(h_rew.numel() * 4 + h_done.numel()) * world}
+            # what the link can do: pinned D2H copy of the same observation tensor, alone (the end-to-end call adds the compute
+            # in front of it and the small H2D / D2H transfers: it is synchronous by contract, results land in the caller's buffers)
+            barrier()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for _ in range(2):
+                h_obs.copy_(eng.obs, non_blocking=True)
+            ev1.record()
+            torch.cuda.synchronize(dev)
+            d2h_gbs = 2 * h_obs.numel() * 4 / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
+            d2h_gbs = -allreduce_max(-d2h_gbs, dev)          # slowest rank (all ranks copy at the same time)
+            e2e['d2h_link'] = {'pinned_d2h_gbs_per_rank_concurrent': d2h_gbs,
+                               'e2e_d2h_gbs_per_rank': e2e['d2h_bytes_per_step'] / world * k2 / float(t_e2e[0]) / 1e9,
+                               'frac_of_link': e2e['d2h_bytes_per_step'] / world * k2 / float(t_e2e[0]) / 1e9 / d2h_gbs}
             del h_obs
         else:
             e2e = {'value': None, 'unit': UNIT, 'note': 'pinned host buffers could not be allocated on every rank'}
@@ -271,18 +348,25 @@ def measure(args, parity, steps, warmup, dev, rank, world, local, with_e2e):
     step_bytes = es.algorithmic_bytes_per_env_step()
     achieved = obs_bytes * n_local / (obs_ms * 1e-3) / 1e9
     tiled = bool(eng.info('tiled_ok')) and args.obs_kernel != 1
-    traffic = None
+    # dram bytes of one launch of the dominant kernel cannot be measured in-run (ncu only): the committed capture is used
+    # when it was taken from the current kernel sources (sha256 stamp), otherwise the key is null
+    traffic, traffic_note = None, 'no ncu capture for this configuration'
     tp = ROOT / 'profiles' / 'obs_kernel_traffic.json'
     if tp.exists():
         try:
-            traffic = json.loads(tp.read_text()).get(f'{args.config}:{parity}:{n_local}')
+            rec = json.loads(tp.read_text())
+            if rec.get('source_sha256') == kernel_source_sha():
+                traffic = rec.get(f'{args.config}:{parity}:{n_local}')
+                traffic_note = f'ncu --set full capture, {rec.get("captured", "?")}' if traffic else traffic_note
+            else:
+                traffic_note = 'committed ncu capture is older than the kernel sources: dropped'
         except Exception:
             traffic = None
     out = {
         'A': A, 'parity': parity, 'steps': steps, 'value': env_steps_per_s * A, 'env_steps_per_s': env_steps_per_s,
         'ms_per_step': elapsed_ms / max(steps, 1), 'tiled': tiled, 'step_bytes': step_bytes, 'n_local': n_local,
         'roofline': {'bound': 'hbm', 'kernel': 'k_obs_tiled' if tiled else 'k_obs_direct',
-                     'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
+                     'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'traffic_note': traffic_note,
                      'peak_source': peak_src, 'bytes_per_env': obs_bytes, 'ms_per_launch': obs_ms,
                      'whole_step': {'bytes_per_env_step': step_bytes,
                                     'achieved': step_bytes * env_steps_per_s / world / 1e9,
@@ -330,14 +414,8 @@ def run_engine(args):
         'metric': METRIC, 'value': m['value'], 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': m['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'u16/f64 state, f32 obs', 'data': 'synthetic',
-        'config': {'workload': f'{args.config} {WORKLOADS.get(args.config, "")}, {n_local} envs per GPU',
-                   'envs_total': world * n_local, 'agents': A, 'parity': m['parity'],
-                   'parity_note': 'faithful = the untouched reference incl. its uid-equality artefact (bit-exact vs oracle-U traces); '
-                                  'identity = the identity-patched reference (oracle-I), reported under other_parity_mode',
-                   'obs_kernel': 'tiled' if m['tiled'] else 'direct',
-                   'l2': f'per-step working set {m["step_bytes"] * n_local / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed)',
-                   'actions': 'device Philox, regenerated every step (inside the timed region)', 'auto_reset': True,
-                   'cuda_graph': bool(args.graph)},
+        'config': workload_config(args, world),
+        'engine': {'obs_kernel': 'tiled' if m['tiled'] else 'direct', 'cuda_graph': bool(args.graph)},
         'env_steps_per_s': m['env_steps_per_s'],
         'roofline': m['roofline'], 'gpu_launches': m['gpu_launches'], 'obs_launch': m['obs_launch'], 'kernel_ms': m['kernel_ms'],
         'clocks': m['clocks'], 'episode_stats': m['episode_stats'],
@@ -349,13 +427,22 @@ def run_engine(args):
         line['e2e'] = m['e2e']
     if world == 1 and not args.no_cpu:
         procs = os.cpu_count() or 1
-        pool = CpuPool(args.config, args.parity == 'faithful', procs)
-        pool.run(50)                                                       # warm-up
-        agent_steps, slowest = pool.run(args.cpu_steps)
-        pool.close()
-        line['cpu_baseline'] = {'value': agent_steps / slowest, 'unit': UNIT, 'cores': procs, 'kind': 'port',
-                                'sample': f'{procs} procs x {args.cpu_steps} env-steps of {args.config}, oracle port of the '
-                                          f'reference step+obs (random actions, in-place reset), {slowest:.1f} s'}
+        faithful = args.parity == 'faithful'
+        v, per, slowest, kind = cpu_sample(args.config, faithful, procs, 'auto', args.cpu_seconds)
+        what = 'UNMODIFIED reference from baseline/_ref, SURVEY 8d protocol' if kind == 'reference' else 'oracle port of the reference step+obs'
+        line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': procs, 'kind': kind,
+                                'sample': f'{procs} procs x {per} env-steps of {args.config}, {what} (own Factory per worker, '
+                                          f'random actions, in-place reset on done), {slowest:.1f} s'}
+        if kind == 'reference':
+            # the port beside it (what round 1 reported), and the other BASELINE configs on the reference (short samples)
+            pv, pper, ps, _ = cpu_sample(args.config, faithful, procs, 'port', min(args.cpu_seconds, 6.0))
+            line['cpu_baseline']['port'] = {'value': pv, 'sample': f'{procs} procs x {pper} env-steps, oracle port, {ps:.1f} s'}
+            others = {}
+            for c in ('cfg1', 'cfg2', 'cfg3'):
+                if c != args.config and not args.no_cpu_sweep:
+                    ov, oper, os_, _ = cpu_sample(c, faithful, procs, 'reference', 4.0)
+                    others[c] = {'value': ov, 'sample': f'{procs} procs x {oper} env-steps, {os_:.1f} s'}
+            line['cpu_baseline']['other_configs'] = others
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -373,7 +460,9 @@ def main():
     ap.add_argument('--obs-kernel', type=int, default=0, help='0 auto, 1 direct, 2 tiled')
     ap.add_argument('--obs-store', type=int, default=1, help='1 TMA bulk store of the tile, 0 LDS/STG loop')
     ap.add_argument('--e2e-steps', type=int, default=5)
-    ap.add_argument('--cpu-steps', type=int, default=12000, help='env-steps per CPU worker for the baseline sample')
+    ap.add_argument('--cpu-seconds', type=float, default=12.0, help='wall-clock budget of the CPU baseline sample (bounded)')
+    ap.add_argument('--no-cpu-sweep', action='store_true', help='skip the short reference samples of the other BASELINE configs')
+    ap.add_argument('--age', type=int, default=-1, help='untimed ageing env-steps before the warm-up (-1: 300 - warmup, at least 0)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--graph', action='store_true', help='replay the fused step as one CUDA graph (launch-bound batch sizes)')

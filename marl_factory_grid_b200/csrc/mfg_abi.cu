@@ -63,6 +63,7 @@ int mfg_create(const MfgSpec* spec, int64_t n_envs, int64_t env_id_offset, MfgHa
   if (!err.empty()) return fail(MFG_E_INVALID, "mfg_create: " + err);
 
   build_vis_tables(*spec, ht);
+  build_win_vis_tables(*spec, ht);
 
   MfgHandle* h = new MfgHandle();
   h->sp = *spec;
@@ -71,7 +72,7 @@ int mfg_create(const MfgSpec* spec, int64_t n_envs, int64_t env_id_offset, MfgHa
   int rc;
 #define UP(field) if ((rc = upload(h, ht.field, &h->tb.field)) != MFG_OK) { mfg_destroy(h); return rc; }
   UP(wall) UP(door_map) UP(floor_pos) UP(floor_index) UP(wall_uid) UP(wall_pos) UP(door_pos) UP(nexthop) UP(wall_win) UP(wall_box) UP(door_near) UP(door_adj)
-  UP(vis_box) UP(wall_cand64) UP(wall_cand_rng) UP(wall_win64)
+  UP(vis_box) UP(wall_cand64) UP(wall_cand_rng) UP(wall_win64) UP(door_win) UP(vis_tab)
 #undef UP
   h->tb.env_id_offset = env_id_offset;
   void* d = nullptr;

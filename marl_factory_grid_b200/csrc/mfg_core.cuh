@@ -126,6 +126,10 @@ struct Tables {
   const uint64_t* wall_cand64;   // [H*W] bit u: wall with uid u < 64 lies on such a cell
   const uint32_t* wall_cand_rng; // [H*W] lo | hi << 16: range of the wall uids >= 64 on such cells (lo > hi: none)
   const uint64_t* wall_win64;    // [H*W] bit u: wall with uid u < 64 lies inside the window of the tile
+  // window visibility as a table (build_win_vis_tables, mfg_obs.cu): walls are static and a window holds few doors, so the ray
+  // march result only depends on (tile, which of the window's doors are closed)
+  const uint32_t* door_win;      // [H*W] up to 4 door indices inside the window (6 bits each) | count << 24 (7 = too many: march)
+  const uint64_t* vis_tab;       // [H*W][16] visibility mask of the window for every closed-door subset
   int64_t env_id_offset;
   unsigned long long* stats;   // [MFG_N_STATS]
 };

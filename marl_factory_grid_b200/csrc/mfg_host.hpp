@@ -75,7 +75,8 @@ struct HostTables {
   std::vector<uint8_t> wall, door_map, nexthop;
   std::vector<uint16_t> floor_pos, floor_index, wall_uid, wall_pos, door_pos;
   std::vector<uint64_t> wall_win, wall_box, door_near, door_adj, vis_box, wall_cand64, wall_win64;
-  std::vector<uint32_t> wall_cand_rng;
+  std::vector<uint32_t> wall_cand_rng, door_win;
+  std::vector<uint64_t> vis_tab;
 };
 
 inline std::string build_tables(const MfgSpec& sp, HostTables& t) {

@@ -158,6 +158,7 @@ cudaError_t launch_random_actions(MfgHandle* h, int32_t* d_actions, uint64_t see
 void plan_obs(MfgHandle* h);
 int obs_ctas_per_sm(const MfgHandle* h);
 void build_vis_tables(const MfgSpec& sp, HostTables& t);
+void build_win_vis_tables(const MfgSpec& sp, HostTables& t);
 cudaError_t launch_obs_direct(MfgHandle* h, float* d_obs, cudaStream_t s);
 cudaError_t launch_obs_tiled(MfgHandle* h, float* d_obs, cudaStream_t s, const uint8_t* skip = nullptr);
 cudaError_t launch_obs_list(MfgHandle* h, float* d_obs, cudaStream_t s, const uint32_t* d_list, const uint32_t* d_count);

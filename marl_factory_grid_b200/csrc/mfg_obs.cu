@@ -172,6 +172,7 @@ __global__ void __launch_bounds__(256, 2) k_obs_tiled(const MfgSpec* __restrict_
   // per-agent channel program (lanes of one warp belong to different agents, so it is read with per-lane indices)
   __shared__ uint16_t s_scal[MFG_MAX_AGENTS][4];               // scalar channels: channel | kind << 8
   __shared__ uint8_t s_nscal[MFG_MAX_AGENTS];
+  __shared__ uint8_t s_hasbat[MFG_MAX_AGENTS];
   __shared__ int s_coff[MFG_MAX_AGENTS];
   constexpr int D = 2 * R + 1, DD = D * D;
   const int A = sp->n_agents;
@@ -220,18 +221,22 @@ __global__ void __launch_bounds__(256, 2) k_obs_tiled(const MfgSpec* __restrict_
   for (int i = threadIdx.x; i < A * MFG_N_TERMS; i += blockDim.x) s_chm[i] = sp->term_chmask[i / MFG_N_TERMS][i % MFG_N_TERMS];
   if (threadIdx.x < A) {
     const int a = threadIdx.x, C = sp->n_channels[a];
-    int n = 0;
+    int n = 0, hb = 0;
     for (int c = 0; c < C; ++c) {
       const int kind = sp->ch_kind[a][c];
       if ((kind == MFG_CH_BATTERY || kind == MFG_CH_GLOBALPOS) && n < 4) s_scal[a][n++] = (uint16_t)(c | (kind << 8));
+      hb |= kind == MFG_CH_BATTERY;
     }
     s_nscal[a] = (uint8_t)n;
+    s_hasbat[a] = (uint8_t)hb;
     s_coff[a] = sp->ch_offset[a];
   }
   for (int i = threadIdx.x; i < sp->H; i += blockDim.x) s_gx[i] = (float)((double)i / (double)sp->H);
   for (int i = threadIdx.x; i < sp->W; i += blockDim.x) s_gy[i] = (float)((double)i / (double)sp->W);
   const int spW = sp->W, n_doors = sp->n_doors, n_dest = sp->n_dest, has_dirt = sp->has_dirt, n_walls = sp->n_walls;
   __syncthreads();
+  bool n_scal_any = false;
+  for (int aa = 0; aa < A; ++aa) n_scal_any |= s_nscal[aa] != 0;
   if (!lmode) mbar_wait0(&bar);
   const uint16_t* blk16 = reinterpret_cast<const uint16_t*>(s_blk);
   const unsigned long long* blk_dopen = reinterpret_cast<const unsigned long long*>(s_blk + sl.off_dopen);
@@ -250,7 +255,9 @@ __global__ void __launch_bounds__(256, 2) k_obs_tiled(const MfgSpec* __restrict_
     // ---------------- phase 1: lane = (env el, agent a) ---------------------------------------------------------
     const int el = lane >> apad_log2, a = lane & ((1 << apad_log2) - 1);
     unsigned long long wv = 0ull;
-    uint32_t skip_mask = 0u;          // bit (el << apad_log2): env el of this pass is skipped
+    uint32_t skip_mask = 0u;
+    float batv = 0.f;                 // Battery channel value of this (env, agent) lane
+    uint32_t axy = 0u;                // agent position of this lane (GlobalPosition channel)          // bit (el << apad_log2): env el of this pass is skipped
     {
       const int eb = sub * EPW + el;
       const bool in_range = eb < n_live;
@@ -273,6 +280,7 @@ __global__ void __launch_bounds__(256, 2) k_obs_tiled(const MfgSpec* __restrict_
         }
         const uint16_t p = pos[sl.agent0 + a];
         const int ax = px(p), ay = py(p);
+        axy = p;
         const int tile_id = ax * spW + ay;
         const unsigned long long W49 = tb.wall_win[tile_id];
         // static walls-only visibility of the radius-D box (faithful conflict filter); requested early, used late
@@ -284,13 +292,24 @@ __global__ void __launch_bounds__(256, 2) k_obs_tiled(const MfgSpec* __restrict_
         }
         // doors inside the radius-D box of this tile (static table): usually 0..3 of them
         const unsigned long long dnear = n_doors ? (tb.door_near[tile_id] & dlisted) : 0ull;
-        unsigned long long B = W49;
-        for (unsigned long long m = dnear & ~dopen; m; m &= m - 1) {
-          const uint16_t q = tb.door_pos[__ffsll((long long)m) - 1];
-          const int dx = px(q) - ax + R, dy = py(q) - ay + R;
-          if ((unsigned)dx < (unsigned)D && (unsigned)dy < (unsigned)D) B |= 1ull << (dx * D + dy);
+        // window visibility: a table look-up keyed by (tile, closed listed doors among the <= 4 doors of the window); the
+        // ray march itself only runs on tiles whose window holds more doors
+        unsigned long long vis;
+        const uint32_t dwin = FAITHFUL ? tb.door_win[tile_id] : (7u << 24);
+        if (FAITHFUL && (dwin >> 24) <= 4u) {          // (identity mode: two dependent table loads cost more than the march's ALU work)
+          const unsigned long long closed = dnear & ~dopen;
+          const uint32_t sub = ((uint32_t)(closed >> (dwin & 63u)) & 1u) | (((uint32_t)(closed >> ((dwin >> 6) & 63u)) & 1u) << 1) |
+                               (((uint32_t)(closed >> ((dwin >> 12) & 63u)) & 1u) << 2) | (((uint32_t)(closed >> ((dwin >> 18) & 63u)) & 1u) << 3);
+          vis = tb.vis_tab[(size_t)tile_id * 16 + (sub & ((1u << (dwin >> 24)) - 1u))];
+        } else {
+          unsigned long long B = W49;
+          for (unsigned long long m = dnear & ~dopen; m; m &= m - 1) {
+            const uint16_t q = tb.door_pos[__ffsll((long long)m) - 1];
+            const int dx = px(q) - ax + R, dy = py(q) - ay + R;
+            if ((unsigned)dx < (unsigned)D && (unsigned)dy < (unsigned)D) B |= 1ull << (dx * D + dy);
+          }
+          vis = march<R>(B);
         }
-        const unsigned long long vis = march<R>(B);
         wv = W49 & vis;
 
         // ---- one pass over the listed entities: which are visible inside the window (`*_w` masks), and (faithful
@@ -471,7 +490,8 @@ __global__ void __launch_bounds__(256, 2) k_obs_tiled(const MfgSpec* __restrict_
           const uint32_t m = chm[MFG_G_AGENT0 + j];
           if (!m) continue;
           const uint16_t q = pos[sl.agent0 + j];
-          if (classify(q) == 3) emit(m, wcell(q), SK_INT, 0, 1.0f);
+          const int bx = px(q) - ax + R, by = py(q) - ay + R;          // agents have string ids: only window visibility matters
+          if ((unsigned)bx < (unsigned)D && (unsigned)by < (unsigned)D && ((vis >> (bx * D + by)) & 1ull)) emit(m, bx * D + by, SK_INT, 0, 1.0f);
         }
         // small groups
         {
@@ -502,16 +522,9 @@ __global__ void __launch_bounds__(256, 2) k_obs_tiled(const MfgSpec* __restrict_
             emit(chm[MFG_G_DIRT], wcell(pos[k]), SK_DIRT, (uint32_t)k, 0.f);
           }
         }
-        // scalar channels
-        for (int i = 0; i < s_nscal[a]; ++i) {
-          const int c = s_scal[a][i] & 0xFF, kind = s_scal[a][i] >> 8;
-          if (kind == MFG_CH_BATTERY) {
-            put((uint32_t)((coff + c) * DD) | (SK_STORE << 16), (float)field_at(st, st.bat, a, e));
-          } else if (kind == MFG_CH_GLOBALPOS) {
-            put((uint32_t)((coff + c) * DD) | (SK_STORE << 16), s_gx[ax]);
-            put((uint32_t)((coff + c) * DD + 1) | (SK_STORE << 16), s_gy[ay]);
-          }
-        }
+        // scalar channels are written straight into the tile in phase 2; the battery level (f64 in HBM) is fetched here,
+        // one coalesced-ish load per (env, agent) lane
+        if (s_hasbat[a]) batv = (float)field_at(st, st.bat, a, e);
       }
     }
     __syncwarp();
@@ -563,30 +576,37 @@ __global__ void __launch_bounds__(256, 2) k_obs_tiled(const MfgSpec* __restrict_
         // (the sprite / dirt-amount loads above are in flight while the previous bulk store drains and the tile is cleared)
         if (ge == 0) clear_tile();
         // wall planes: 1.0 where a visible wall is.  Nothing else can be on a wall cell, so the (predicated) store has
-        // a unique writer and needs no ordering against the sprite adds below.
-        // Lane = (plane slot, window row): four planes per round, each lane writes the (at most D) wall cells of one row.
-        for (int w0 = 0; w0 < wp.n; w0 += 4) {
-          const int w = w0 + (lane >> 3), row = lane & 7;
-          const bool mine = w < wp.n && row < D;
-          const int src = (elx << apad_log2) + (mine ? (int)wp.agent[w] : 0);
+        // a unique writer and needs no ordering against the sprite adds below.  Lane = window cell (two cells per lane).
+        for (int w = 0; w < wp.n; ++w) {
+          const int src = (elx << apad_log2) + (int)wp.agent[w];
           const uint32_t m_lo = __shfl_sync(0xffffffffu, wv_lo, src), m_hi = __shfl_sync(0xffffffffu, wv_hi, src);
-          if (mine) {
-            const uint32_t bits = (uint32_t)((((unsigned long long)m_hi << 32) | m_lo) >> (row * D)) & ((1u << D) - 1u);
-            float* cells = te + (int)wp.plane[w] * DD + row * D;
-#pragma unroll
-            for (int c = 0; c < D; ++c) if ((bits >> c) & 1u) cells[c] = 1.0f;
+          float* cells = te + (int)wp.plane[w] * DD;
+          if ((m_lo >> lane) & 1u) cells[lane] = 1.0f;
+          if (lane + 32 < DD && ((m_hi >> lane) & 1u)) cells[lane + 32] = 1.0f;
+        }
+        // scalar channels (observation_builder.py:205-218): battery level / (x / H, y / W) at the first cells of their plane;
+        // the values sit in the (env, agent) lanes of phase 1
+        if (n_scal_any) {
+#pragma unroll 1
+          for (int aa = 0; aa < A; ++aa) {
+            const int src = (elx << apad_log2) + aa;
+            const float bv = __shfl_sync(0xffffffffu, batv, src);
+            const uint32_t pp = __shfl_sync(0xffffffffu, axy, src);
+            if (lane < s_nscal[aa]) {
+              const int c = s_scal[aa][lane] & 0xFF, kind = s_scal[aa][lane] >> 8;
+              float* pl = te + (s_coff[aa] + c) * DD;
+              if (kind == MFG_CH_BATTERY) pl[0] = bv;
+              else { pl[0] = s_gx[pp >> 8]; pl[1] = s_gy[pp & 255u]; }
+            }
           }
         }
-        // pass A: integer-valued sprites (stacks add up exactly) and direct stores
+        // pass A: integer-valued sprites (stacks add up exactly)
         if (k0 == SK_INT) atomicAdd(&te[s0.w & 0xFFFF], s0.val);
-        else if (k0 == SK_STORE) te[s0.w & 0xFFFF] = s0.val;
         if (k1 == SK_INT) atomicAdd(&te[s1.w & 0xFFFF], s1.val);
-        else if (k1 == SK_STORE) te[s1.w & 0xFFFF] = s1.val;
         for (int i = lane + 64; i < cnt; i += 32) {
           const Sprite s = s_spr[(size_t)elx * cap + i];
           const uint32_t kind = (s.w >> 16) & 0xFF;
           if (kind == SK_INT) atomicAdd(&te[s.w & 0xFFFF], s.val);
-          else if (kind == SK_STORE) te[s.w & 0xFFFF] = s.val;
         }
         // fractional encodings last: value = (float)((double)integer_stack + encoding), one rounding like the reference
         const bool door_here = k0 == SK_DOOR || k1 == SK_DOOR || cnt > 64;
@@ -806,6 +826,62 @@ void build_vis_tables(const MfgSpec& sp, HostTables& t) {
     case 1: build_vis_tables_r<1>(sp, t); break;
     case 2: build_vis_tables_r<2>(sp, t); break;
     case 3: build_vis_tables_r<3>(sp, t); break;
+    default: break;
+  }
+}
+
+// window visibility table: vis_tab[tile][subset] = march(wall mask of the window | closed doors of the subset), for the (at most
+// 4) doors inside the tile's window; door_win[tile] names them.  Replaces the per-agent ray march of the tiled kernel by one
+// 8-byte load (the march stays as the fall-back for tiles whose window holds more than 4 doors).
+template <int R>
+static uint64_t march_host(uint64_t B) {
+  using T = RayTrie<R>;
+  constexpr int D = 2 * R + 1, centre = R * D + R;
+  uint64_t vis = 1ull << centre, cont = 0;
+  if (B & (1ull << centre)) return vis;
+  for (int n = 0; n < T::N; ++n) {
+    const int p = T::parent(n), c = T::cell(n), da = T::da(n), db = T::db(n);
+    const bool reach = p < 0 ? true : ((cont >> p) & 1ull) != 0;
+    const bool hits = (B >> c) & 1ull;
+    const bool diag = da != 255 && ((B >> da) & 1ull) && ((B >> db) & 1ull);
+    if (reach && !diag) vis |= 1ull << c;
+    if (reach && !hits && !diag) cont |= 1ull << n;
+  }
+  return vis;
+}
+template <int R>
+static void build_win_vis_r(const MfgSpec& sp, HostTables& t) {
+  constexpr int D = 2 * R + 1;
+  const int H = sp.H, W = sp.W;
+  for (int x = 0; x < H; ++x)
+    for (int y = 0; y < W; ++y) {
+      const size_t tile = (size_t)x * W + y;
+      int idx[4], cell[4], n = 0;
+      bool many = false;
+      for (int d = 0; d < sp.n_doors; ++d) {
+        const int dx = px(sp.door_pos[d]) - x + R, dy = py(sp.door_pos[d]) - y + R;
+        if (dx < 0 || dy < 0 || dx >= D || dy >= D) continue;
+        if (n == 4) { many = true; break; }
+        idx[n] = d; cell[n] = dx * D + dy; ++n;
+      }
+      if (many) { t.door_win[tile] = 7u << 24; continue; }
+      uint32_t rec = (uint32_t)n << 24;
+      for (int k = 0; k < n; ++k) rec |= (uint32_t)idx[k] << (6 * k);
+      t.door_win[tile] = rec;
+      for (int sub = 0; sub < (1 << n); ++sub) {
+        uint64_t B = t.wall_win[tile];
+        for (int k = 0; k < n; ++k) if ((sub >> k) & 1) B |= 1ull << cell[k];
+        t.vis_tab[tile * 16 + sub] = march_host<R>(B);
+      }
+    }
+}
+void build_win_vis_tables(const MfgSpec& sp, HostTables& t) {
+  t.door_win.assign((size_t)sp.H * sp.W, 7u << 24);
+  t.vis_tab.assign((size_t)sp.H * sp.W * 16, 0);
+  switch (sp.pomdp_r) {
+    case 1: build_win_vis_r<1>(sp, t); break;
+    case 2: build_win_vis_r<2>(sp, t); break;
+    case 3: build_win_vis_r<3>(sp, t); break;
     default: break;
   }
 }
