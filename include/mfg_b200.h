@@ -62,7 +62,9 @@ enum { MFG_CH_TERMS = 0, MFG_CH_ZERO, MFG_CH_BATTERY, MFG_CH_GLOBALPOS };
 /* rule opcodes (environment/rules.py, modules/<m>/rules.py) */
 enum { MFG_R_WATCH_COLLISIONS = 0, MFG_R_RESPAWN_DIRT, MFG_R_SMEAR_DIRT, MFG_R_DOOR_AUTO_CLOSE, MFG_R_DONE_ALL_DIRT,
        MFG_R_BATTERY_DECHARGE, MFG_R_DONE_BATTERY, MFG_R_DEST_REACH_REWARD, MFG_R_DONE_DEST, MFG_R_RESPAWN_ITEMS,
-       MFG_R_MOVE_MAINTAINERS, MFG_R_DONE_MAINT_COLLISION, MFG_R_DONE_MAX_STEPS };
+       MFG_R_MOVE_MAINTAINERS, MFG_R_DONE_MAINT_COLLISION, MFG_R_DONE_MAX_STEPS, MFG_R_RANDOM_INITIAL_STEPS };
+/* how Destinations are spawned (modules/destinations/rules.py:95-162) */
+enum { MFG_DEST_FREE = 0, MFG_DEST_ON_AGENT = 1, MFG_DEST_PER_AGENT = 2 };
 /* maintainer tape codes: 0..7 move direction (Move8 order), then */
 enum { MFG_MAINT_NOOP = 8, MFG_MAINT_DOORUSE = 9, MFG_MAINT_MACHINE = 10 };
 
@@ -113,6 +115,15 @@ typedef struct MfgSpec {
   int32_t ray_len[MFG_MAX_RAYS];
   int8_t ray_dx[MFG_MAX_RAYS][MFG_MAX_RAY_LEN];
   int8_t ray_dy[MFG_MAX_RAYS][MFG_MAX_RAY_LEN];
+  /* bound destinations: SpawnDestinationOnAgent / SpawnDestinationsPerAgent (modules/destinations/rules.py:95-162) */
+  int32_t dest_mode;                                       /* MFG_DEST_* */
+  int32_t random_initial_steps;                            /* DoRandomInitialSteps.random_steps (environment/rules.py:328-355), 0 = rule absent */
+  int32_t dest_bound[MFG_MAX_SMALL];                       /* agent a destination is bound to, or -1 */
+  int32_t dest_n_cand[MFG_MAX_SMALL];                      /* per-agent mode: candidate tiles (0 = any floor tile) */
+  uint16_t dest_cand[MFG_MAX_SMALL][MFG_MAX_FIXED];
+  /* BatteryDecharge.per_action_costs given as a dict (batteries/rules.py:50-63): cost by the class name of the action taken;
+   * used when rule_param[r][5] != 0, act_cost[a][n_actions[a]] = the 'Noop' entry (a paralysed agent's default state) */
+  double act_cost[MFG_MAX_AGENTS][MFG_MAX_ACTIONS + 1];
   /* level tables (host pointers) */
   const uint8_t* walls;           /* [H*W] 1 = wall */
   const uint16_t* floor_pos;      /* [n_floor] pos16, row-major */

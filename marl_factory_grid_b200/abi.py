@@ -54,6 +54,10 @@ class MfgSpec(C.Structure):
         ('group_n_fixed', C.c_int32 * MAX_GROUPS), ('group_fixed_pos', (C.c_uint16 * MAX_FIXED) * MAX_GROUPS),
         ('ray_len', C.c_int32 * MAX_RAYS), ('ray_dx', (C.c_int8 * MAX_RAY_LEN) * MAX_RAYS),
         ('ray_dy', (C.c_int8 * MAX_RAY_LEN) * MAX_RAYS),
+        ('dest_mode', C.c_int32), ('random_initial_steps', C.c_int32),
+        ('dest_bound', C.c_int32 * MAX_SMALL), ('dest_n_cand', C.c_int32 * MAX_SMALL),
+        ('dest_cand', (C.c_uint16 * MAX_FIXED) * MAX_SMALL),
+        ('act_cost', (C.c_double * (MAX_ACTIONS + 1)) * MAX_AGENTS),
         ('walls', C.c_void_p), ('floor_pos', C.c_void_p), ('door_pos', C.c_void_p), ('nexthop', C.c_void_p),
     ]
 
@@ -159,6 +163,20 @@ class PackedSpec:
                 s.group_n_fixed[g] = len(grp.coords)
                 for j, p in enumerate(grp.coords):
                     s.group_fixed_pos[g][j] = pos16(p)
+        s.dest_mode, s.random_initial_steps = es.dest_mode, es.random_initial_steps
+        for k in range(MAX_SMALL):
+            s.dest_bound[k] = -1
+        for k, b in enumerate(es.dest_bound):
+            s.dest_bound[k] = b
+        for k, cands in enumerate(es.dest_cands):
+            if len(cands) > MAX_FIXED:
+                raise ValueError(f'Destinations: more than {MAX_FIXED} candidate positions for one agent.')
+            s.dest_n_cand[k] = len(cands)
+            for j, pxy in enumerate(cands):
+                s.dest_cand[k][j] = pos16(pxy)
+        for i, costs in enumerate(es.act_costs):
+            for j, v in enumerate(costs):
+                s.act_cost[i][j] = float(v)
         # ray radius = min(observation shape): the window diameter for POMDP, min(H, W) for full observability
         # (observation_builder.py:244)
         rays = full_ray_table(min(es.obs_shape))

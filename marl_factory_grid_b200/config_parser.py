@@ -171,6 +171,7 @@ class FactoryConfigParser:
                      individual_rewards=bool(general.get('individual_rewards', False)),
                      agents=[], rules=[], groups=[], dirt_slots=int(dirt_slots))
 
+        self._pending_dest_rule = None
         # ---- Entities (yaml order = spawn order, config_parser.py:80-126 + level_parser.py:62-102)
         for gname, kwargs in (self.entities or {}).items():
             kwargs = dict(kwargs or {})
@@ -201,6 +202,13 @@ class FactoryConfigParser:
                     es.has_inventories = True
                 else:
                     es.has_globalpos = True
+            elif gname == 'Destinations' and kwargs.get('spawnrule'):
+                # a custom spawn rule replaces the group's SpawnEntity rule (groups/collection.py:70-80)
+                self._pending_dest_rule = dict(kwargs['spawnrule'])
+                if len(self._pending_dest_rule) != 1 or next(iter(self._pending_dest_rule)) not in (
+                        'SpawnDestinationOnAgent', 'SpawnDestinationsPerAgent'):
+                    raise NotImplementedError(f'Destinations.spawnrule {sorted(self._pending_dest_rule)} is not supported.')
+                es.n_dest = -1                                    # resolved once the agents are known
             elif gname in _QUANTITY_GROUPS:
                 q = kwargs.get('coords_or_quantity', None)
                 if isinstance(q, int) and not isinstance(q, bool):
@@ -238,6 +246,7 @@ class FactoryConfigParser:
                     raise ValueError(f'Agent {name}: position {pos} is not a floor tile of level {level_name}.')
             es.agents.append(AgentSpec(agent_names[idx], list(conf['actions']), channels, list(conf['positions']),
                                        bool(conf['other'].get('is_blocking_pos', False))))
+        self._compile_dest_spawnrule(es, list(parsed))
         self._check_actions_vs_groups(es)
 
         # ---- Rules (yaml order; config_parser.py:201-250)
@@ -259,7 +268,7 @@ class FactoryConfigParser:
             if name not in S.GROUP_NAMES:
                 raise ValueError(f'# No combination of "{name}" and "{me}" could be found in the observation sources.')
             present = {'Walls': True, 'Doors': es.has_doors, 'DirtPiles': es.has_dirt, 'Items': es.n_items > 0,
-                       'DropOffLocations': es.n_dropoff > 0, 'ChargePods': es.n_pods > 0, 'Destinations': es.n_dest > 0,
+                       'DropOffLocations': es.n_dropoff > 0, 'ChargePods': es.n_pods > 0, 'Destinations': es.n_dest != 0,
                        'Machines': es.n_machines > 0, 'Maintainers': es.n_maint > 0}[name]
             if not present:
                 raise ValueError(f'Observation "{name}" requested by {me} but "{name}" is not in Entities.')
@@ -298,6 +307,13 @@ class FactoryConfigParser:
                 if not es.has_globalpos:
                     raise ValueError(f'Observation "GlobalPosition" requested by {me} but "GlobalPositions" is missing.')
                 out.append(ChannelSpec(obs, S.CH_GLOBALPOS))
+            elif obs == 'Destination':
+                # the singular name resolves (by the bound-entity regex, observation_builder.py:176-185) to the agent's own
+                # bound Destination, which is positional => the plane is left untouched: always zeros [verified on the
+                # reference's eight_puzzle / narrow_corridor scenarios]
+                if es.n_dest == 0:
+                    raise ValueError(f'# No combination of "Destination" and "{me}" could be found in the observation sources.')
+                out.append(ChannelSpec(obs, S.CH_ZERO))
             elif obs == 'Inventory':
                 if not es.has_inventories:
                     raise ValueError(f'Observation "Inventory" requested by {me} but "Inventories" is not in Entities.')
@@ -305,6 +321,44 @@ class FactoryConfigParser:
             else:
                 out.append(ChannelSpec(obs, S.CH_TERMS, [group_term(obs)]))
         return out
+
+    def _compile_dest_spawnrule(self, es: EnvSpec, conf_names: List[str]):
+        """SpawnDestinationOnAgent / SpawnDestinationsPerAgent (modules/destinations/rules.py:95-162): one destination per agent
+        (resp. per dict entry), bound to that agent."""
+        rule = self._pending_dest_rule
+        es.dest_bound = [-1] * es.n_dest
+        if not rule:
+            return
+        name, kw = next(iter(rule.items()))
+        kw = dict(kw or {})
+        if name == 'SpawnDestinationOnAgent':
+            if kw:
+                raise TypeError(f'SpawnDestinationOnAgent.__init__() got unexpected keyword argument(s) {sorted(kw)}.')
+            es.dest_mode = S.DEST_ON_AGENT
+            es.n_dest = es.n_agents
+            es.dest_bound = list(range(es.n_agents))
+            es.dest_cands = [[] for _ in range(es.n_agents)]
+        else:
+            per_agent = kw.pop('coords_or_quantity', None)
+            if kw or not isinstance(per_agent, dict) or not per_agent:
+                raise TypeError('SpawnDestinationsPerAgent needs coords_or_quantity: {agent name: [coordinates] | int}.')
+            es.dest_mode = S.DEST_PER_AGENT
+            es.dest_bound, es.dest_cands = [], []
+            for agent_name, value in per_agent.items():
+                # `h.get_first(state[c.AGENT], lambda x: agent_name in x.name)`: first agent whose name contains the key
+                idx = next((i for i, a in enumerate(es.agents) if str(agent_name) in a.name), None)
+                if idx is None:
+                    raise AssertionError(f'SpawnDestinationsPerAgent: no agent matches "{agent_name}".')
+                es.dest_bound.append(idx)
+                if isinstance(value, int):
+                    es.dest_cands.append([])                      # any floor tile (one destination, rules.py:127-143)
+                else:
+                    es.dest_cands.append([tuple(ast.literal_eval(x)) if isinstance(x, str) else tuple(x) for x in value])
+            es.n_dest = len(es.dest_bound)
+        if es.n_dest > S.MAX_SMALL_GROUP:
+            raise ValueError(f'Entities.Destinations: {es.n_dest} exceeds the supported maximum {S.MAX_SMALL_GROUP}.')
+        g = es.group('Destinations')
+        g.quantity = es.n_dest
 
     @staticmethod
     def _check_actions_vs_groups(es: EnvSpec):
@@ -358,8 +412,18 @@ class FactoryConfigParser:
             take('battery_failed_reward', -0.1)
             pac = take('per_action_costs', 0.02)
             if isinstance(pac, dict):
-                raise NotImplementedError(f'{name}.per_action_costs as a per-action dict is not supported.')
-            p[0] = float(pac)
+                # cost by the class name of the action the agent took this tick (batteries/rules.py:55-58); a paralysed agent's
+                # default state is a valid 'Noop' (entity.py:19).  A missing name is a KeyError at the first tick there.
+                es.act_costs = []
+                for ag in es.agents:
+                    names = [a.class_name for a in ag.actions] + ['Noop']
+                    missing = [n for n in names if n not in pac]
+                    if missing:
+                        raise KeyError(f'{name}.per_action_costs has no entry for {missing[0]!r} ({ag.name}).')
+                    es.act_costs.append([float(pac[n]) for n in names])
+                p[5] = 1.0
+            else:
+                p[0] = float(pac)
             p[1] = float(take('battery_discharge_reward', -1.0))
             p[2] = float(bool(take('paralyze_agents_on_discharge', False)))
             if op == S.R_DONE_BATTERY:
@@ -384,6 +448,11 @@ class FactoryConfigParser:
             _require(es.n_maint > 0 and es.n_machines > 0 and es.has_doors, name, 'Maintainers + Machines + Doors')
         elif op == S.R_DONE_MAINT_COLLISION:
             _require(es.n_maint > 0, name, 'Maintainers')
+        elif op == S.R_RANDOM_INITIAL_STEPS:    # environment/rules.py:328-355
+            if 'random_steps' not in kw:
+                raise TypeError("DoRandomInitialSteps.__init__() missing 1 required positional argument: 'random_steps'")
+            es.random_initial_steps = int(take('random_steps', 0))
+            p[0] = float(es.random_initial_steps)
         elif op == S.R_DONE_MAX_STEPS:          # environment/rules.py:204
             p[0] = float(int(take('max_steps', 500)))
             if not 0 <= p[0] <= 65535:

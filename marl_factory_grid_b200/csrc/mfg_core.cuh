@@ -218,6 +218,8 @@ struct HotSpec {
   double act_aux[AMAX][MFG_MAX_ACTIONS];
   int32_t rule_op[MFG_MAX_RULES];
   double rule_param[MFG_MAX_RULES][MFG_RULE_NPARAM];
+  int8_t dest_bound[MFG_MAX_SMALL];
+  double act_cost[AMAX][MFG_MAX_ACTIONS + 1];
 };
 
 template <int AMAX>
@@ -239,7 +241,9 @@ inline void fill_hot_spec(const MfgSpec& s, HotSpec<AMAX>& h) {
       h.act_fail[i][a] = in ? s.act_fail[i][a] : 0.0;
       h.act_aux[i][a] = in ? s.act_aux[i][a] : 0.0;
     }
+    for (int a = 0; a <= MFG_MAX_ACTIONS; ++a) h.act_cost[i][a] = in ? s.act_cost[i][a] : 0.0;
   }
+  for (int k = 0; k < MFG_MAX_SMALL; ++k) h.dest_bound[k] = (int8_t)s.dest_bound[k];
   for (int r = 0; r < MFG_MAX_RULES; ++r) {
     h.rule_op[r] = s.rule_op[r];
     for (int k = 0; k < MFG_RULE_NPARAM; ++k) h.rule_param[r][k] = s.rule_param[r][k];
@@ -609,6 +613,40 @@ MFG_HD void env_reset_inl(const MfgSpec& sp, const Tables& tb, const State& st, 
       for (int j = 0; j < qa; ++j) amounts[j] = sp.dirt_initial_amount + rng.uniform(-sp.dirt_amount_var, sp.dirt_amount_var);
       int n = got < qa ? got : qa;
       v.dirt_spawn(n, [&](int j) { return chosen[j]; }, [&](int j) { return amounts[j]; });
+    } else if (gid == MFG_SP_DEST && sp.dest_mode != MFG_DEST_FREE) {
+      // bound destinations (modules/destinations/rules.py:95-162): one per agent / per dict entry
+      for (int k = 0; k < sp.n_dest; ++k) {
+        const int ag = sp.dest_bound[k];
+        uint16_t p = NO_POS;
+        if (sp.dest_mode == MFG_DEST_ON_AGENT) {
+          p = v.apos[ag];                                   // "just below him": the agent's own tile
+        } else {
+          // shuffled candidate list, first tile that is not the agent's and holds no destination yet == a uniform draw
+          // among the valid candidates
+          const int nc = sp.dest_n_cand[k] > 0 ? sp.dest_n_cand[k] : sp.n_floor;
+          uint16_t valid[MFG_MAX_FIXED];
+          int nv = 0;
+          if (sp.dest_n_cand[k] > 0) {
+            for (int j = 0; j < nc; ++j) {
+              const uint16_t q = sp.dest_cand[k][j];
+              bool ok = q != v.apos[ag];
+              for (int m = 0; ok && m < k; ++m) ok = v.at(st.dest_pos, m) != q;
+              if (ok) valid[nv++] = q;
+            }
+            if (nv) p = valid[rng.below((uint32_t)nv)];
+          } else {
+            for (int attempt = 0; attempt < 64 + 16 * sp.n_floor && p == NO_POS; ++attempt) {
+              const uint16_t q = tb.floor_pos[rng.below((uint32_t)sp.n_floor)];
+              bool ok = q != v.apos[ag];
+              for (int m = 0; ok && m < k; ++m) ok = v.at(st.dest_pos, m) != q;
+              if (ok) p = q;
+            }
+          }
+        }
+        if (p == NO_POS) { stat_add(tb, MFG_ST_SPAWN_FAIL, 1); continue; }        // the reference exits here
+        v.at(st.dest_pos, k) = p;
+        v.l_add(C_DEST, k, k, p);
+      }
     } else if (gid == MFG_SP_PODS || gid == MFG_SP_DEST || gid == MFG_SP_ITEMS || gid == MFG_SP_DROPOFF ||
                gid == MFG_SP_MACHINES || gid == MFG_SP_MAINT) {
       int c = gid == MFG_SP_PODS ? C_POD : gid == MFG_SP_DEST ? C_DEST : gid == MFG_SP_ITEMS ? C_ITEM
@@ -626,6 +664,34 @@ MFG_HD void env_reset_inl(const MfgSpec& sp, const Tables& tb, const State& st, 
         v.l_add(c, j, j, chosen[j]);
       }
     }
+  }
+  // ---- DoRandomInitialSteps.on_reset_post_spawn (environment/rules.py:341-355): a random free tile, one of its 4 floor
+  // neighbours, the first agent standing there moves onto the free tile
+  if (sp.random_initial_steps > 0) {
+    uint32_t clock = v.at(st.clock, 0);
+    for (int it = 0; it < sp.random_initial_steps; ++it) {
+      const uint16_t fp = v.sample_free(rng, nullptr, 0, false);
+      if (fp == NO_POS) break;
+      uint16_t nb[4];
+      int nn = 0;
+      for (int d = 0; d < 4; ++d) {                         // POS_MASK_4, restricted to floor tiles
+        const int x = px(fp) + dir_dx(d), y = py(fp) + dir_dy(d);
+        if (v.in_grid(x, y) && !v.tbl(tb.wall, x * sp.W + y)) nb[nn++] = mkpos(x, y);
+      }
+      if (!nn) continue;
+      const uint16_t from = nb[rng.below((uint32_t)nn)];
+      int who = -1;
+      uint32_t best = 0;
+      for (int i = 0; i < A; ++i)                           // Agents.by_pos: the agent that arrived first
+        if (v.apos[i] == from) { const uint32_t s2 = v.at(st.astamp, i); if (who < 0 || s2 < best) { who = i; best = s2; } }
+      if (who < 0) continue;                                // (the reference asserts an agent stands there)
+      // Entity.move re-validates against the live state (entity.py:175-199)
+      const int x = px(fp), y = py(fp);
+      if (v.blocked(x, y) || (sp.agent_blocking[who] && v.n_coll(x, y) >= 1)) continue;
+      v.apos[who] = fp;
+      v.at(st.astamp, who) = clock++;
+    }
+    v.at(st.clock, 0) = clock;
   }
   v.store();
 }
@@ -704,8 +770,10 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
   // front with independent loads (one round trip instead of a dependent one per use) and keep them in registers.
   double bat[AMAX], epr[AMAX];
   int act[AMAX];
+  bool skipped[AMAX];
 #pragma unroll
   for (int i = 0; i < AMAX; ++i) {
+    skipped[i] = false;
     bat[i] = (i < A && sp.has_batteries) ? v.at(st.bat, i) : 1.0;
     epr[i] = i < A ? v.at(st.ep_ret, i) : 0.0;
     act[i] = i < A ? io.actions[(size_t)e * A + i] : 0;
@@ -715,7 +783,7 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
 #pragma unroll
   for (int i = 0; i < AMAX; ++i) {
     if (i >= A) break;
-    if (v.at(st.aflag, i) & 1) continue;                       // paralysed: skipped entirely
+    if (v.at(st.aflag, i) & 1) { skipped[i] = true; continue; }      // paralysed: skipped entirely
     int a = act[i];
     if (a < 0 || a >= sp.n_actions[i]) a = 0;
     const int op = sp.act_opcode[i][a];
@@ -864,7 +932,14 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
     } else if (op == MFG_R_BATTERY_DECHARGE || op == MFG_R_DONE_BATTERY) {   // batteries/rules.py:50-63
 #pragma unroll
       for (int i = 0; i < AMAX; ++i) {
-        if (i < A && bat[i] != 0) bat[i] = fmax(0.0, P[0] + bat[i]);
+        if (i >= A) continue;
+        double cost = P[0];
+        if (P[5] != 0) {                      // per_action_costs as a dict: keyed by the class of the action taken this tick
+          int a = act[i];
+          if (a < 0 || a >= sp.n_actions[i]) a = 0;
+          cost = sp.act_cost[i][skipped[i] ? sp.n_actions[i] : a];          // a paralysed agent's default state is a 'Noop'
+        }
+        if (bat[i] != 0) bat[i] = fmax(0.0, cost + bat[i]);
       }
     } else if (op == MFG_R_DEST_REACH_REWARD || op == MFG_R_DONE_DEST) {     // destinations/rules.py:34-54
       uint32_t reached = v.at(st.dest_reached, 0);
@@ -879,6 +954,15 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
             uint32_t s = v.at(st.astamp, i);
             if (last < 0 || s > best) { last = i; best = s; }
           }
+        }
+        // a bound destination (SpawnDestinationsPerAgent / OnAgent) is only reached by its own agent; the reward still goes
+        // to the last agent listed on the tile (the loop variable of destinations/rules.py:40-50)
+        const int bound = sp.dest_bound[k];
+        if (last >= 0 && bound >= 0) {
+          bool there = false;
+#pragma unroll
+          for (int i = 0; i < AMAX; ++i) there |= i < A && i == bound && v.apos[i] == q;
+          if (!there) last = -1;
         }
         if (last >= 0) {
           reached |= 1u << k;

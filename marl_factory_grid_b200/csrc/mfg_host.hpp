@@ -178,6 +178,12 @@ inline std::string validate_spec(const MfgSpec& sp) {
   }
   for (int r = 0; r < sp.n_rays; ++r) if (sp.ray_len[r] < 1 || sp.ray_len[r] > MFG_MAX_RAY_LEN) return "ray_len out of range";
   if (sp.n_floor < sp.n_agents) return "fewer floor tiles than agents";
+  if (sp.dest_mode < MFG_DEST_FREE || sp.dest_mode > MFG_DEST_PER_AGENT) return "dest_mode out of range";
+  for (int k = 0; k < sp.n_dest; ++k) {
+    if (sp.dest_bound[k] < -1 || sp.dest_bound[k] >= sp.n_agents) return "dest_bound out of range";
+    if (sp.dest_mode != MFG_DEST_FREE && sp.dest_bound[k] < 0) return "bound destination spawn modes need dest_bound";
+    if (sp.dest_n_cand[k] < 0 || sp.dest_n_cand[k] > MFG_MAX_FIXED) return "dest_n_cand out of range";
+  }
   for (int r = 0; r < sp.n_rules; ++r)
     if (sp.rule_op[r] == MFG_R_DONE_MAX_STEPS && !(sp.rule_param[r][0] >= 0 && sp.rule_param[r][0] <= 65535))
       return "DoneAtMaxStepsReached.max_steps must be within 0..65535 (16-bit step counter)";

@@ -54,7 +54,7 @@ CH_TERMS, CH_ZERO, CH_BATTERY, CH_GLOBALPOS = range(4)
 # ---------------------------------------------------------------------------------------------
 (R_WATCH_COLLISIONS, R_RESPAWN_DIRT, R_SMEAR_DIRT, R_DOOR_AUTO_CLOSE, R_DONE_ALL_DIRT, R_BATTERY_DECHARGE,
  R_DONE_BATTERY, R_DEST_REACH_REWARD, R_DONE_DEST, R_RESPAWN_ITEMS, R_MOVE_MAINTAINERS, R_DONE_MAINT_COLLISION,
- R_DONE_MAX_STEPS) = range(13)
+ R_DONE_MAX_STEPS, R_RANDOM_INITIAL_STEPS) = range(14)
 RULE_NAMES = {
     'WatchCollisions': R_WATCH_COLLISIONS, 'RespawnDirt': R_RESPAWN_DIRT, 'EntitiesSmearDirtOnMove': R_SMEAR_DIRT,
     'DoorAutoClose': R_DOOR_AUTO_CLOSE, 'DoneOnAllDirtCleaned': R_DONE_ALL_DIRT,
@@ -62,7 +62,10 @@ RULE_NAMES = {
     'DestinationReachReward': R_DEST_REACH_REWARD, 'DoneAtDestinationReach': R_DONE_DEST,
     'RespawnItems': R_RESPAWN_ITEMS, 'MoveMaintainers': R_MOVE_MAINTAINERS,
     'DoneAtMaintainerCollision': R_DONE_MAINT_COLLISION, 'DoneAtMaxStepsReached': R_DONE_MAX_STEPS,
+    'DoRandomInitialSteps': R_RANDOM_INITIAL_STEPS,
 }
+# how Destinations are spawned (modules/destinations/rules.py:95-162)
+DEST_FREE, DEST_ON_AGENT, DEST_PER_AGENT = range(3)
 RULE_NPARAM = 6                 # f64 parameters per rule entry (meaning depends on the opcode)
 
 # capacities shared with the kernels (include/mfg_b200.h)
@@ -159,6 +162,12 @@ class EnvSpec:
     n_dest: int = 0
     n_machines: int = 0
     n_maint: int = 0
+    # bound destinations (SpawnDestinationOnAgent / SpawnDestinationsPerAgent) and DoRandomInitialSteps
+    dest_mode: int = 0
+    dest_bound: List[int] = field(default_factory=list)                     # agent index per destination (-1: unbound)
+    dest_cands: List[List[Tuple[int, int]]] = field(default_factory=list)   # per-agent mode: candidate tiles ([] = any floor tile)
+    random_initial_steps: int = 0
+    act_costs: List[List[float]] = field(default_factory=list)              # BatteryDecharge.per_action_costs as a dict
 
     # ------------------------------------------------------------------ derived helpers
     @property

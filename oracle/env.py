@@ -182,9 +182,11 @@ class OracleEnv:
         glob = 0.0
 
         # ---- agents act sequentially against the live state (states.py:189-198)
+        acted = [None] * A                      # index of the action each agent took this tick (None: paralysed, skipped)
         for i in range(A):
             if self.paralysed[i]:
                 continue
+            acted[i] = int(actions[i])
             act = sp.agents[i].actions[int(actions[i])]
             p = self.apos[i]
             op = act.opcode
@@ -268,12 +270,19 @@ class OracleEnv:
                     self.dirt_next_spawn -= 1
             elif op in (S.R_BATTERY_DECHARGE, S.R_DONE_BATTERY):    # batteries/rules.py:50-63, entitites.py:60-69
                 for i in range(A):
+                    cost = P[0]
+                    if P[5]:        # per_action_costs as a dict: class name of the action taken; a skipped (paralysed) agent: 'Noop'
+                        costs = sp.act_costs[i]
+                        cost = costs[-1] if acted[i] is None else costs[acted[i]]
                     if self.bat[i] != 0:
-                        self.bat[i] = max(0, P[0] + self.bat[i])
+                        self.bat[i] = max(0, cost + self.bat[i])
             elif op in (S.R_DEST_REACH_REWARD, S.R_DONE_DEST):      # destinations/rules.py:34-54
-                for d in self.dests:
+                for k, d in enumerate(self.dests):
                     if not d.reached:
                         here = [i for i in range(A) if self.apos[i] == d.pos]
+                        bound = sp.dest_bound[k] if k < len(sp.dest_bound) else -1
+                        if here and bound >= 0 and bound not in here:
+                            here = []           # a bound destination is only reached by its own agent (rules.py:40-47)
                         if here:
                             d.reached = True
                             last = max(here, key=lambda i: self.stamp[i])   # last in Agents.pos_dict list order

@@ -84,6 +84,21 @@ class FreeRunEnv(OracleEnv):
                 amounts = [sp.dirt_initial_amount + self.rng.uniform(-sp.dirt_amount_var, sp.dirt_amount_var)
                            for _ in range(q)]
                 self.dirt_spawn(tiles, amounts)
+            elif g.name == 'Destinations' and sp.dest_mode != S.DEST_FREE:
+                # bound destinations (modules/destinations/rules.py:95-162)
+                for k in range(sp.n_dest):
+                    ag = sp.dest_bound[k]
+                    if sp.dest_mode == S.DEST_ON_AGENT:
+                        p = self.apos[ag]
+                    else:
+                        cands = [tuple(c) for c in sp.dest_cands[k]] or list(self.floor)
+                        cands = [c for c in cands if c != self.apos[ag] and all(d.pos != c for d in self.dests)]
+                        if not cands:
+                            raise SystemExit(f'Could not spawn Destinations at: {sp.dest_cands[k]}')
+                        p = cands[int(self.rng.integers(len(cands)))]
+                    e = Ent('dest', k, p)
+                    self.dests.append(e)
+                    self.l_add(e)
             elif g.name in lists:
                 cls, lst = lists[g.name]
                 tiles = [tuple(c) for c in g.coords] if g.coords else self.n_free(g.quantity)
@@ -92,6 +107,26 @@ class FreeRunEnv(OracleEnv):
                     lst.append(e)
                     self.l_add(e)
         self._maint_state = [dict(path_target=None, nxt=[], last_serviced=None) for _ in self.maints]
+        # DoRandomInitialSteps.on_reset_post_spawn (environment/rules.py:341-355)
+        for _ in range(sp.random_initial_steps):
+            free = self.n_free(1)
+            if not free:
+                break
+            fp = free[0]
+            nbs = [(fp[0] + dx, fp[1] + dy) for dx, dy in S.DIR_DELTA[:4]]
+            nbs = [q for q in nbs if self.in_grid(q) and not self.wall[q]]
+            if not nbs:
+                continue
+            frm = nbs[int(self.rng.integers(len(nbs)))]
+            here = [i for i in range(self.A) if self.apos[i] == frm]
+            if not here:
+                continue                        # (the reference asserts an agent stands there)
+            who = min(here, key=lambda i: self.stamp[i])
+            if self.blocked(fp) or (sp.agents[who].is_blocking_pos and self.n_coll(fp) >= 1):
+                continue
+            self.apos[who] = fp
+            self.stamp[who] = self.clock
+            self.clock += 1
         return self.observe()
 
     # ------------------------------------------------------------------ maintainer policy

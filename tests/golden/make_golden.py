@@ -236,6 +236,10 @@ PLAN = {
     'stress3': [(s, 'U', 120) for s in range(6)] + [(s, 'I', 120) for s in range(6, 8)],
     'dest_all': [(s, 'U', 400) for s in range(3)] + [(3, 'I', 400)],
     'dest_simul': [(s, 'U', 600) for s in range(3)] + [(3, 'I', 600)],
+    # the reference's shipped full-observability scenarios: bound destinations, DoRandomInitialSteps, blocking agents
+    'eight_puzzle': [(s, 'U', 200) for s in range(4)] + [(4, 'I', 100)],
+    'narrow_corridor': [(s, 'U', 200) for s in range(3)] + [(3, 'I', 100)],
+    'stress4': [(s, 'U', 120) for s in range(3)] + [(3, 'I', 120)],          # dict per_action_costs
 }
 
 

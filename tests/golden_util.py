@@ -11,8 +11,8 @@ ROOT = Path(__file__).resolve().parent.parent
 GOLDEN = ROOT / 'tests' / 'golden'
 CONFIGS = ROOT / 'marl_factory_grid_b200' / 'configs'
 ALL_CFGS = ['cfg1', 'cfg2', 'cfg3', 'cfg4', 'stress', 'stress2', 'default_config', 'clean_and_bring', 'stress3', 'dest_all',
-            'dest_simul']      # POMDP configs: oracle, direct AND tiled observation kernels
-FULL_OBS_CFGS = ['obs_test']                                          # pomdp_r = 0 (full observability): oracle and the direct kernel
+            'dest_simul', 'stress4']      # POMDP configs: oracle, direct AND tiled observation kernels
+FULL_OBS_CFGS = ['obs_test', 'eight_puzzle', 'narrow_corridor']                                          # pomdp_r = 0 (full observability): oracle and the direct kernel
 ORACLE_ONLY_CFGS = []
 
 SNAP_KEYS = ['agent_pos', 'door_open', 'door_timer', 'door_listed', 'dirt_n', 'dirt_pos', 'dirt_amt', 'dirt_uid',

@@ -113,7 +113,7 @@ def test_replay_full_observability(cfg, mode):
     _replay_batch(cfg, mode, obs_kernels=[0])
 
 
-@pytest.mark.parametrize('cfg', ['cfg1', 'cfg2', 'cfg3', 'cfg4', 'stress2'])
+@pytest.mark.parametrize('cfg', ['cfg1', 'cfg2', 'cfg3', 'cfg4', 'stress2', 'eight_puzzle', 'narrow_corridor', 'stress4'])
 @pytest.mark.parametrize('faithful', [False, True])
 def test_freerun_matches_host_build_of_device_code(cfg, faithful):
     """Free-running (Philox spawn, dirt respawn, maintainer policy, in-kernel auto reset): the CUDA kernels and the

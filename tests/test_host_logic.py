@@ -46,7 +46,7 @@ def test_engine_fails_loudly_without_cuda():
 
 
 @pytest.mark.parametrize('cfg', ['cfg1', 'cfg2', 'cfg3', 'cfg4', 'stress', 'stress2', 'default_config', 'clean_and_bring',
-                                 'stress3', 'dest_all', 'dest_simul', 'obs_test'])
+                                 'stress3', 'dest_all', 'dest_simul', 'obs_test', 'eight_puzzle', 'narrow_corridor', 'stress4'])
 def test_named_spaces_equal_the_reference(cfg):
     """Agent names, named action space, action counts and the per-agent observation layer names recorded from the
     reference's own `Factory` (meta of the golden traces) == what the config compiler derives (no GPU needed)."""
@@ -137,7 +137,7 @@ def test_algorithmic_bytes_match_survey_8d():
     assert [spec_for(c).algorithmic_bytes_per_env_step() for c in ('cfg1', 'cfg2', 'cfg3', 'cfg4')] == [1225, 2427, 4097, 8105]
 
 
-@pytest.mark.parametrize('cfg', ['cfg1', 'cfg2', 'cfg3', 'cfg4', 'stress', 'stress2'])
+@pytest.mark.parametrize('cfg', ['cfg1', 'cfg2', 'cfg3', 'cfg4', 'stress', 'stress2', 'narrow_corridor', 'stress4'])
 def test_freerun_invariants_host_build(cfg):
     """Philox spawn + free-running rules on the host build of the device code: structural invariants of the
     reference (SURVEY.md §4 iii) hold on every step, for a batch that auto-resets."""
@@ -160,7 +160,8 @@ def test_freerun_invariants_host_build(cfg):
             assert s['dirt_n'] in (es.dirt_quantity - 1, es.dirt_quantity)
             amt = s['dirt_amt'][:s['dirt_n']]
             assert np.all(np.abs(amt - es.dirt_initial_amount) <= es.dirt_amount_var + 1e-12)
-    assert len({tuple(map(tuple, s['agent_pos'])) for s in snap0}) > N // 2                       # envs differ
+    if not all(a.positions for a in es.agents):              # (fixed start positions: every env starts the same)
+        assert len({tuple(map(tuple, s['agent_pos'])) for s in snap0}) > N // 2                   # envs differ
     n_act = es.n_actions
     for t in range(120):
         a = np.stack([rng.integers(0, n, N) for n in n_act], 1).astype(np.int32)
@@ -238,3 +239,32 @@ def test_limits_are_rejected_not_wrapped(tmp_path):
     env.reset()
     with pytest.raises(TypeError):
         env.step_free([0] * es.n_agents)
+
+
+def test_bound_destination_spawn_rules_host_build():
+    """SpawnDestinationOnAgent + DoRandomInitialSteps (eight_puzzle) and SpawnDestinationsPerAgent (narrow_corridor) in the
+    Philox spawn of the device code: destinations are bound one per agent; eight_puzzle keeps its single free tile and at most
+    `random_steps` agents have left their destination; narrow_corridor puts every destination on the candidate tile that is not
+    the agent's own (modules/destinations/rules.py:95-162, environment/rules.py:328-355)."""
+    from hostsim_util import HostSim
+    es = spec_for('eight_puzzle')
+    assert es.dest_mode == 1 and es.dest_bound == list(range(8)) and es.random_initial_steps == 2
+    sim = HostSim(es, 64, faithful=True, seed=9)
+    sim.reset()
+    moved_hist = np.zeros(4, int)
+    for e in range(64):
+        s = sim.snapshot(e)
+        apos, dpos = [tuple(p) for p in s['agent_pos']], [tuple(p) for p in s['dest_pos']]
+        assert len(set(apos)) == 8 and len(set(dpos)) == 8
+        moved = sum(a != d for a, d in zip(apos, dpos))
+        assert moved <= 2
+        moved_hist[moved] += 1
+    assert moved_hist[1] + moved_hist[2] > 0                  # the random initial steps do move agents
+    es = spec_for('narrow_corridor')
+    assert es.dest_mode == 2 and es.dest_bound == [0, 1]
+    sim = HostSim(es, 32, faithful=True, seed=9)
+    sim.reset()
+    for e in range(32):
+        s = sim.snapshot(e)
+        apos, dpos = [tuple(p) for p in s['agent_pos']], [tuple(p) for p in s['dest_pos']]
+        assert apos == [(2, 1), (2, 5)] and dpos == [(2, 5), (2, 1)]
