@@ -68,6 +68,12 @@ enum { MFG_DEST_FREE = 0, MFG_DEST_ON_AGENT = 1, MFG_DEST_PER_AGENT = 2 };
 /* maintainer tape codes: 0..7 move direction (Move8 order), then */
 enum { MFG_MAINT_NOOP = 8, MFG_MAINT_DOORUSE = 9, MFG_MAINT_MACHINE = 10 };
 
+/* per-agent result bits of one step (mfg_bind_step_flags): what the reference reports through `info` / `agent.state`
+ * (utils/results.py:42-52, factory.py:222-239): the action was valid, the agent was paralysed and skipped, the agent stands on a
+ * collision tile (WatchCollisions), the agent's move "introduced a collision" (actions.py:80-96: it failed, or ended on a tile
+ * shared with another collidable entity), the action paid its auxiliary reward (ItemAction on a drop-off, items/actions.py:41-63) */
+enum { MFG_FLAG_VALID = 1, MFG_FLAG_SKIPPED = 2, MFG_FLAG_COLLISION = 4, MFG_FLAG_MOVE_COLLISION = 8, MFG_FLAG_AUX_REWARD = 16 };
+
 /* indices into the statistics vector returned by mfg_stats (int64 counters, doubles bit-cast for sums) */
 enum { MFG_ST_EPISODES = 0, MFG_ST_STEPS, MFG_ST_DONE_MAX_STEPS, MFG_ST_DONE_ALL_DIRT, MFG_ST_DONE_BATTERY,
        MFG_ST_DONE_DEST, MFG_ST_DONE_MAINT, MFG_ST_DONE_COLLISION, MFG_ST_COLLISIONS, MFG_ST_DIRT_OVERFLOW,
@@ -178,6 +184,10 @@ int mfg_random_actions(MfgHandle* h, int32_t* d_actions, uint64_t seed, uint64_t
 /* Host-buffer convenience path (what a caller holding numpy arrays uses): H2D actions, step+observe, D2H results. */
 int mfg_step_host(MfgHandle* h, const int32_t* h_actions, float* h_reward, uint8_t* h_done, float* h_obs,
                   int auto_reset, void* stream);
+/* Optional per-step result flags: d_flags [N][A + 1] uint8, written by every following mfg_step / mfg_step_observe: per agent the
+ * MFG_FLAG_* bits, then the done reason of the env (0 = not done, else the MFG_ST_DONE_* index of the first rule that fired,
+ * 255 = other).  NULL switches the output off (default).  This is the batched form of the reference's per-step `info` dict. */
+int mfg_bind_step_flags(MfgHandle* h, uint8_t* d_flags);
 /* copies the MFG_N_STATS int64 statistics vector (device) into d_out; zero_after != 0 clears it afterwards */
 int mfg_stats(MfgHandle* h, int64_t* d_out, int zero_after, void* stream);
 /* options: "obs_kernel" (0 auto, 1 direct per-agent kernel, 2 tiled shared-memory kernel), "obs_store" (1 TMA bulk store),

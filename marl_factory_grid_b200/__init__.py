@@ -12,7 +12,7 @@ from .config_parser import FactoryConfigParser, named_action_space  # noqa: F401
 from .level_parser import LevelParser  # noqa: F401
 from .spec import EnvSpec  # noqa: F401
 
-__all__ = ['Factory', 'EnvMonitor', 'FactoryConfigParser', 'LevelParser', 'EnvSpec', 'named_action_space']
+__all__ = ['Factory', 'EnvMonitor', 'EnvRecorder', 'FactoryConfigParser', 'LevelParser', 'EnvSpec', 'named_action_space']
 
 
 def __getattr__(name):
@@ -22,4 +22,7 @@ def __getattr__(name):
     if name == 'EnvMonitor':
         from .monitor import EnvMonitor
         return EnvMonitor
+    if name == 'EnvRecorder':
+        from .monitor import EnvRecorder
+        return EnvRecorder
     raise AttributeError(name)

@@ -29,6 +29,9 @@ ST_EPISODES, ST_STEPS, ST_DONE_MAX_STEPS, ST_DONE_ALL_DIRT, ST_DONE_BATTERY, ST_
     ST_DONE_COLLISION, ST_COLLISIONS, ST_DIRT_OVERFLOW, ST_SPAWN_FAIL, ST_RETURN_SUM, ST_RETURN_AGENT0 = range(13)
 
 
+FLAG_VALID, FLAG_SKIPPED, FLAG_COLLISION, FLAG_MOVE_COLLISION, FLAG_AUX_REWARD = 1, 2, 4, 8, 16        # MFG_FLAG_* (mfg_bind_step_flags)
+
+
 class MfgSpec(C.Structure):
     _fields_ = [
         ('H', C.c_int32), ('W', C.c_int32), ('pomdp_r', C.c_int32), ('n_agents', C.c_int32),

@@ -171,7 +171,7 @@ static int step_impl(MfgHandle* h, const int32_t* d_actions, const MfgTape* tape
   const bool defer = auto_reset && h->defer_reset;
   StepIO io{d_actions, tape ? tape->d_maint_action : nullptr, tape ? tape->d_respawn_n : nullptr,
             tape ? tape->d_respawn_pos : nullptr, d_reward, d_done, auto_reset,
-            defer ? h->d_reset_list : nullptr, defer ? h->d_reset_count : nullptr};
+            defer ? h->d_reset_list : nullptr, defer ? h->d_reset_count : nullptr, h->d_flags};
   bool need_policy = false;
   for (int r = 0; r < h->sp.n_rules; ++r) need_policy |= h->sp.rule_op[r] == MFG_R_MOVE_MAINTAINERS;
   if (need_policy && !io.maint_act && !h->tb.nexthop)
@@ -281,6 +281,12 @@ int mfg_step_host(MfgHandle* h, const int32_t* h_actions, float* h_reward, uint8
   CUDA_TRY(cudaMemcpyAsync(h_done, h->d_done, (size_t)h->N, cudaMemcpyDeviceToHost, s));
   if (h_obs) CUDA_TRY(cudaMemcpyAsync(h_obs, h->d_obs, obs_bytes, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
+  return MFG_OK;
+}
+
+int mfg_bind_step_flags(MfgHandle* h, uint8_t* d_flags) {
+  if (!h) return fail(MFG_E_INVALID, "mfg_bind_step_flags: bad arguments");
+  h->d_flags = d_flags;
   return MFG_OK;
 }
 

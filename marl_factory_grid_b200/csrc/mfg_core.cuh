@@ -709,6 +709,7 @@ struct StepIO {
   int auto_reset;             // 0 = never, 1 = re-spawn finished envs (inline, or deferred when reset_list is set)
   uint32_t* reset_list;       // deferred reset: finished env ids are appended here and re-spawned by k_reset_list, packed
   uint32_t* reset_count;      //                 (an in-line reset makes almost every warp run the long spawn path for 1-2 lanes)
+  uint8_t* flags;             // optional [N][A + 1]: per agent MFG_FLAG_* bits of this step, then the done reason (0 = not done)
 };
 
 // maintainer policy when no tape is given (maintenance/entities.py:37-136), next hop from the BFS table
@@ -766,6 +767,7 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
 #pragma unroll
   for (int i = 0; i < AMAX; ++i) rew[i] = 0.0;
   double glob = 0.0;
+  uint32_t okmask = 0u, collmask = 0u, mcollmask = 0u, auxmask = 0u;          // per-agent result bits of this step (StepIO.flags)
   // The f64 fields live in HBM (never staged): fetch every battery level, episode return and action of this env up
   // front with independent loads (one round trip instead of a dependent one per use) and keep them in registers.
   double bat[AMAX], epr[AMAX];
@@ -800,6 +802,8 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
         v.at(st.astamp, i) = c;
         v.at(st.clock, 0) = c + 1;
       }
+      // actions.py:80-96 action_introduced_collision: the move failed, or the mover now shares its tile with a collidable
+      if (io.flags && (!ok || v.n_coll(px(t), py(t)) > 1)) mcollmask |= 1u << i;
     } else if (op == MFG_OP_NOOP) {
       ok = true;
     } else if (op == MFG_OP_DOORUSE) {
@@ -839,6 +843,8 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
       for (int k = 0; k < sp.n_machines; ++k) ok |= v.at(st.mach_pos, k) == p;
     }
     rew[i] += use_extra ? r_extra : (ok ? sp.act_valid[i][a] : sp.act_fail[i][a]);
+    if (ok) okmask |= 1u << i;
+    if (use_extra) auxmask |= 1u << i;
   }
 
   // ---- tick_step hooks in yaml order (states.py:56-61)
@@ -982,7 +988,7 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
     if (op == MFG_R_WATCH_COLLISIONS) {                          // rules.py:276-306, states.py:228-238
 #pragma unroll
       for (int i = 0; i < AMAX; ++i) {
-        if (i < A && v.n_coll(px(v.apos[i]), py(v.apos[i])) >= 2) { rew[i] += P[0]; ++n_collisions; }
+        if (i < A && v.n_coll(px(v.apos[i]), py(v.apos[i])) >= 2) { rew[i] += P[0]; ++n_collisions; collmask |= 1u << i; }
       }
     } else if (op == MFG_R_BATTERY_DECHARGE || op == MFG_R_DONE_BATTERY) {   // batteries/rules.py:66-87
 #pragma unroll
@@ -1065,6 +1071,16 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
     }
   }
   io.done[e] = done ? 1 : 0;
+  if (io.flags) {
+    uint8_t* f = io.flags + (size_t)e * (A + 1);
+#pragma unroll
+    for (int i = 0; i < AMAX; ++i)
+      if (i < A) f[i] = (uint8_t)((((okmask >> i) & 1u) ? MFG_FLAG_VALID : 0) | (skipped[i] ? MFG_FLAG_SKIPPED : 0) |
+                                  (((collmask >> i) & 1u) ? MFG_FLAG_COLLISION : 0) |
+                                  (((mcollmask >> i) & 1u) ? MFG_FLAG_MOVE_COLLISION : 0) |
+                                  (((auxmask >> i) & 1u) ? MFG_FLAG_AUX_REWARD : 0));
+    f[A] = (uint8_t)(done ? (reason >= 0 ? reason : 255) : 0);
+  }
   if (sp.has_batteries) {
 #pragma unroll
     for (int i = 0; i < AMAX; ++i) if (i < A) v.at(st.bat, i) = bat[i];

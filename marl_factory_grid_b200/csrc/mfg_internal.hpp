@@ -131,6 +131,7 @@ struct MfgHandle {
   // host-buffer path staging
   int32_t* d_actions = nullptr; float* d_reward = nullptr; uint8_t* d_done = nullptr; float* d_obs = nullptr;
   int64_t launches = 0;
+  uint8_t* d_flags = nullptr;         // optional per-step result flags (caller-owned, mfg_bind_step_flags)
   uint32_t* d_reset_list = nullptr;   // [N] ids of envs that finished in the current step
   uint32_t* d_reset_count = nullptr;
   uint32_t* d_row_tab = nullptr;      // ColTab rows (built at mfg_bind_state)

@@ -25,7 +25,7 @@ _lib = None
 
 EXPORTS = ['mfg_create', 'mfg_destroy', 'mfg_last_error', 'mfg_version', 'mfg_state_bytes', 'mfg_state_field',
            'mfg_bind_state', 'mfg_reset', 'mfg_step', 'mfg_observe', 'mfg_step_observe', 'mfg_random_actions',
-           'mfg_step_host', 'mfg_stats', 'mfg_set_option', 'mfg_get_info']
+           'mfg_step_host', 'mfg_stats', 'mfg_set_option', 'mfg_get_info', 'mfg_bind_step_flags']
 
 
 def load_library(path: Path = LIB_PATH):
@@ -54,6 +54,7 @@ def load_library(path: Path = LIB_PATH):
     L.mfg_random_actions.argtypes = [vp, vp, u64, u64, vp]
     L.mfg_step_host.argtypes = [vp, vp, vp, vp, vp, i32, vp]
     L.mfg_stats.argtypes = [vp, vp, i32, vp]
+    L.mfg_bind_step_flags.argtypes = [vp, vp]
     L.mfg_set_option.argtypes = [vp, C.c_char_p, i64]
     L.mfg_get_info.argtypes = [vp, C.c_char_p]
     L.mfg_get_info.restype = i64
@@ -140,6 +141,13 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+    def enable_step_flags(self, on: bool = True):
+        """Per-step result flags [N, A + 1] uint8 (MFG_FLAG_* per agent, then the env's done reason): the batched form of the
+        reference's `info` dict.  Written by every following step."""
+        self.flags = self.torch.zeros((self.N, self.es.n_agents + 1), dtype=self.torch.uint8, device=self.device) if on else None
+        self._check(self.lib.mfg_bind_step_flags(self.h, self.flags.data_ptr() if on else None))
+        return self.flags
 
     def set_option(self, name: str, value: int):
         self._check(self.lib.mfg_set_option(self.h, name.encode(), int(value)))

@@ -84,3 +84,42 @@ class EnvMonitor:
 
     def report_possible_colum_keys(self):
         print(self.monitor_df.columns)
+
+
+class EnvRecorder:
+    """Episode recorder over the batched `Factory` (reference: marl_factory_grid/utils/logging/recorder.py:14-82): every
+    `step` appends `env.summarize_state(env_index)` of ONE chosen env of the batch, `reset` starts a new episode with the
+    header; `save_records` writes the list of episodes as yaml / json like the reference's non-protobuf path."""
+
+    def __init__(self, env, env_index: int = 0, filepath: Union[str, Path, None] = None, episodes: Optional[List[int]] = None):
+        self.env, self.env_index, self.filepath, self.episodes = env, int(env_index), filepath, episodes
+        self._curr_episode = 0
+        self._curr_ep_recorder, self._recorder_out_list = [], []
+
+    def __getattr__(self, name):
+        return getattr(self.env, name)
+
+    def reset(self, *a, **kw):
+        self._curr_ep_recorder, self._curr_episode = [], self._curr_episode + 1
+        return self.env.reset(*a, **kw)
+
+    def step(self, actions):
+        out = self.env.step(actions)
+        done = out[3]
+        if self.episodes is None or self._curr_episode in self.episodes:
+            self._curr_ep_recorder.append({'episode': self._curr_episode, **self.env.summarize_state(self.env_index)})
+        finished = bool(done) if isinstance(done, bool) else bool(done[self.env_index])
+        if finished and self._curr_ep_recorder:
+            self._recorder_out_list.append({'steps': self._curr_ep_recorder, 'episode': self._curr_episode})
+            self._curr_ep_recorder = []
+        return out
+
+    def save_records(self, filepath: Union[Path, str, None] = None, only_deltas: bool = False, save_occupation_map: bool = False,
+                     save_trajectory_map: bool = False):
+        import json
+        filepath = Path(filepath or self.filepath)
+        filepath.parent.mkdir(exist_ok=True, parents=True)
+        out = {'n_episodes': self._curr_episode, 'env_params': self.env.params, 'header': self.env.summarize_header(),
+               'episodes': self._recorder_out_list}
+        filepath.write_text(json.dumps(out, default=lambda o: o.item() if hasattr(o, 'item') else str(o)))
+        return out

@@ -163,13 +163,14 @@ def run_episode(cfg_path, seed, mode, max_steps, action_seed):
     init_dirt_spawn = EV['dirt_spawn'][:]
     EV['dirt_spawn'] = []
     EV['maint'] = []
-    actions, rewards, dones, maint_act, maint_valid, resp_n, resp_tiles = [], [], [], [], [], [], []
+    actions, rewards, dones, maint_act, maint_valid, resp_n, resp_tiles, infos = [], [], [], [], [], [], [], []
     n_maint = len(group(f.state, 'Maintainers'))
     for t in range(max_steps):
         a = [int(arng.integers(0, n)) for n in n_act]
         with contextlib.redirect_stdout(io.StringIO()):
             _, o, r, d, info = f.step(a)
         actions.append(a)
+        infos.append({k: float(v) for k, v in info.items()})
         rewards.append(np.asarray(r, np.float64).reshape(-1))
         dones.append(bool(d))
         snaps.append(snapshot(f))
@@ -205,6 +206,7 @@ def run_episode(cfg_path, seed, mode, max_steps, action_seed):
         'obs': np.stack(obs, 0),
         'door_pos': np.array([d.pos for d in group(f.state, 'Doors')], np.int16).reshape(-1, 2),
         'init_dirt_n_proposed': np.int32(len(init_dirt_spawn[0]) if init_dirt_spawn else 0),
+        'info_json': np.frombuffer(json.dumps(infos).encode(), np.uint8),      # the reference's per-step `info` dicts
     }
     for key in snaps[0]:
         ep[key] = np.stack([s[key] for s in snaps], 0)

@@ -21,6 +21,7 @@ struct HsHandle {
   size_t bytes;
   std::vector<unsigned long long> stats;
   bool ever_reset = false;
+  uint8_t* flags = nullptr;
 };
 
 template <typename Fn>
@@ -79,7 +80,7 @@ void hs_reset(HsHandle* h, const uint8_t* mask) {
 }
 void hs_step(HsHandle* h, const int32_t* actions, const uint8_t* maint_act, const int8_t* respawn_n,
              const uint16_t* respawn_pos, float* reward, uint8_t* done, int auto_reset) {
-  StepIO io{actions, maint_act, respawn_n, respawn_pos, reward, done, auto_reset, nullptr, nullptr};
+  StepIO io{actions, maint_act, respawn_n, respawn_pos, reward, done, auto_reset, nullptr, nullptr, h->flags};
   dispatch(h->sp.n_agents, [&](auto amax) {
     for (int64_t e = 0; e < h->N; ++e) env_step<decltype(amax)::value, MfgSpec>(h->sp, h->sp, h->tb, h->st, e, io);
   });
@@ -95,5 +96,6 @@ void hs_observe(HsHandle* h, float* obs) {
                                                 obs + ((size_t)e * total + h->sp.ch_offset[a]) * DD);
   });
 }
+void hs_bind_flags(HsHandle* h, uint8_t* flags) { h->flags = flags; }
 void hs_stats(HsHandle* h, int64_t* out) { for (int i = 0; i < MFG_N_STATS; ++i) out[i] = (int64_t)h->stats[i]; }
 }

@@ -46,6 +46,7 @@ def lib():
         L.hs_step.argtypes = [C.c_void_p] + [C.c_void_p] * 6 + [C.c_int]
         L.hs_observe.argtypes = [C.c_void_p, C.c_void_p]
         L.hs_stats.argtypes = [C.c_void_p, C.c_void_p]
+        L.hs_bind_flags.argtypes = [C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -112,6 +113,11 @@ class HostSim:
                       None if rn is None else rn.ctypes.data, None if rp is None else rp.ctypes.data,
                       self.reward.ctypes.data, self.done.ctypes.data, int(auto_reset))
         return self.reward, self.done
+
+    def enable_step_flags(self):
+        self.flags = np.zeros((self.N, self.es.n_agents + 1), np.uint8)
+        lib().hs_bind_flags(self.h, self.flags.ctypes.data)
+        return self.flags
 
     def observe(self):
         lib().hs_observe(self.h, self.obs.ctypes.data)
