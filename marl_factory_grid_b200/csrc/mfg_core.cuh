@@ -753,7 +753,8 @@ MFG_HD int maint_policy(Env<AMAX, SpecT>& v, int k, uint32_t step) {
 }
 
 // `sp` may be the full MfgSpec or its compact HotSpec copy; `full` (the MfgSpec) is only read by the in-kernel reset
-template <int AMAX, typename SpecT>
+// FLAGS: also write the per-agent result flags (StepIO.flags); a compile-time switch so that the plain step does not carry it
+template <int AMAX, typename SpecT, bool FLAGS = true>
 MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, const State& st, int64_t e_local,
                       const StepIO& io, int64_t eg = -1) {
   Env<AMAX, SpecT> v(sp, tb, st, e_local, eg);
@@ -803,7 +804,7 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
         v.at(st.clock, 0) = c + 1;
       }
       // actions.py:80-96 action_introduced_collision: the move failed, or the mover now shares its tile with a collidable
-      if (io.flags && (!ok || v.n_coll(px(t), py(t)) > 1)) mcollmask |= 1u << i;
+      if (FLAGS && io.flags && (!ok || v.n_coll(px(t), py(t)) > 1)) mcollmask |= 1u << i;
     } else if (op == MFG_OP_NOOP) {
       ok = true;
     } else if (op == MFG_OP_DOORUSE) {
@@ -843,8 +844,8 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
       for (int k = 0; k < sp.n_machines; ++k) ok |= v.at(st.mach_pos, k) == p;
     }
     rew[i] += use_extra ? r_extra : (ok ? sp.act_valid[i][a] : sp.act_fail[i][a]);
-    if (ok) okmask |= 1u << i;
-    if (use_extra) auxmask |= 1u << i;
+    if (FLAGS && ok) okmask |= 1u << i;
+    if (FLAGS && use_extra) auxmask |= 1u << i;
   }
 
   // ---- tick_step hooks in yaml order (states.py:56-61)
@@ -988,7 +989,7 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
     if (op == MFG_R_WATCH_COLLISIONS) {                          // rules.py:276-306, states.py:228-238
 #pragma unroll
       for (int i = 0; i < AMAX; ++i) {
-        if (i < A && v.n_coll(px(v.apos[i]), py(v.apos[i])) >= 2) { rew[i] += P[0]; ++n_collisions; collmask |= 1u << i; }
+        if (i < A && v.n_coll(px(v.apos[i]), py(v.apos[i])) >= 2) { rew[i] += P[0]; ++n_collisions; if (FLAGS) collmask |= 1u << i; }
       }
     } else if (op == MFG_R_BATTERY_DECHARGE || op == MFG_R_DONE_BATTERY) {   // batteries/rules.py:66-87
 #pragma unroll
@@ -1071,7 +1072,7 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
     }
   }
   io.done[e] = done ? 1 : 0;
-  if (io.flags) {
+  if (FLAGS && io.flags) {
     uint8_t* f = io.flags + (size_t)e * (A + 1);
 #pragma unroll
     for (int i = 0; i < AMAX; ++i)

@@ -37,7 +37,9 @@ struct WallPlanes {               // channels that contain Walls, as (agent, pla
 
 struct ObsPlan {
   bool ok = false;        // tiled kernel usable for this spec
-  int ge = 1;             // envs per output tile (tile = whole number of 16-byte vectors)
+  int ge = 1;             // (unused: one env per output tile)
+  int bulk = 1;           // parts of 4k planes are whole numbers of 16-byte vectors: bulk (TMA) stores possible
+  int ppp = 4;            // planes per part (the tile is composed in shared memory part by part)
   int nw = 4;             // warps per CTA
   int apad_log2 = 0;      // log2 of the agent count rounded up to a power of two (lanes per env in phase 1)
   int nbuf = 1;           // tile buffers per warp (2 = overlap the bulk store with the next env)

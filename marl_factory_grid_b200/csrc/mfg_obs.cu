@@ -114,7 +114,13 @@ struct BlkPos {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bulk_store_tile(float* dst, const float* src_smem, uint32_t bytes) {
+#if defined(MFG_ZFILL_EVICT_LAST)
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(pol));
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;\n" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes), "l"(pol) : "memory");
+#else
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+#endif
   asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
 }
 
@@ -162,10 +168,13 @@ __device__ __forceinline__ void mbar_wait0(unsigned long long* bar) {
 // CTA = one 128-env state block.  Every warp works on its own sub-groups of EPW = 32 / APAD envs (APAD = agent count
 // rounded up to a power of two): lane = (env, agent) in phase 1, the same warp expands the tiles of those envs in phase 2,
 // so after the prefix has landed no CTA-wide barrier is needed and warps in different phases overlap on the SM.
+#ifndef MFG_OBS_CTAS_F
+#define MFG_OBS_CTAS_F 2          // resident CTAs per SM the faithful kernel is compiled for (register cap 128 / 80)
+#endif
 template <int R, bool FAITHFUL>
-__global__ void __launch_bounds__(256, 2) k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st, ObsSlots sl, WallPlanes wp,
+__global__ void __launch_bounds__(256, FAITHFUL ? MFG_OBS_CTAS_F : 4) k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st, ObsSlots sl, WallPlanes wp,
                                                     float* __restrict__ obs, int total_channels, int cap, int apad_log2,
-                                                    int GE, int bulk, uint32_t* __restrict__ redo,
+                                                    int bulk, int ppp, uint32_t* __restrict__ redo,
                                                     const uint8_t* __restrict__ skip, ObsList ol) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long bar;
@@ -174,6 +183,9 @@ __global__ void __launch_bounds__(256, 2) k_obs_tiled(const MfgSpec* __restrict_
   __shared__ uint8_t s_nscal[MFG_MAX_AGENTS];
   __shared__ uint8_t s_hasbat[MFG_MAX_AGENTS];
   __shared__ int s_coff[MFG_MAX_AGENTS];
+  __shared__ uint16_t s_wplane[MAX_WALL_PLANES];                // wall planes: packed channel index | agent << 10, ascending
+  __shared__ uint32_t s_scl[MFG_MAX_AGENTS * 4];                // scalar channels of all agents: packed plane | kind << 12 | agent << 16
+  __shared__ int s_nscl;
   constexpr int D = 2 * R + 1, DD = D * D;
   const int A = sp->n_agents;
   const int NW = blockDim.x >> 5;
@@ -184,16 +196,18 @@ __global__ void __launch_bounds__(256, 2) k_obs_tiled(const MfgSpec* __restrict_
   // their columns are gathered into the same shared-memory image the block mode fills with one bulk copy
   const bool lmode = ol.ids != nullptr;
   const uint32_t n_listed = lmode ? *ol.count : 0u;
-  const int tile_floats = GE * total_channels * DD;
+  const int tile_floats = total_channels * DD;                     // one env's packed observation
+  const int part_floats = ppp * DD;                                // the tile is composed `ppp` planes at a time (bulk: a multiple of 4 planes = whole 16-byte vectors)
 
-  // shared memory carve-up (every region start stays 16-byte aligned): prefix | per warp: tile, sprite lists, counters
+  // shared memory carve-up (every region start stays 16-byte aligned):
+  //   prefix | per warp: part buffer, sprite lists, counters | candidate masks (faithful) | channel masks | x / H, y / W
   unsigned char* s_blk = smem_raw;                                                          // staged block prefix
-  const size_t per_warp = (size_t)tile_floats * 4 + (size_t)EPW * cap * 8 + 128;
+  const size_t part_bytes = ((size_t)part_floats * 4 + 15) & ~(size_t)15;
+  const size_t per_warp = part_bytes + (size_t)EPW * cap * 8 + (((size_t)EPW * 4 + 15) & ~(size_t)15);
   unsigned char* wbase = smem_raw + sl.prefix_bytes + (size_t)warp * per_warp;
-  float* tile = reinterpret_cast<float*>(wbase);
-  Sprite* s_spr = reinterpret_cast<Sprite*>(wbase + (size_t)tile_floats * 4);               // [EPW][cap]
-  int* s_cnt = reinterpret_cast<int*>(wbase + (size_t)tile_floats * 4 + (size_t)EPW * cap * 8);   // [EPW]
-  // misc region behind the per-warp regions: candidate masks (faithful), channel masks, GlobalPosition encodings
+  float* tile = reinterpret_cast<float*>(wbase);                                            // one part of one env's tile
+  Sprite* s_spr = reinterpret_cast<Sprite*>(wbase + part_bytes);                            // [EPW][cap]
+  int* s_cnt = reinterpret_cast<int*>(wbase + part_bytes + (size_t)EPW * cap * 8);          // [EPW]
   unsigned char* misc = smem_raw + sl.prefix_bytes + (size_t)NW * per_warp;
   unsigned long long* s_cm = reinterpret_cast<unsigned long long*>(misc) + (size_t)warp * 128 + lane;      // [NW][4][32]: word w of this lane = s_cm[w * 32]
   uint32_t* s_chm = reinterpret_cast<uint32_t*>(misc + (FAITHFUL ? (size_t)NW * 1024 : 0));                   // [A][MFG_N_TERMS] term -> channel bits
@@ -231,12 +245,26 @@ __global__ void __launch_bounds__(256, 2) k_obs_tiled(const MfgSpec* __restrict_
     s_hasbat[a] = (uint8_t)hb;
     s_coff[a] = sp->ch_offset[a];
   }
+  for (int w = threadIdx.x; w < wp.n; w += blockDim.x) s_wplane[w] = (uint16_t)(wp.plane[w] | ((uint32_t)wp.agent[w] << 10));
+  if (threadIdx.x == 32) {
+    int n = 0;
+    for (int a = 0; a < A; ++a) {
+      int na = 0;
+      for (int c = 0; c < sp->n_channels[a]; ++c) {
+        const int kind = sp->ch_kind[a][c];
+        if ((kind == MFG_CH_BATTERY || kind == MFG_CH_GLOBALPOS) && na < 4) {
+          s_scl[n++] = (uint32_t)(sp->ch_offset[a] + c) | ((uint32_t)kind << 12) | ((uint32_t)a << 16);
+          ++na;
+        }
+      }
+    }
+    s_nscl = n;
+  }
   for (int i = threadIdx.x; i < sp->H; i += blockDim.x) s_gx[i] = (float)((double)i / (double)sp->H);
   for (int i = threadIdx.x; i < sp->W; i += blockDim.x) s_gy[i] = (float)((double)i / (double)sp->W);
   const int spW = sp->W, n_doors = sp->n_doors, n_dest = sp->n_dest, has_dirt = sp->has_dirt, n_walls = sp->n_walls;
   __syncthreads();
-  bool n_scal_any = false;
-  for (int aa = 0; aa < A; ++aa) n_scal_any |= s_nscal[aa] != 0;
+  const int n_scl = s_nscl, n_wp = wp.n;
   if (!lmode) mbar_wait0(&bar);
   const uint16_t* blk16 = reinterpret_cast<const uint16_t*>(s_blk);
   const unsigned long long* blk_dopen = reinterpret_cast<const unsigned long long*>(s_blk + sl.off_dopen);
@@ -256,6 +284,7 @@ __global__ void __launch_bounds__(256, 2) k_obs_tiled(const MfgSpec* __restrict_
     const int el = lane >> apad_log2, a = lane & ((1 << apad_log2) - 1);
     unsigned long long wv = 0ull;
     uint32_t skip_mask = 0u;
+    bool lane_on = false;             // this lane computed an (env, agent) pair in phase 1
     float batv = 0.f;                 // Battery channel value of this (env, agent) lane
     uint32_t axy = 0u;                // agent position of this lane (GlobalPosition channel)          // bit (el << apad_log2): env el of this pass is skipped
     {
@@ -377,7 +406,11 @@ __global__ void __launch_bounds__(256, 2) k_obs_tiled(const MfgSpec* __restrict_
             const int k = __ffsll((long long)dm) - 1;
             const uint16_t q = pos[k];
             const int c = classify(q);
-            if (c == 3) dirt_w |= 1ull << k;
+            if (c == 3) {
+              dirt_w |= 1ull << k;
+              // the pile's f64 amount is read in phase 2 (HBM, uncoalesced): start the fetch now
+              asm volatile("prefetch.global.L2 [%0];\n" ::"l"(&field_at(st, st.dirt_amt, k, e)));
+            }
             if (FAITHFUL && c) {
               const uint32_t uid = blk_dirt_uid[k * ENV_BLOCK + eb];
               bool cf;
@@ -522,149 +555,169 @@ __global__ void __launch_bounds__(256, 2) k_obs_tiled(const MfgSpec* __restrict_
             emit(chm[MFG_G_DIRT], wcell(pos[k]), SK_DIRT, (uint32_t)k, 0.f);
           }
         }
-        // scalar channels are written straight into the tile in phase 2; the battery level (f64 in HBM) is fetched here,
-        // one coalesced-ish load per (env, agent) lane
+        // the battery level (f64 in HBM) of this (env, agent) lane: Battery channel, written in phase 2
         if (s_hasbat[a]) batv = (float)field_at(st, st.bat, a, e);
+        lane_on = true;
       }
     }
     __syncwarp();
-
-    // ---------------- phase 2: the warp expands its EPW envs, one tile of GE envs at a time ----------------------
+    // ---------------- phase 2: the warp composes its EPW tiles in shared memory, `ppp` planes at a time ---------------
     const uint32_t wv_lo = (uint32_t)wv, wv_hi = (uint32_t)(wv >> 32);
-    for (int g = 0; g * GE < EPW; ++g) {
-      const int eb0 = sub * EPW + g * GE;            // first env of this tile inside the CTA's 128
-      if (eb0 >= n_live) break;
-      // Each lane keeps (up to) two sprites of the env in registers across the three passes; further rounds only exist
-      // with a raised sprite capacity.  Dirt amounts (f64, uncoalesced) are requested as soon as the sprite is decoded
-      // so that their latency overlaps the integer pass.
-      auto clear_tile = [&]() {
-        if (bulk) {
-          // the bulk store that last read the tile buffer must have finished reading shared memory
+    for (int elx = 0; elx < EPW; ++elx) {
+      const int eb = sub * EPW + elx;
+      if (eb >= n_live) break;
+      if ((skip_mask >> (elx << apad_log2)) & 1u) continue;     // being re-spawned concurrently: the list-mode launch writes it
+      const int64_t e = env_of(eb);
+      float* te = obs + (size_t)e * tile_floats;
+      const int cnt = s_cnt[elx];
+      if (cnt > cap) {                      // sprite list overflowed (or too many uid conflicts): k_obs_redo rewrites this env
+        if (lane == 0) redo[1 + atomicAdd(redo, 1u)] = (uint32_t)(e);
+        continue;
+      }
+      // sprites.  Value of a cell = (float)((double)integer stack + fractional encoding): the integer-valued sprites of a cell
+      // add up exactly, a door / dirt encoding is added last with one rounding each (like the reference's f64 sums).
+      // One sprite per lane (cnt <= 32): lanes that hit the same cell are grouped by a warp match and the group's first lane
+      // carries the final value; the dirt amounts (f64, HBM, uncoalesced) are in flight while the first part is cleared.
+      uint32_t idx = 0xFFFFFFFFu;           // cell this lane writes (tile-relative), none by default
+      float out = 0.f;
+      double d0 = 0.0;
+      Sprite s0{0u, 0.f};
+      uint32_t k0 = 0xFF;
+      const bool on = lane < cnt && cnt <= 32;
+      if (on) {
+        s0 = s_spr[(size_t)elx * cap + lane];
+        k0 = (s0.w >> 16) & 0xFF;
+        if (k0 == SK_DIRT) d0 = field_at(st, st.dirt_amt, (int)(s0.w >> 24), e);
+      }
+      const uint32_t act = __ballot_sync(0xffffffffu, on);
+      // walls: bit 2a / 2a + 1 of wmask = agent a sees a wall on window cell `lane` / `lane + 32` (lane = window cell)
+      uint32_t wmask = 0u;
+      const int src0 = elx << apad_log2;
+      for (int aa = 0; aa < A; ++aa) {
+        const uint32_t m_lo = __shfl_sync(0xffffffffu, wv_lo, src0 + aa), m_hi = __shfl_sync(0xffffffffu, wv_hi, src0 + aa);
+        wmask |= (((m_lo >> lane) & 1u) | ((lane + 32 < DD ? (m_hi >> lane) & 1u : 0u) << 1)) << (2 * aa);
+      }
+      // scalar channels (observation_builder.py:205-218): lane i holds entry i of the list: battery level / (x / H, y / W) at
+      // the first cells of the plane; the values sit in the (env, agent) lanes of phase 1
+      int sc_pl = -1;
+      float sc_v0 = 0.f, sc_v1 = 0.f;
+      bool sc_two = false;
+      if (n_scl) {
+        const uint32_t rec = lane < n_scl ? s_scl[lane] : 0u;
+        const float bv = __shfl_sync(0xffffffffu, batv, src0 + (int)(rec >> 16));
+        const uint32_t pp = __shfl_sync(0xffffffffu, axy, src0 + (int)(rec >> 16));
+        if (lane < n_scl) {
+          sc_pl = (int)(rec & 4095u);
+          sc_two = ((rec >> 12) & 15u) != MFG_CH_BATTERY;
+          sc_v0 = sc_two ? s_gx[pp >> 8] : bv;
+          sc_v1 = s_gy[pp & 255u];
+        }
+      }
+      bool resolved = false;
+      int w = 0, f_lo = 0;
+      for (int p0 = 0; p0 < total_channels; p0 += ppp, f_lo += part_floats) {
+        const int p1 = p0 + ppp < total_channels ? p0 + ppp : total_channels;
+        const int nfl = (p1 - p0) * DD;
+        if (bulk) {      // the bulk store that last read the part buffer must have finished reading shared memory
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
           __syncwarp();
         }
-        float4* t4 = reinterpret_cast<float4*>(tile);
-        const int n4 = tile_floats >> 2;
-#pragma unroll 4
-        for (int i = lane; i < n4; i += 32) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        __syncwarp();
-      };
-      for (int ge = 0; ge < GE; ++ge) {
-        const int elx = g * GE + ge;
-        if (elx >= EPW || sub * EPW + elx >= n_live) break;
-        const int64_t e = env_of(sub * EPW + elx);
-        float* te = tile + (size_t)ge * total_channels * DD;
-        const int cnt = s_cnt[elx];
-        if (cnt > cap) {                      // sprite list overflowed (or too many uid conflicts): k_obs_redo rewrites this env
-          if (ge == 0) clear_tile();
-          if (lane == 0) redo[1 + atomicAdd(redo, 1u)] = (uint32_t)(e);
-          continue;
+        {      // whole rows of 32 x 16 bytes with a warp-uniform trip count, then the ragged rest
+          float4* t4 = reinterpret_cast<float4*>(tile) + lane;
+          const int n4 = (nfl + 3) >> 2, rows = n4 >> 5;
+          for (int r = 0; r < rows; ++r) t4[r * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (lane < (n4 & 31)) t4[rows * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        Sprite s0{0u, 0.f}, s1{0u, 0.f};
-        uint32_t k0 = 0xFF, k1 = 0xFF;
-        double d0 = 0.0, d1 = 0.0;
-        if (lane < cnt) {
-          s0 = s_spr[(size_t)elx * cap + lane];
-          k0 = (s0.w >> 16) & 0xFF;
-          if (k0 == SK_DIRT) d0 = field_at(st, st.dirt_amt, (int)(s0.w >> 24), e);
-        }
-        if (lane + 32 < cnt) {
-          s1 = s_spr[(size_t)elx * cap + lane + 32];
-          k1 = (s1.w >> 16) & 0xFF;
-          if (k1 == SK_DIRT) d1 = field_at(st, st.dirt_amt, (int)(s1.w >> 24), e);
-        }
-        // (the sprite / dirt-amount loads above are in flight while the previous bulk store drains and the tile is cleared)
-        if (ge == 0) clear_tile();
-        // wall planes: 1.0 where a visible wall is.  Nothing else can be on a wall cell, so the (predicated) store has
-        // a unique writer and needs no ordering against the sprite adds below.  Lane = window cell (two cells per lane).
-        for (int w = 0; w < wp.n; ++w) {
-          const int src = (elx << apad_log2) + (int)wp.agent[w];
-          const uint32_t m_lo = __shfl_sync(0xffffffffu, wv_lo, src), m_hi = __shfl_sync(0xffffffffu, wv_hi, src);
-          float* cells = te + (int)wp.plane[w] * DD;
-          if ((m_lo >> lane) & 1u) cells[lane] = 1.0f;
-          if (lane + 32 < DD && ((m_hi >> lane) & 1u)) cells[lane + 32] = 1.0f;
-        }
-        // scalar channels (observation_builder.py:205-218): battery level / (x / H, y / W) at the first cells of their plane;
-        // the values sit in the (env, agent) lanes of phase 1
-        if (n_scal_any) {
-#pragma unroll 1
-          for (int aa = 0; aa < A; ++aa) {
-            const int src = (elx << apad_log2) + aa;
-            const float bv = __shfl_sync(0xffffffffu, batv, src);
-            const uint32_t pp = __shfl_sync(0xffffffffu, axy, src);
-            if (lane < s_nscal[aa]) {
-              const int c = s_scal[aa][lane] & 0xFF, kind = s_scal[aa][lane] >> 8;
-              float* pl = te + (s_coff[aa] + c) * DD;
-              if (kind == MFG_CH_BATTERY) pl[0] = bv;
-              else { pl[0] = s_gx[pp >> 8]; pl[1] = s_gy[pp & 255u]; }
+        if (!resolved) {       // (after the clear has been issued: the dirt amounts had time to arrive)
+          resolved = true;
+          if (on) {
+            idx = s0.w & 0xFFFFu;
+            const uint32_t grp = __match_any_sync(act, idx);
+            if (grp == (1u << lane)) {
+              out = k0 == SK_INT ? s0.val : k0 == SK_DOOR ? (float)(0.0 + ((s0.w >> 24) ? ENC_DOOR_OPEN : ENC_DOOR_CLOSED)) : (float)(0.0 + d0);
+            } else {
+              const int isum = __reduce_add_sync(grp, k0 == SK_INT ? (int)s0.val : 0);
+              const uint32_t doors = __ballot_sync(grp, k0 == SK_DOOR) & grp, dirts = __ballot_sync(grp, k0 == SK_DIRT) & grp;
+              const uint32_t w_door = __shfl_sync(grp, s0.w, doors ? __ffs(doors) - 1 : lane);
+              const double d_dirt = __shfl_sync(grp, d0, dirts ? __ffs(dirts) - 1 : lane);
+              float f = (float)isum;
+              if (doors) f = (float)((double)f + ((w_door >> 24) ? ENC_DOOR_OPEN : ENC_DOOR_CLOSED));
+              if (dirts) f = (float)((double)f + d_dirt);
+              out = f;
+              if ((uint32_t)(__ffs(grp) - 1) != (uint32_t)lane) idx = 0xFFFFFFFFu;       // the group's first lane writes
             }
           }
         }
-        // pass A: integer-valued sprites (stacks add up exactly)
-        if (k0 == SK_INT) atomicAdd(&te[s0.w & 0xFFFF], s0.val);
-        if (k1 == SK_INT) atomicAdd(&te[s1.w & 0xFFFF], s1.val);
-        for (int i = lane + 64; i < cnt; i += 32) {
-          const Sprite s = s_spr[(size_t)elx * cap + i];
-          const uint32_t kind = (s.w >> 16) & 0xFF;
-          if (kind == SK_INT) atomicAdd(&te[s.w & 0xFFFF], s.val);
+        __syncwarp();
+        // wall planes of this part (the list is ascending): 1.0 where a visible wall is.  Nothing else can be on a wall cell,
+        // so the (predicated) stores have a unique writer.
+        for (; w < n_wp; ++w) {
+          const uint32_t rec = s_wplane[w];
+          const int pl = (int)(rec & 1023u);
+          if (pl >= p1) break;
+          const uint32_t bits = wmask >> (2 * (rec >> 10));
+          float* cells = tile + (pl - p0) * DD;
+          if (bits & 1u) cells[lane] = 1.0f;
+          if (bits & 2u) cells[lane + 32] = 1.0f;
         }
-        // fractional encodings last: value = (float)((double)integer_stack + encoding), one rounding like the reference
-        const bool door_here = k0 == SK_DOOR || k1 == SK_DOOR || cnt > 64;
-        const bool dirt_here = k0 == SK_DIRT || k1 == SK_DIRT || cnt > 64;
-        if (__any_sync(0xffffffffu, door_here)) {
-          __syncwarp();
-          if (k0 == SK_DOOR) { float* f = &te[s0.w & 0xFFFF]; *f = (float)((double)*f + ((s0.w >> 24) ? ENC_DOOR_OPEN : ENC_DOOR_CLOSED)); }
-          if (k1 == SK_DOOR) { float* f = &te[s1.w & 0xFFFF]; *f = (float)((double)*f + ((s1.w >> 24) ? ENC_DOOR_OPEN : ENC_DOOR_CLOSED)); }
-          for (int i = lane + 64; i < cnt; i += 32) {
-            const Sprite s = s_spr[(size_t)elx * cap + i];
-            if (((s.w >> 16) & 0xFF) == SK_DOOR) { float* f = &te[s.w & 0xFFFF]; *f = (float)((double)*f + ((s.w >> 24) ? ENC_DOOR_OPEN : ENC_DOOR_CLOSED)); }
+        if ((unsigned)(sc_pl - p0) < (unsigned)(p1 - p0)) {
+          float* cells = tile + (sc_pl - p0) * DD;
+          cells[0] = sc_v0;
+          if (sc_two) cells[1] = sc_v1;
+        }
+        if (n_scl > 32) {           // more scalar channels than lanes (many agents): the remaining entries, round by round
+          for (int base = 32; base < n_scl; base += 32) {
+            const uint32_t rec = base + lane < n_scl ? s_scl[base + lane] : 0u;
+            const float bv = __shfl_sync(0xffffffffu, batv, src0 + (int)(rec >> 16));
+            const uint32_t pp = __shfl_sync(0xffffffffu, axy, src0 + (int)(rec >> 16));
+            const int pl = (int)(rec & 4095u);
+            if (base + lane < n_scl && (unsigned)(pl - p0) < (unsigned)(p1 - p0)) {
+              float* cells = tile + (pl - p0) * DD;
+              if (((rec >> 12) & 15u) == MFG_CH_BATTERY) cells[0] = bv;
+              else { cells[0] = s_gx[pp >> 8]; cells[1] = s_gy[pp & 255u]; }
+            }
           }
         }
-        if (__any_sync(0xffffffffu, dirt_here)) {
+        if (idx - (uint32_t)f_lo < (uint32_t)nfl) tile[idx - f_lo] = out;
+        if (cnt > 32) {
+          // rare (large sprite capacities only): rounds of 32 sprites, one pass per kind, read-modify-write in the part buffer
+          // (ordered by the warp barriers); same arithmetic as above
           __syncwarp();
-          if (k0 == SK_DIRT) { float* f = &te[s0.w & 0xFFFF]; *f = (float)((double)*f + d0); }
-          if (k1 == SK_DIRT) { float* f = &te[s1.w & 0xFFFF]; *f = (float)((double)*f + d1); }
-          for (int i = lane + 64; i < cnt; i += 32) {
-            const Sprite s = s_spr[(size_t)elx * cap + i];
-            if (((s.w >> 16) & 0xFF) == SK_DIRT) { float* f = &te[s.w & 0xFFFF]; *f = (float)((double)*f + field_at(st, st.dirt_amt, (int)(s.w >> 24), e)); }
+          for (int kind = SK_INT; kind <= SK_DIRT; ++kind) {
+            if (kind == SK_STORE) continue;
+            for (int base = 0; base < cnt; base += 32) {
+              const int i = base + lane;
+              Sprite s1{0u, 0.f};
+              if (i < cnt) s1 = s_spr[(size_t)elx * cap + i];
+              const uint32_t ix = s1.w & 0xFFFFu;
+              const bool on1 = i < cnt && (int)((s1.w >> 16) & 0xFF) == kind && ix - (uint32_t)f_lo < (uint32_t)nfl;
+              const uint32_t act1 = __ballot_sync(0xffffffffu, on1);
+              if (on1) {
+                const uint32_t grp = __match_any_sync(act1, ix);
+                const float cur = tile[ix - f_lo];
+                float f;
+                if (kind == SK_INT) f = cur + (float)__reduce_add_sync(grp, (int)s1.val);
+                else if (kind == SK_DOOR) f = (float)((double)cur + ((s1.w >> 24) ? ENC_DOOR_OPEN : ENC_DOOR_CLOSED));
+                else f = (float)((double)cur + field_at(st, st.dirt_amt, (int)(s1.w >> 24), e));
+                if ((uint32_t)(__ffs(grp) - 1) == (uint32_t)lane) tile[ix - f_lo] = f;
+              }
+              __syncwarp();
+            }
           }
         }
-      }
-      // ---- stream the tile out
-      int ne = EPW - g * GE < GE ? EPW - g * GE : GE;
-      if (n_live - eb0 < ne) ne = n_live - eb0;
-      float* dst = obs + (size_t)env_of(eb0) * total_channels * DD;
-      // envs that are being re-spawned concurrently (skip flags) are written by the list-mode launch, not here; in list
-      // mode the envs of a multi-env tile are not neighbours in the output tensor
-      bool per_env = lmode && GE > 1;
-      for (int ge = 0; ge < ne; ++ge) per_env |= ((skip_mask >> ((g * GE + ge) << apad_log2)) & 1u) != 0;
-      if (per_env) {
-        __syncwarp();
-        const int per = total_channels * DD;
-        for (int ge = 0; ge < ne; ++ge) {
-          if ((skip_mask >> ((g * GE + ge) << apad_log2)) & 1u) continue;
-          float* d1 = obs + (size_t)env_of(eb0 + ge) * per;
-          for (int i = lane; i < per; i += 32) d1[i] = tile[ge * per + i];
-        }
-        __syncwarp();
-      } else if (bulk && ne == GE) {
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> visible to the async proxy
-        __syncwarp();
-        if (lane == 0) bulk_store_tile(dst, tile, (uint32_t)(tile_floats * sizeof(float)));
-      } else {
-        __syncwarp();
-        const int nfl = ne * total_channels * DD;
-        if (ne == GE) {
-          const float4* t4 = reinterpret_cast<const float4*>(tile);
-          float4* d4 = reinterpret_cast<float4*>(dst);
-          const int n4 = nfl >> 2;
-          for (int i = lane; i < n4; i += 32) __stcs(&d4[i], t4[i]);
+        // ---- stream the part out
+        if (bulk) {
+          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> visible to the async proxy
+          __syncwarp();
+          if (lane == 0) bulk_store_tile(te + f_lo, tile, (uint32_t)(nfl * sizeof(float)));
         } else {
-          for (int i = lane; i < nfl; i += 32) dst[i] = tile[i];
+          __syncwarp();
+          for (int i = lane; i < nfl; i += 32) te[f_lo + i] = tile[i];
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
+    __syncwarp();
   }
   if (!lmode) break;
   __syncthreads();                   // every warp is done with the image before the next chunk is staged
@@ -925,22 +978,32 @@ void plan_obs(MfgHandle* h) {
       if (*o < 0) *o = 0;                       // absent fields are never dereferenced; keep the pointers in range
   }
   const int tcdd = h->total_channels * h->DD;
-  p.ge = (tcdd % 4 == 0) ? 1 : (tcdd % 2 == 0) ? 2 : 4;
+  p.ge = 1;
   p.apad_log2 = 0;
   while ((1 << p.apad_log2) < sp.n_agents) ++p.apad_log2;
   const int epw = 32 >> p.apad_log2;                            // envs per warp pass
   p.cap = 8 * sp.n_agents < 16 ? 16 : 8 * sp.n_agents;        // sprite slots per env (overflow => generic slow path)
   p.cap_max = p.cap;
-  auto smem_for = [&](int nw) {
-    size_t per_warp = (size_t)p.ge * tcdd * sizeof(float) + (size_t)epw * p.cap_max * 8 + 128;   // tile, sprite lists, counters
+  // bulk (TMA) stores need parts that are whole numbers of 16-byte vectors: 4 planes of (2r+1)^2 floats are, so the tile is
+  // composed in parts of `ppp` = 4k planes; with a channel count that is not a multiple of 4 the parts are copied out by the
+  // warp itself
+  p.bulk = (h->total_channels % 4 == 0) ? 1 : 0;
+  auto smem_for = [&](int nw, int ppp) {
+    size_t part = (((size_t)ppp * h->DD * 4) + 15) & ~(size_t)15;
+    size_t per_warp = part + (size_t)epw * p.cap_max * 8 + (((size_t)epw * 4 + 15) & ~(size_t)15);   // part buffer, sprite lists, counters
     size_t misc = (sp.faithful ? (size_t)nw * 1024 : 0) + (size_t)((sp.n_agents * MFG_N_TERMS + 3) & ~3) * 4 +
                   (size_t)((sp.H + 3) & ~3) * 4 + (size_t)((sp.W + 3) & ~3) * 4;      // candidate masks, channel masks, x / H, y / W
     return (size_t)sl.prefix_bytes + 32 + (size_t)nw * per_warp + misc;
   };
-  // as many warps as there are sub-groups in a block, at most 8; fewer when the tiles are large
+  // as many warps as there are sub-groups in a block, at most 8; resident CTAs per SM aimed at: 3 (faithful: 80 registers) or
+  // 4 (identity: 64 registers) => (228 KB - 1 KB reserve per CTA) / CTAs, minus the static shared memory
   p.nw = ENV_BLOCK / epw < 8 ? ENV_BLOCK / epw : 8;
-  while (p.nw > 1 && smem_for(p.nw) > 115200) p.nw >>= 1;        // two CTAs per SM: (228 KB - 2 x 1 KB reserve) / 2, minus static
-  p.smem = smem_for(p.nw);
+  const size_t budget = (size_t)233472 / (sp.faithful ? MFG_OBS_CTAS_F : 4) - 1024 - 512;
+  p.ppp = (h->total_channels + 3) / 4 * 4;                     // whole tile first
+  while (p.ppp > 4 && smem_for(p.nw, p.ppp) > budget) p.ppp -= 4;
+  while (p.nw > 1 && smem_for(p.nw, p.ppp) > budget) p.nw >>= 1;
+  if (p.ppp > h->total_channels) p.ppp = h->total_channels;
+  p.smem = smem_for(p.nw, p.ppp);
   p.nbuf = 1;
   WindowRays wr;
   build_window_rays(sp, wr);
@@ -959,8 +1022,8 @@ void plan_obs(MfgHandle* h) {
       }
   bool full_ok = !sp.faithful || (sp.pomdp_r == 1 ? full_trie_matches<1>(sp) : sp.pomdp_r == 2 ? full_trie_matches<2>(sp)
                                   : sp.pomdp_r == 3 ? full_trie_matches<3>(sp) : false);
-  if (sl.agent0 - sl.item0 > 64 || sp.n_walls > 0xFFFE || epw < p.ge) full_ok = false;   // 64-bit visibility masks; whole tiles per warp pass
-  p.ok = trie_ok && full_ok && walls_fit && p.smem <= 200 * 1024 && tcdd * p.ge <= 0xFFFF;
+  if (sl.agent0 - sl.item0 > 64 || sp.n_walls > 0xFFFE) full_ok = false;   // 64-bit visibility masks
+  p.ok = trie_ok && full_ok && walls_fit && p.smem <= 200 * 1024 && tcdd <= 0xFFFF;
 }
 
 // exact per-agent observation of the envs in a device-side list (k_obs_redo)
@@ -998,7 +1061,7 @@ static cudaError_t launch_tiled_f(MfgHandle* h, float* d_obs, cudaStream_t s, co
   unsigned blocks = (unsigned)((h->N + ENV_BLOCK - 1) / ENV_BLOCK);
   if (ol.ids && blocks > 592u) blocks = 592u;        // list mode: grid-stride over the list inside the kernel (idle CTAs exit at once)
   kern<<<blocks, p.nw * 32, p.smem, s>>>(h->d_sp, h->tb, h->st, p.slots, p.walls, d_obs, h->total_channels, p.cap, p.apad_log2,
-                                         p.ge, h->obs_store != 0 ? 1 : 0, redo, skip, ol);
+                                         (h->obs_store != 0 && p.bulk) ? 1 : 0, p.ppp, redo, skip, ol);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   return launch_obs_list(h, d_obs, s, redo + 1, redo);
 }

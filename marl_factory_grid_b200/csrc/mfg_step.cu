@@ -82,7 +82,7 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, uint32
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
 }
 
-template <int AMAX>
+template <int AMAX, bool FLAGS>
 __global__ void __launch_bounds__(STEP_ENVS, 5) k_step(const __grid_constant__ HotSpec<AMAX> hs, const MfgSpec* __restrict__ full,
                                                     Tables tb, State st, StepIO io) {
   extern __shared__ __align__(128) unsigned char stage[];
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(STEP_ENVS, 5) k_step(const __grid_constant__ H
   __syncthreads();                  // barrier init + table copies visible
   mbar_wait(&bar, 0);
 
-  if (eg < st.N) env_step<AMAX, HotSpec<AMAX>>(hs, *full, tbs, ss, el, io, eg);
+  if (eg < st.N) env_step<AMAX, HotSpec<AMAX>, FLAGS>(hs, *full, tbs, ss, el, io, eg);
 
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   __syncthreads();
@@ -177,7 +177,7 @@ cudaError_t launch_step_kernel(MfgHandle* h, const StepIO& io, cudaStream_t s) {
   cudaError_t err = cudaSuccess;
   dispatch_amax(h->sp.n_agents, [&](auto amax) {
     constexpr int AMAX = decltype(amax)::value;
-    auto kern = k_step<AMAX>;
+    auto kern = io.flags ? k_step<AMAX, true> : k_step<AMAX, false>;
     HotSpec<AMAX> hs;
     fill_hot_spec<AMAX>(h->sp, hs);
     if (smem > 48 * 1024) err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -99,6 +99,9 @@ class EnvRecorder:
     def __getattr__(self, name):
         return getattr(self.env, name)
 
+    def __getitem__(self, item):
+        return self.env[item]
+
     def reset(self, *a, **kw):
         self._curr_ep_recorder, self._curr_episode = [], self._curr_episode + 1
         return self.env.reset(*a, **kw)
