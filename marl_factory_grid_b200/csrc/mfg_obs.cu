@@ -294,6 +294,10 @@ __global__ void __launch_bounds__(256, FAITHFUL ? MFG_OBS_CTAS_F : 4) k_obs_tile
       // skipped envs (being re-spawned concurrently) are rewritten later; one flag load per lane, shared through a ballot
       const bool lane_skip = skip != nullptr && in_range && skip[e] != 0;
       skip_mask = __ballot_sync(0xffffffffu, lane_skip);
+      // faithful mode: the phase-1 results phase 2 needs (wall mask, battery level, position) are handed over through the
+      // lane's candidate-mask slots (dead once the lane's classification is done) instead of registers that would have to
+      // live across the whole pass (80-register budget for three resident CTAs per SM)
+      if (FAITHFUL && !(a < A && in_range && !lane_skip)) { s_cm[0] = 0ull; s_cm[32] = 0ull; }
       if (a < A && in_range && !lane_skip) {
         const BlkPos pos{blk16, eb};
         const unsigned long long dopen = n_doors ? blk_dopen[eb] : 0ull;
@@ -558,6 +562,7 @@ __global__ void __launch_bounds__(256, FAITHFUL ? MFG_OBS_CTAS_F : 4) k_obs_tile
         // the battery level (f64 in HBM) of this (env, agent) lane: Battery channel, written in phase 2
         if (s_hasbat[a]) batv = (float)field_at(st, st.bat, a, e);
         lane_on = true;
+        if (FAITHFUL) { s_cm[0] = wv; s_cm[32] = (unsigned long long)__float_as_uint(batv) | ((unsigned long long)axy << 32); }
       }
     }
     __syncwarp();
@@ -593,8 +598,15 @@ __global__ void __launch_bounds__(256, FAITHFUL ? MFG_OBS_CTAS_F : 4) k_obs_tile
       // walls: bit 2a / 2a + 1 of wmask = agent a sees a wall on window cell `lane` / `lane + 32` (lane = window cell)
       uint32_t wmask = 0u;
       const int src0 = elx << apad_log2;
+      const unsigned long long* s_res = s_cm - lane;           // [4][32]: word 0 = wall mask, word 1 = battery | position << 32
       for (int aa = 0; aa < A; ++aa) {
-        const uint32_t m_lo = __shfl_sync(0xffffffffu, wv_lo, src0 + aa), m_hi = __shfl_sync(0xffffffffu, wv_hi, src0 + aa);
+        uint32_t m_lo, m_hi;
+        if (FAITHFUL) {
+          const unsigned long long m = s_res[src0 + aa];
+          m_lo = (uint32_t)m; m_hi = (uint32_t)(m >> 32);
+        } else {
+          m_lo = __shfl_sync(0xffffffffu, wv_lo, src0 + aa); m_hi = __shfl_sync(0xffffffffu, wv_hi, src0 + aa);
+        }
         wmask |= (((m_lo >> lane) & 1u) | ((lane + 32 < DD ? (m_hi >> lane) & 1u : 0u) << 1)) << (2 * aa);
       }
       // scalar channels (observation_builder.py:205-218): lane i holds entry i of the list: battery level / (x / H, y / W) at
@@ -604,8 +616,15 @@ __global__ void __launch_bounds__(256, FAITHFUL ? MFG_OBS_CTAS_F : 4) k_obs_tile
       bool sc_two = false;
       if (n_scl) {
         const uint32_t rec = lane < n_scl ? s_scl[lane] : 0u;
-        const float bv = __shfl_sync(0xffffffffu, batv, src0 + (int)(rec >> 16));
-        const uint32_t pp = __shfl_sync(0xffffffffu, axy, src0 + (int)(rec >> 16));
+        float bv;
+        uint32_t pp;
+        if (FAITHFUL) {
+          const unsigned long long v = s_res[32 + src0 + (int)(rec >> 16)];
+          bv = __uint_as_float((uint32_t)v); pp = (uint32_t)(v >> 32);
+        } else {
+          bv = __shfl_sync(0xffffffffu, batv, src0 + (int)(rec >> 16));
+          pp = __shfl_sync(0xffffffffu, axy, src0 + (int)(rec >> 16));
+        }
         if (lane < n_scl) {
           sc_pl = (int)(rec & 4095u);
           sc_two = ((rec >> 12) & 15u) != MFG_CH_BATTERY;
@@ -668,8 +687,15 @@ __global__ void __launch_bounds__(256, FAITHFUL ? MFG_OBS_CTAS_F : 4) k_obs_tile
         if (n_scl > 32) {           // more scalar channels than lanes (many agents): the remaining entries, round by round
           for (int base = 32; base < n_scl; base += 32) {
             const uint32_t rec = base + lane < n_scl ? s_scl[base + lane] : 0u;
-            const float bv = __shfl_sync(0xffffffffu, batv, src0 + (int)(rec >> 16));
-            const uint32_t pp = __shfl_sync(0xffffffffu, axy, src0 + (int)(rec >> 16));
+            float bv;
+            uint32_t pp;
+            if (FAITHFUL) {
+              const unsigned long long v = s_res[32 + src0 + (int)(rec >> 16)];
+              bv = __uint_as_float((uint32_t)v); pp = (uint32_t)(v >> 32);
+            } else {
+              bv = __shfl_sync(0xffffffffu, batv, src0 + (int)(rec >> 16));
+              pp = __shfl_sync(0xffffffffu, axy, src0 + (int)(rec >> 16));
+            }
             const int pl = (int)(rec & 4095u);
             if (base + lane < n_scl && (unsigned)(pl - p0) < (unsigned)(p1 - p0)) {
               float* cells = tile + (pl - p0) * DD;
