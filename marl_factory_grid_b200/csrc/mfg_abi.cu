@@ -108,6 +108,7 @@ void mfg_destroy(MfgHandle* h) {
   if (h->d_reset_list) cudaFree(h->d_reset_list);
   if (h->d_reset_count) cudaFree(h->d_reset_count);
   if (h->d_redo) cudaFree(h->d_redo);
+  if (h->d_obs_prog) cudaFree(h->d_obs_prog);
   if (h->d_row_tab) cudaFree(h->d_row_tab);
   drain_ns(h->t_step); drain_ns(h->t_obs); drain_ns(h->t_reset);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);

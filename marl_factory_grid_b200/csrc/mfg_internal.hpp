@@ -35,6 +35,12 @@ struct WallPlanes {               // channels that contain Walls, as (agent, pla
   uint8_t agent[MAX_WALL_PLANES];
 };
 
+// word offsets of the constant table the tiled observation kernel copies into shared memory (built by plan_obs)
+struct ObsProg {
+  enum { N_SCL = 0, N_WP = 1, COFF = 2, HASBAT = COFF + MFG_MAX_AGENTS, SCL = HASBAT + MFG_MAX_AGENTS,
+         WPLANE = SCL + MFG_MAX_AGENTS * 4, CHM = WPLANE + MAX_WALL_PLANES };
+};
+
 struct ObsPlan {
   bool ok = false;        // tiled kernel usable for this spec
   int ge = 1;             // (unused: one env per output tile)
@@ -48,6 +54,7 @@ struct ObsPlan {
   WallPlanes walls{};
   size_t smem = 0;
   ObsSlots slots{};
+  std::vector<uint32_t> prog;        // ObsProg image
 };
 
 }  // namespace mfg
@@ -139,6 +146,7 @@ struct MfgHandle {
   uint32_t* d_row_tab = nullptr;      // ColTab rows (built at mfg_bind_state)
   int n_row_tab = 0;
   std::vector<uint32_t> row_tab_host;
+  uint32_t* d_obs_prog = nullptr;     // device copy of plan.prog
   uint32_t* d_redo = nullptr;         // [1 + N] observation redo list: count, env ids (tiled kernel's rare exact path)
   int defer_reset = 1;
   // mfg_step_observe overlaps the packed re-spawn (side stream) with the observation kernel (caller's stream)

@@ -175,17 +175,10 @@ template <int R, bool FAITHFUL>
 __global__ void __launch_bounds__(256, FAITHFUL ? MFG_OBS_CTAS_F : 4) k_obs_tiled(const MfgSpec* __restrict__ sp, Tables tb, State st, ObsSlots sl, WallPlanes wp,
                                                     float* __restrict__ obs, int total_channels, int cap, int apad_log2,
                                                     int bulk, int ppp, uint32_t* __restrict__ redo,
-                                                    const uint8_t* __restrict__ skip, ObsList ol) {
+                                                    const uint8_t* __restrict__ skip, ObsList ol,
+                                                    const uint32_t* __restrict__ prog, int prog_words) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long bar;
-  // per-agent channel program (lanes of one warp belong to different agents, so it is read with per-lane indices)
-  __shared__ uint16_t s_scal[MFG_MAX_AGENTS][4];               // scalar channels: channel | kind << 8
-  __shared__ uint8_t s_nscal[MFG_MAX_AGENTS];
-  __shared__ uint8_t s_hasbat[MFG_MAX_AGENTS];
-  __shared__ int s_coff[MFG_MAX_AGENTS];
-  __shared__ uint16_t s_wplane[MAX_WALL_PLANES];                // wall planes: packed channel index | agent << 10, ascending
-  __shared__ uint32_t s_scl[MFG_MAX_AGENTS * 4];                // scalar channels of all agents: packed plane | kind << 12 | agent << 16
-  __shared__ int s_nscl;
   constexpr int D = 2 * R + 1, DD = D * D;
   const int A = sp->n_agents;
   const int NW = blockDim.x >> 5;
@@ -210,9 +203,16 @@ __global__ void __launch_bounds__(256, FAITHFUL ? MFG_OBS_CTAS_F : 4) k_obs_tile
   int* s_cnt = reinterpret_cast<int*>(wbase + part_bytes + (size_t)EPW * cap * 8);          // [EPW]
   unsigned char* misc = smem_raw + sl.prefix_bytes + (size_t)NW * per_warp;
   unsigned long long* s_cm = reinterpret_cast<unsigned long long*>(misc) + (size_t)warp * 128 + lane;      // [NW][4][32]: word w of this lane = s_cm[w * 32]
-  uint32_t* s_chm = reinterpret_cast<uint32_t*>(misc + (FAITHFUL ? (size_t)NW * 1024 : 0));                   // [A][MFG_N_TERMS] term -> channel bits
-  float* s_gx = reinterpret_cast<float*>(s_chm + ((A * MFG_N_TERMS + 3) & ~3));                               // x / H, y / W (entity/util.py:56-66)
-  float* s_gy = s_gx + ((sp->H + 3) & ~3);
+  // the per-spec constant "observation program" (built once by plan_obs, see ObsProg): per-agent channel offsets and scalar
+  // channels, the wall planes, term -> channel masks, the GlobalPosition encodings x / H, y / W (entity/util.py:56-66)
+  uint32_t* s_prog = reinterpret_cast<uint32_t*>(misc + (FAITHFUL ? (size_t)NW * 1024 : 0));
+  const int* s_coff = reinterpret_cast<const int*>(s_prog + ObsProg::COFF);
+  const uint32_t* s_hasbat = s_prog + ObsProg::HASBAT;
+  const uint32_t* s_scl = s_prog + ObsProg::SCL;              // scalar channels of all agents: packed plane | kind << 12 | agent << 16
+  const uint32_t* s_wplane = s_prog + ObsProg::WPLANE;        // wall planes: packed channel index | agent << 10, ascending
+  const uint32_t* s_chm = s_prog + ObsProg::CHM;              // [A][MFG_N_TERMS] term -> channel bits
+  const float* s_gx = reinterpret_cast<const float*>(s_chm + ((A * MFG_N_TERMS + 3) & ~3));
+  const float* s_gy = s_gx + ((sp->H + 3) & ~3);
   // ---- stage the positional prefix of this block: one TMA bulk copy (dirt/item/.../agent positions, door + dest masks)
   // block mode: one pass; list mode: grid-stride over chunks of 128 listed envs
   for (uint32_t lbase = blockIdx.x * ENV_BLOCK;; lbase += gridDim.x * ENV_BLOCK) {
@@ -232,39 +232,10 @@ __global__ void __launch_bounds__(256, FAITHFUL ? MFG_OBS_CTAS_F : 4) k_obs_tile
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(s_blk)),
                  "l"(st.base_i + (size_t)blockIdx.x * st.blk_i), "r"((uint32_t)sl.prefix_bytes), "r"(smem_u32(&bar)) : "memory");
   }
-  for (int i = threadIdx.x; i < A * MFG_N_TERMS; i += blockDim.x) s_chm[i] = sp->term_chmask[i / MFG_N_TERMS][i % MFG_N_TERMS];
-  if (threadIdx.x < A) {
-    const int a = threadIdx.x, C = sp->n_channels[a];
-    int n = 0, hb = 0;
-    for (int c = 0; c < C; ++c) {
-      const int kind = sp->ch_kind[a][c];
-      if ((kind == MFG_CH_BATTERY || kind == MFG_CH_GLOBALPOS) && n < 4) s_scal[a][n++] = (uint16_t)(c | (kind << 8));
-      hb |= kind == MFG_CH_BATTERY;
-    }
-    s_nscal[a] = (uint8_t)n;
-    s_hasbat[a] = (uint8_t)hb;
-    s_coff[a] = sp->ch_offset[a];
-  }
-  for (int w = threadIdx.x; w < wp.n; w += blockDim.x) s_wplane[w] = (uint16_t)(wp.plane[w] | ((uint32_t)wp.agent[w] << 10));
-  if (threadIdx.x == 32) {
-    int n = 0;
-    for (int a = 0; a < A; ++a) {
-      int na = 0;
-      for (int c = 0; c < sp->n_channels[a]; ++c) {
-        const int kind = sp->ch_kind[a][c];
-        if ((kind == MFG_CH_BATTERY || kind == MFG_CH_GLOBALPOS) && na < 4) {
-          s_scl[n++] = (uint32_t)(sp->ch_offset[a] + c) | ((uint32_t)kind << 12) | ((uint32_t)a << 16);
-          ++na;
-        }
-      }
-    }
-    s_nscl = n;
-  }
-  for (int i = threadIdx.x; i < sp->H; i += blockDim.x) s_gx[i] = (float)((double)i / (double)sp->H);
-  for (int i = threadIdx.x; i < sp->W; i += blockDim.x) s_gy[i] = (float)((double)i / (double)sp->W);
+  for (int i = threadIdx.x; i < prog_words; i += blockDim.x) s_prog[i] = prog[i];
   const int spW = sp->W, n_doors = sp->n_doors, n_dest = sp->n_dest, has_dirt = sp->has_dirt, n_walls = sp->n_walls;
   __syncthreads();
-  const int n_scl = s_nscl, n_wp = wp.n;
+  const int n_scl = (int)s_prog[ObsProg::N_SCL], n_wp = (int)s_prog[ObsProg::N_WP];
   if (!lmode) mbar_wait0(&bar);
   const uint16_t* blk16 = reinterpret_cast<const uint16_t*>(s_blk);
   const unsigned long long* blk_dopen = reinterpret_cast<const unsigned long long*>(s_blk + sl.off_dopen);
@@ -595,19 +566,20 @@ __global__ void __launch_bounds__(256, FAITHFUL ? MFG_OBS_CTAS_F : 4) k_obs_tile
         if (k0 == SK_DIRT) d0 = field_at(st, st.dirt_amt, (int)(s0.w >> 24), e);
       }
       const uint32_t act = __ballot_sync(0xffffffffu, on);
-      // walls: bit 2a / 2a + 1 of wmask = agent a sees a wall on window cell `lane` / `lane + 32` (lane = window cell)
-      uint32_t wmask = 0u;
+      // walls: lane L handles one third (17 / 17 / 15 window cells) of wall plane L / 3 and sets its cells one by one - a
+      // handful of iterations for all planes at once (lane = window cell took two predicated stores per plane)
       const int src0 = elx << apad_log2;
-      const unsigned long long* s_res = s_cm - lane;           // [4][32]: word 0 = wall mask, word 1 = battery | position << 32
-      for (int aa = 0; aa < A; ++aa) {
-        uint32_t m_lo, m_hi;
-        if (FAITHFUL) {
-          const unsigned long long m = s_res[src0 + aa];
-          m_lo = (uint32_t)m; m_hi = (uint32_t)(m >> 32);
-        } else {
-          m_lo = __shfl_sync(0xffffffffu, wv_lo, src0 + aa); m_hi = __shfl_sync(0xffffffffu, wv_hi, src0 + aa);
-        }
-        wmask |= (((m_lo >> lane) & 1u) | ((lane + 32 < DD ? (m_hi >> lane) & 1u : 0u) << 1)) << (2 * aa);
+      const unsigned long long* s_res = s_cm - lane;           // faithful: [4][32], word 0 = wall mask, word 1 = battery | position << 32
+      int w_pl = -1, w_base = 0;                                // this lane's wall plane (packed channel index) / first cell
+      uint32_t w_bits = 0u;                                     // visible walls among the cells [w_base, w_base + 17)
+      {
+        const int j = lane / 3, t = lane - 3 * j;
+        const uint32_t rec = j < n_wp ? s_wplane[j] : 0u;
+        unsigned long long m;
+        if (FAITHFUL) m = s_res[src0 + (int)(rec >> 10)];
+        else m = (unsigned long long)__shfl_sync(0xffffffffu, wv_lo, src0 + (int)(rec >> 10)) |
+                 ((unsigned long long)__shfl_sync(0xffffffffu, wv_hi, src0 + (int)(rec >> 10)) << 32);
+        if (j < n_wp) { w_pl = (int)(rec & 1023u); w_base = 17 * t; w_bits = (uint32_t)(m >> w_base) & 0x1FFFFu; }
       }
       // scalar channels (observation_builder.py:205-218): lane i holds entry i of the list: battery level / (x / H, y / W) at
       // the first cells of the plane; the values sit in the (env, agent) lanes of phase 1
@@ -625,15 +597,14 @@ __global__ void __launch_bounds__(256, FAITHFUL ? MFG_OBS_CTAS_F : 4) k_obs_tile
           bv = __shfl_sync(0xffffffffu, batv, src0 + (int)(rec >> 16));
           pp = __shfl_sync(0xffffffffu, axy, src0 + (int)(rec >> 16));
         }
-        if (lane < n_scl) {
-          sc_pl = (int)(rec & 4095u);
-          sc_two = ((rec >> 12) & 15u) != MFG_CH_BATTERY;
-          sc_v0 = sc_two ? s_gx[pp >> 8] : bv;
-          sc_v1 = s_gy[pp & 255u];
-        }
+        const float gx = s_gx[pp >> 8], gy = s_gy[pp & 255u];
+        sc_two = ((rec >> 12) & 15u) != MFG_CH_BATTERY;
+        sc_v0 = sc_two ? gx : bv;
+        sc_v1 = gy;
+        sc_pl = lane < n_scl ? (int)(rec & 4095u) : -1;
       }
       bool resolved = false;
-      int w = 0, f_lo = 0;
+      int f_lo = 0;
       for (int p0 = 0; p0 < total_channels; p0 += ppp, f_lo += part_floats) {
         const int p1 = p0 + ppp < total_channels ? p0 + ppp : total_channels;
         const int nfl = (p1 - p0) * DD;
@@ -641,11 +612,11 @@ __global__ void __launch_bounds__(256, FAITHFUL ? MFG_OBS_CTAS_F : 4) k_obs_tile
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
           __syncwarp();
         }
-        {      // whole rows of 32 x 16 bytes with a warp-uniform trip count, then the ragged rest
-          float4* t4 = reinterpret_cast<float4*>(tile) + lane;
-          const int n4 = (nfl + 3) >> 2, rows = n4 >> 5;
-          for (int r = 0; r < rows; ++r) t4[r * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (lane < (n4 & 31)) t4[rows * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+        {
+          float4* t4 = reinterpret_cast<float4*>(tile);
+          const int n4 = (nfl + 3) >> 2;
+#pragma unroll 1
+          for (int i = lane; i < n4; i += 32) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (!resolved) {       // (after the clear has been issued: the dirt amounts had time to arrive)
           resolved = true;
@@ -668,16 +639,25 @@ __global__ void __launch_bounds__(256, FAITHFUL ? MFG_OBS_CTAS_F : 4) k_obs_tile
           }
         }
         __syncwarp();
-        // wall planes of this part (the list is ascending): 1.0 where a visible wall is.  Nothing else can be on a wall cell,
-        // so the (predicated) stores have a unique writer.
-        for (; w < n_wp; ++w) {
-          const uint32_t rec = s_wplane[w];
+        // wall planes of this part: 1.0 where a visible wall is.  Nothing else can be on a wall cell, so every store has a
+        // unique writer.
+        if ((unsigned)(w_pl - p0) < (unsigned)(p1 - p0)) {
+          float* cells = tile + (w_pl - p0) * DD + w_base;
+          for (uint32_t m = w_bits; m; m &= m - 1) cells[__ffs(m) - 1] = 1.0f;
+        }
+        for (int base = 32; base < 3 * n_wp; base += 32) {        // more than 10 wall planes: the remaining ones, round by round
+          const int L = base + lane, j = L / 3, t = L - 3 * j;
+          const bool valid = L < 3 * n_wp;
+          const uint32_t rec = valid ? s_wplane[j] : 0u;
+          unsigned long long m;
+          if (FAITHFUL) m = s_res[src0 + (int)(rec >> 10)];
+          else m = (unsigned long long)__shfl_sync(0xffffffffu, wv_lo, src0 + (int)(rec >> 10)) |
+                   ((unsigned long long)__shfl_sync(0xffffffffu, wv_hi, src0 + (int)(rec >> 10)) << 32);
           const int pl = (int)(rec & 1023u);
-          if (pl >= p1) break;
-          const uint32_t bits = wmask >> (2 * (rec >> 10));
-          float* cells = tile + (pl - p0) * DD;
-          if (bits & 1u) cells[lane] = 1.0f;
-          if (bits & 2u) cells[lane + 32] = 1.0f;
+          if (valid && (unsigned)(pl - p0) < (unsigned)(p1 - p0)) {
+            float* cells = tile + (pl - p0) * DD + 17 * t;
+            for (uint32_t b = (uint32_t)(m >> (17 * t)) & 0x1FFFFu; b; b &= b - 1) cells[__ffs(b) - 1] = 1.0f;
+          }
         }
         if ((unsigned)(sc_pl - p0) < (unsigned)(p1 - p0)) {
           float* cells = tile + (sc_pl - p0) * DD;
@@ -1010,6 +990,31 @@ void plan_obs(MfgHandle* h) {
   const int epw = 32 >> p.apad_log2;                            // envs per warp pass
   p.cap = 8 * sp.n_agents < 16 ? 16 : 8 * sp.n_agents;        // sprite slots per env (overflow => generic slow path)
   p.cap_max = p.cap;
+  // the constant table the kernel copies into shared memory (ObsProg): everything its prologue used to derive from the spec
+  const size_t prog_words = (size_t)ObsProg::CHM + (size_t)((sp.n_agents * MFG_N_TERMS + 3) & ~3) + (size_t)((sp.H + 3) & ~3) +
+                            (size_t)((sp.W + 3) & ~3);
+  {
+    p.prog.assign(prog_words, 0u);
+    uint32_t n_scl = 0;
+    for (int a = 0; a < sp.n_agents; ++a) {
+      p.prog[ObsProg::COFF + a] = (uint32_t)sp.ch_offset[a];
+      int na = 0;
+      for (int c = 0; c < sp.n_channels[a]; ++c) {
+        const int kind = sp.ch_kind[a][c];
+        if (kind == MFG_CH_BATTERY) p.prog[ObsProg::HASBAT + a] = 1u;
+        if ((kind == MFG_CH_BATTERY || kind == MFG_CH_GLOBALPOS) && na < 4) {      // scalar channels: packed plane | kind << 12 | agent << 16
+          p.prog[ObsProg::SCL + n_scl++] = (uint32_t)(sp.ch_offset[a] + c) | ((uint32_t)kind << 12) | ((uint32_t)a << 16);
+          ++na;
+        }
+      }
+      for (int t = 0; t < MFG_N_TERMS; ++t) p.prog[ObsProg::CHM + a * MFG_N_TERMS + t] = sp.term_chmask[a][t];
+    }
+    p.prog[ObsProg::N_SCL] = n_scl;
+    float* gx = reinterpret_cast<float*>(&p.prog[ObsProg::CHM + ((sp.n_agents * MFG_N_TERMS + 3) & ~3)]);
+    float* gy = gx + ((sp.H + 3) & ~3);
+    for (int i = 0; i < sp.H; ++i) gx[i] = (float)((double)i / (double)sp.H);      // entity/util.py:56-66
+    for (int i = 0; i < sp.W; ++i) gy[i] = (float)((double)i / (double)sp.W);
+  }
   // bulk (TMA) stores need parts that are whole numbers of 16-byte vectors: 4 planes of (2r+1)^2 floats are, so the tile is
   // composed in parts of `ppp` = 4k planes; with a channel count that is not a multiple of 4 the parts are copied out by the
   // warp itself
@@ -1017,8 +1022,7 @@ void plan_obs(MfgHandle* h) {
   auto smem_for = [&](int nw, int ppp) {
     size_t part = (((size_t)ppp * h->DD * 4) + 15) & ~(size_t)15;
     size_t per_warp = part + (size_t)epw * p.cap_max * 8 + (((size_t)epw * 4 + 15) & ~(size_t)15);   // part buffer, sprite lists, counters
-    size_t misc = (sp.faithful ? (size_t)nw * 1024 : 0) + (size_t)((sp.n_agents * MFG_N_TERMS + 3) & ~3) * 4 +
-                  (size_t)((sp.H + 3) & ~3) * 4 + (size_t)((sp.W + 3) & ~3) * 4;      // candidate masks, channel masks, x / H, y / W
+    size_t misc = (sp.faithful ? (size_t)nw * 1024 : 0) + prog_words * 4;     // candidate masks, the constant table (ObsProg)
     return (size_t)sl.prefix_bytes + 32 + (size_t)nw * per_warp + misc;
   };
   // as many warps as there are sub-groups in a block, at most 8; resident CTAs per SM aimed at: 3 (faithful: 80 registers) or
@@ -1046,6 +1050,8 @@ void plan_obs(MfgHandle* h) {
         p.walls.plane[p.walls.n] = (uint16_t)(sp.ch_offset[a] + c);
         p.walls.n++;
       }
+  p.prog[ObsProg::N_WP] = (uint32_t)p.walls.n;
+  for (int w = 0; w < p.walls.n; ++w) p.prog[ObsProg::WPLANE + w] = (uint32_t)p.walls.plane[w] | ((uint32_t)p.walls.agent[w] << 10);
   bool full_ok = !sp.faithful || (sp.pomdp_r == 1 ? full_trie_matches<1>(sp) : sp.pomdp_r == 2 ? full_trie_matches<2>(sp)
                                   : sp.pomdp_r == 3 ? full_trie_matches<3>(sp) : false);
   if (sl.agent0 - sl.item0 > 64 || sp.n_walls > 0xFFFE) full_ok = false;   // 64-bit visibility masks
@@ -1081,13 +1087,18 @@ static cudaError_t launch_tiled_f(MfgHandle* h, float* d_obs, cudaStream_t s, co
     cudaError_t e = cudaMalloc(&h->d_redo, 2 * ((size_t)h->N + 1) * sizeof(uint32_t));
     if (e != cudaSuccess) return e;
   }
+  if (!h->d_obs_prog) {
+    cudaError_t e = cudaMalloc(&h->d_obs_prog, p.prog.size() * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_obs_prog, p.prog.data(), p.prog.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return e;
+  }
   uint32_t* redo = h->d_redo + (ol.ids ? (size_t)h->N + 1 : 0);
   cudaError_t e = cudaMemsetAsync(redo, 0, sizeof(uint32_t), s);
   if (e != cudaSuccess) return e;
   unsigned blocks = (unsigned)((h->N + ENV_BLOCK - 1) / ENV_BLOCK);
   if (ol.ids && blocks > 592u) blocks = 592u;        // list mode: grid-stride over the list inside the kernel (idle CTAs exit at once)
   kern<<<blocks, p.nw * 32, p.smem, s>>>(h->d_sp, h->tb, h->st, p.slots, p.walls, d_obs, h->total_channels, p.cap, p.apad_log2,
-                                         (h->obs_store != 0 && p.bulk) ? 1 : 0, p.ppp, redo, skip, ol);
+                                         (h->obs_store != 0 && p.bulk) ? 1 : 0, p.ppp, redo, skip, ol, h->d_obs_prog, (int)p.prog.size());
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   return launch_obs_list(h, d_obs, s, redo + 1, redo);
 }
