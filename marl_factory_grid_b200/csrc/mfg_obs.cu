@@ -299,8 +299,11 @@ __global__ void __launch_bounds__(256, FAITHFUL ? MFG_OBS_CTAS_F : 4) k_obs_tile
         // window visibility: a table look-up keyed by (tile, closed listed doors among the <= 4 doors of the window); the
         // ray march itself only runs on tiles whose window holds more doors
         unsigned long long vis;
-        const uint32_t dwin = FAITHFUL ? tb.door_win[tile_id] : (7u << 24);
-        if (FAITHFUL && (dwin >> 24) <= 4u) {          // (identity mode: two dependent table loads cost more than the march's ALU work)
+#ifndef MFG_OBS_VISTAB_I
+#define MFG_OBS_VISTAB_I 1        // identity mode: 1 = visibility table as well, 0 = always march (the kernel is issue-bound at 4 CTAs per SM)
+#endif
+        const uint32_t dwin = (FAITHFUL || MFG_OBS_VISTAB_I) ? tb.door_win[tile_id] : (7u << 24);
+        if ((FAITHFUL || MFG_OBS_VISTAB_I) && (dwin >> 24) <= 4u) {
           const unsigned long long closed = dnear & ~dopen;
           const uint32_t sub = ((uint32_t)(closed >> (dwin & 63u)) & 1u) | (((uint32_t)(closed >> ((dwin >> 6) & 63u)) & 1u) << 1) |
                                (((uint32_t)(closed >> ((dwin >> 12) & 63u)) & 1u) << 2) | (((uint32_t)(closed >> ((dwin >> 18) & 63u)) & 1u) << 3);
@@ -377,8 +380,11 @@ __global__ void __launch_bounds__(256, FAITHFUL ? MFG_OBS_CTAS_F : 4) k_obs_tile
         bool overflow = false;
         {
           const uint32_t wrng = FAITHFUL ? tb.wall_cand_rng[tile_id] : 0xFFFFu;     // [lo, hi] of the candidate wall uids >= 64
-          for (unsigned long long dm = dirtlisted; dm; dm &= dm - 1) {     // listed piles (identity mode: the live ones)
-            const int k = __ffsll((long long)dm) - 1;
+          // listed piles (identity mode: the live ones); the 64-bit slot mask is walked as two 32-bit words
+#pragma unroll
+          for (int half = 0; half < 2; ++half)
+          for (uint32_t dm = half ? (uint32_t)(dirtlisted >> 32) : (uint32_t)dirtlisted; dm; dm &= dm - 1) {
+            const int k = __ffs(dm) - 1 + 32 * half;
             const uint16_t q = pos[k];
             const int c = classify(q);
             if (c == 3) {
