@@ -190,7 +190,7 @@ int mfg_step_host(MfgHandle* h, const int32_t* h_actions, float* h_reward, uint8
 int mfg_bind_step_flags(MfgHandle* h, uint8_t* d_flags);
 /* copies the MFG_N_STATS int64 statistics vector (device) into d_out; zero_after != 0 clears it afterwards */
 int mfg_stats(MfgHandle* h, int64_t* d_out, int zero_after, void* stream);
-/* options: "obs_kernel" (0 auto, 1 direct per-agent kernel, 2 tiled shared-memory kernel), "obs_store" (1 TMA bulk store),
+/* options: "obs_kernel" (0 auto, 1 exact per-agent kernel over block-staged state, 2 tiled shared-memory kernel, 3 exact kernel on plain global state), "obs_store" (1 TMA bulk store),
  * "obs_cap" (sprite slots per env), "defer_reset" (1 packed reset kernel), "overlap_reset" (1 side stream in
  * mfg_step_observe), "timing" (1: CUDA event pairs around the kernels, read with mfg_get_info "step_ns" / "obs_ns" /
  * "reset_ns").  info: "launches", "tiled_ok", "obs_smem", "obs_threads", "obs_ctas_per_sm", "obs_cap", "obs_cap_max". */

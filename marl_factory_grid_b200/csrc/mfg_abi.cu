@@ -64,6 +64,7 @@ int mfg_create(const MfgSpec* spec, int64_t n_envs, int64_t env_id_offset, MfgHa
 
   build_vis_tables(*spec, ht);
   build_win_vis_tables(*spec, ht);
+  build_rank_table(*spec, ht);
 
   MfgHandle* h = new MfgHandle();
   h->sp = *spec;
@@ -72,7 +73,7 @@ int mfg_create(const MfgSpec* spec, int64_t n_envs, int64_t env_id_offset, MfgHa
   int rc;
 #define UP(field) if ((rc = upload(h, ht.field, &h->tb.field)) != MFG_OK) { mfg_destroy(h); return rc; }
   UP(wall) UP(door_map) UP(floor_pos) UP(floor_index) UP(wall_uid) UP(wall_pos) UP(door_pos) UP(nexthop) UP(wall_win) UP(wall_box) UP(door_near) UP(door_adj)
-  UP(vis_box) UP(wall_cand64) UP(wall_cand_rng) UP(wall_win64) UP(door_win) UP(vis_tab)
+  UP(vis_box) UP(wall_cand64) UP(wall_cand_rng) UP(wall_win64) UP(door_win) UP(vis_tab) UP(rank_tab)
 #undef UP
   h->tb.env_id_offset = env_id_offset;
   void* d = nullptr;
@@ -205,7 +206,7 @@ int mfg_observe(MfgHandle* h, float* d_obs, void* stream) {
   if (!d_obs) return fail(MFG_E_INVALID, "mfg_observe: NULL buffer");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (h->obs_kernel == 2 && !h->plan.ok) return fail(MFG_E_UNSUPPORTED, "tiled observation kernel not available for this spec");
-  const bool tiled = h->plan.ok && h->obs_kernel != 1;
+  const bool tiled = h->plan.ok && h->obs_kernel != 1 && h->obs_kernel != 3;
   Timed t(h, h->t_obs, s);
   CUDA_TRY(tiled ? launch_obs_tiled(h, d_obs, s) : launch_obs_direct(h, d_obs, s));
   h->launches += tiled ? 2 : 1;       // tiled kernel + its redo pass
@@ -215,7 +216,7 @@ int mfg_observe(MfgHandle* h, float* d_obs, void* stream) {
 int mfg_step_observe(MfgHandle* h, const int32_t* d_actions, const MfgTape* tape, float* d_reward, uint8_t* d_done,
                      float* d_obs, int auto_reset, void* stream) {
   NEED_BOUND(h);
-  const bool tiled = h->plan.ok && h->obs_kernel != 1;
+  const bool tiled = h->plan.ok && h->obs_kernel != 1 && h->obs_kernel != 3;
   if (!(auto_reset && h->defer_reset && h->overlap_reset && tiled && d_obs)) {
     int rc = mfg_step(h, d_actions, tape, d_reward, d_done, auto_reset, stream);
     if (rc != MFG_OK) return rc;
@@ -302,7 +303,7 @@ int mfg_stats(MfgHandle* h, int64_t* d_out, int zero_after, void* stream) {
 int mfg_set_option(MfgHandle* h, const char* name, int64_t value) {
   if (!h || !name) return fail(MFG_E_INVALID, "mfg_set_option: bad arguments");
   if (strcmp(name, "obs_kernel") == 0) {
-    if (value < 0 || value > 2) return fail(MFG_E_INVALID, "obs_kernel must be 0 (auto), 1 (direct) or 2 (tiled)");
+    if (value < 0 || value > 3) return fail(MFG_E_INVALID, "obs_kernel must be 0 (auto), 1 (exact, block-staged), 2 (tiled) or 3 (exact, plain)");
     if (value == 2 && !h->plan.ok) return fail(MFG_E_UNSUPPORTED, "tiled observation kernel not available for this spec");
     h->obs_kernel = (int)value;
     return MFG_OK;

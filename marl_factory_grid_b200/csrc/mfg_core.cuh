@@ -130,6 +130,9 @@ struct Tables {
   // march result only depends on (tile, which of the window's doors are closed)
   const uint32_t* door_win;      // [H*W] up to 4 door indices inside the window (6 bits each) | count << 24 (7 = too many: march)
   const uint64_t* vis_tab;       // [H*W][16] visibility mask of the window for every closed-door subset
+  // exact per-agent observation path, full observability with at most 4 doors (built by build_tables): first-visit ranks of
+  // the ray-radius box for every (tile, closed listed door subset) - the ray walk becomes a table look-up
+  const uint16_t* rank_tab;    // [H*W][1 << n_doors][(2R+1)^2] or null
   int64_t env_id_offset;
   unsigned long long* stats;   // [MFG_N_STATS]
 };
@@ -1135,12 +1138,36 @@ MFG_HD bool obs_full(const MfgSpec& sp) { return sp.pomdp_r == 0; }
 MFG_HD int obs_plane_cells(const MfgSpec& sp) { return obs_full(sp) ? sp.H * sp.W : (2 * sp.pomdp_r + 1) * (2 * sp.pomdp_r + 1); }
 MFG_HD int obs_ray_radius(const MfgSpec& sp) { return obs_full(sp) ? (sp.H < sp.W ? sp.H : sp.W) : 2 * sp.pomdp_r + 1; }
 
+// ray walk (ray_caster.py:81-103): first-visit order of the cells of the radius box around (ax, ay); rays in the reference's
+// order, a ray stops at a light-blocking cell or between two diagonal blockers
+template <typename BlocksLight>
+MFG_HD void ray_walk(const MfgSpec& sp, int ax, int ay, int R, int BW, BlocksLight blocks_light, rank_t* rank) {
+  for (int i = 0; i < BW * BW; ++i) rank[i] = RANK_INF;
+  int visit = 0;
+  for (int ray = 0; ray < sp.n_rays; ++ray) {
+    int pxr = ax, pyr = ay;
+    for (int s = 0; s < sp.ray_len[ray]; ++s) {
+      int dx = sp.ray_dx[ray][s], dy = sp.ray_dy[ray][s];
+      int x = ax + dx, y = ay + dy;
+      int cx = x - pxr, cy = y - pyr;
+      bool hits = blocks_light(x, y);
+      bool diag = (cx != 0 && cy != 0) && blocks_light(x, y - cy) && blocks_light(x - cx, y);
+      if (!diag) {
+        rank_t& rk = rank[(dx + R) * BW + (dy + R)];
+        if (rk == RANK_INF) rk = (rank_t)visit++;
+      }
+      if (hits || diag) break;
+      pxr = x; pyr = y;
+    }
+  }
+}
+
 template <int AMAX>
 struct ObsCtx {
   Env<AMAX>& v;
   int a, ax, ay, r, D, R, BW;
-  rank_t* rank;                           // [(2R+1)^2] first-visit order of every cell of the radius box, RANK_INF = unseen
-  MFG_HD ObsCtx(Env<AMAX>& v_, rank_t* rank_) : v(v_), rank(rank_) {}
+  const rank_t* rank;                     // [(2R+1)^2] first-visit order of every cell of the radius box, RANK_INF = unseen
+  MFG_HD ObsCtx(Env<AMAX>& v_, const rank_t* rank_) : v(v_), rank(rank_) {}
   MFG_HD bool blocks_light(int x, int y) const {
     if (!v.in_grid(x, y)) return false;
     return v.tbl(v.tb.wall, x * v.sp.W + y) || v.closed_listed_door(x, y);
@@ -1192,26 +1219,16 @@ MFG_HDN void obs_agent_exact(const MfgSpec& sp, const Tables& tb, const State& s
   const bool full = obs_full(sp);
   const int r = sp.pomdp_r, D = 2 * r + 1, R = obs_ray_radius(sp), BW = 2 * R + 1;
   o.a = a; o.ax = px(v.apos[a]); o.ay = py(v.apos[a]); o.r = r; o.D = D; o.R = R; o.BW = BW;
-  for (int i = 0; i < BW * BW; ++i) rank[i] = RANK_INF;
-
-  // ---- ray walk: first-visit order of the cells of the radius box
-  int visit = 0;
-  for (int ray = 0; ray < sp.n_rays; ++ray) {
-    int pxr = o.ax, pyr = o.ay;
-    for (int s = 0; s < sp.ray_len[ray]; ++s) {
-      int dx = sp.ray_dx[ray][s], dy = sp.ray_dy[ray][s];
-      int x = o.ax + dx, y = o.ay + dy;
-      int cx = x - pxr, cy = y - pyr;
-      bool hits = o.blocks_light(x, y);
-      bool diag = (cx != 0 && cy != 0) && o.blocks_light(x, y - cy) && o.blocks_light(x - cx, y);
-      if (!diag) {
-        rank_t& rk = rank[(dx + R) * BW + (dy + R)];
-        if (rk == RANK_INF) rk = (rank_t)visit++;
-      }
-      if (hits || diag) break;
-      pxr = x; pyr = y;
-    }
+  // ---- first-visit order of the cells of the radius box: from the per-(tile, closed door subset) table when there is one,
+  // else the ray walk
+  if (tb.rank_tab) {
+    const uint32_t nsub = 1u << sp.n_doors;
+    const uint32_t sub = (uint32_t)(~v.dopen & v.dlisted) & (nsub - 1u);
+    o.rank = tb.rank_tab + ((size_t)(o.ax * sp.W + o.ay) * nsub + sub) * (size_t)(BW * BW);
+  } else {
+    ray_walk(sp, o.ax, o.ay, R, BW, [&](int x, int y) { return o.blocks_light(x, y); }, rank);
   }
+  const rank_t* const rankv = o.rank;
 
   const uint32_t* chm = sp.term_chmask[a];
   auto in_window = [&](uint16_t p, int& cell) {
@@ -1223,12 +1240,14 @@ MFG_HDN void obs_agent_exact(const MfgSpec& sp, const Tables& tb, const State& s
   };
 
   // ---- walls (uid = row-major wall index)
+  int max_small = 0;
+  for (int c = C_ITEM; c <= C_MAINT; ++c) max_small = v.cls_count(c) > max_small ? v.cls_count(c) : max_small;
   if (chm[MFG_G_WALLS]) {
     const int wr = full ? R : r;                 // walls can only be seen inside the ray radius
     for (int dx = -wr; dx <= wr; ++dx) for (int dy = -wr; dy <= wr; ++dy) {
       int x = o.ax + dx, y = o.ay + dy;
       if (!v.in_grid(x, y) || !v.tbl(tb.wall, x * sp.W + y)) continue;
-      int rk = rank[(dx + R) * BW + (dy + R)];
+      int rk = rankv[(dx + R) * BW + (dy + R)];
       if (rk == RANK_INF) continue;
       if (sp.faithful) {
         // walls are never shadowed by other walls; only a dynamic entity with the same uid seen earlier hides it
@@ -1238,8 +1257,9 @@ MFG_HDN void obs_agent_exact(const MfgSpec& sp, const Tables& tb, const State& s
         if (!sh && sp.has_dirt && uid < (int)v.at(st.dirt_next_uid, 0))
           for (int k = 0; k < v.dirt_end && !sh; ++k)
             sh = v.at(st.dirt_uid, k) == uid && ((v.dirt_listed >> k) & 1) && o.rank_of(v.at(st.dirt_pos, k)) < rk;
-        for (int c = C_ITEM; c <= C_MAINT && !sh; ++c)
-          sh = uid < v.cls_count(c) && ((v.at(v.cls_listed(c), 0) >> uid) & 1) && o.rank_of(v.at(v.cls_pos(c), uid)) < rk;
+        if (uid < max_small)                  // (most walls have a larger uid than any small group has members)
+          for (int c = C_ITEM; c <= C_MAINT && !sh; ++c)
+            sh = uid < v.cls_count(c) && ((v.at(v.cls_listed(c), 0) >> uid) & 1) && o.rank_of(v.at(v.cls_pos(c), uid)) < rk;
         if (sh) continue;
       }
       sink.wall(full ? x * sp.W + y : (dx + r) * D + (dy + r));
@@ -1313,8 +1333,7 @@ struct FloatSink {
   uint32_t wall_mask;
   MFG_HD void add(uint32_t mask, int cell, double val) {
     while (mask) {
-      int c = 0;
-      while (!((mask >> c) & 1)) ++c;
+      const int c = ctz64(mask);
       mask &= mask - 1;
       float& f = out[c * DD + cell];
       f = (float)((double)f + val);
@@ -1327,10 +1346,10 @@ struct FloatSink {
 
 template <int AMAX>
 MFG_HDN void obs_agent_direct(const MfgSpec& sp, const Tables& tb, const State& st, int64_t e, int a, float* out,
-                              int64_t eg = -1) {
+                              int64_t eg = -1, bool zero = true) {
   const int DD = obs_plane_cells(sp);
   const int C = sp.n_channels[a];
-  for (int i = 0; i < C * DD; ++i) out[i] = 0.0f;
+  if (zero) for (int i = 0; i < C * DD; ++i) out[i] = 0.0f;      // (false: the caller has cleared the planes)
   rank_t rank[RANK_CELLS];
   FloatSink sink{out, DD, sp.term_chmask[a][MFG_G_WALLS]};
   obs_agent_exact<AMAX>(sp, tb, st, e, a, rank, sink, eg);

@@ -77,7 +77,33 @@ struct HostTables {
   std::vector<uint64_t> wall_win, wall_box, door_near, door_adj, vis_box, wall_cand64, wall_win64;
   std::vector<uint32_t> wall_cand_rng, door_win;
   std::vector<uint64_t> vis_tab;
+  std::vector<uint16_t> rank_tab;
 };
+
+// first-visit rank tables of the exact observation path (Tables::rank_tab): full observability, at most 4 doors, bounded size.
+// Built with the very ray walk the kernels use (ray_walk, mfg_core.cuh) over every (tile, closed door subset).
+inline void build_rank_table(const MfgSpec& sp, HostTables& t) {
+  t.rank_tab.clear();
+  if (sp.pomdp_r != 0 || sp.n_doors > 4 || sp.n_rays <= 0) return;
+  const int H = sp.H, W = sp.W, R = obs_ray_radius(sp), BW = 2 * R + 1;
+  if (R > RANK_RMAX) return;
+  const size_t nsub = (size_t)1 << sp.n_doors, cells = (size_t)BW * BW;
+  if ((size_t)H * W * nsub * cells > ((size_t)32 << 20)) return;             // keep it well inside L2
+  t.rank_tab.assign((size_t)H * W * nsub * cells, (uint16_t)RANK_INF);
+  for (int x = 0; x < H; ++x)
+    for (int y = 0; y < W; ++y) {
+      if (t.wall[(size_t)x * W + y]) continue;
+      for (size_t sub = 0; sub < nsub; ++sub) {
+        auto blocks = [&](int xx, int yy) -> bool {
+          if (xx < 0 || yy < 0 || xx >= H || yy >= W) return false;
+          if (t.wall[(size_t)xx * W + yy]) return true;
+          const int d = t.door_map[(size_t)xx * W + yy];
+          return d != 0xFF && ((sub >> d) & 1);
+        };
+        ray_walk(sp, x, y, R, BW, blocks, &t.rank_tab[(((size_t)x * W + y) * nsub + sub) * cells]);
+      }
+    }
+}
 
 inline std::string build_tables(const MfgSpec& sp, HostTables& t) {
   const int H = sp.H, W = sp.W;

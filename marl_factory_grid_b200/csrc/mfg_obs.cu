@@ -25,15 +25,39 @@ using namespace mfg;
 
 template <int AMAX>
 __global__ void __launch_bounds__(128) k_obs_direct(const MfgSpec* __restrict__ sp, Tables tb, State st, float* obs,
-                                                    int total_channels) {
+                                                    int total_channels, int stride) {
   // agent-major thread mapping: consecutive threads = consecutive envs of the same agent (coalesced state loads)
+  extern __shared__ __align__(16) float s_planes[];
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int A = sp->n_agents;
-  if (t >= st.N * A) return;
-  int a = (int)(t / st.N);
-  int64_t e = t - (int64_t)a * st.N;
   const int DD = obs_plane_cells(*sp);
-  obs_agent_direct<AMAX>(*sp, tb, st, e, a, obs + ((size_t)e * total_channels + sp->ch_offset[a]) * DD);
+  const bool live = t < st.N * A;
+  const int a = live ? (int)(t / st.N) : 0;
+  const int64_t e = live ? t - (int64_t)a * st.N : 0;
+  float* out = obs + ((size_t)e * total_channels + sp->ch_offset[a]) * DD;
+  if (stride == 0) {                   // planes too large for shared memory: accumulate in the output tensor itself
+    if (live) obs_agent_direct<AMAX>(*sp, tb, st, e, a, out);
+    return;
+  }
+  // small planes (full observability on the small shipped levels): every thread composes its agent's planes in its own
+  // shared-memory slice (the accumulation is a read-modify-write per contribution - in global memory that was a dependent
+  // HBM round trip each), then the CTA copies the slices out with coalesced stores
+  float* mine = s_planes + (size_t)threadIdx.x * stride;
+  const int nfl = sp->n_channels[a] * DD;
+  if (live) obs_agent_direct<AMAX>(*sp, tb, st, e, a, mine);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = warp; j < (int)blockDim.x; j += (int)(blockDim.x >> 5)) {      // slice j belongs to thread j of the CTA
+    const int64_t tj = (int64_t)blockIdx.x * blockDim.x + j;
+    if (tj >= st.N * A) break;
+    const int aj = (int)(tj / st.N);
+    const int64_t ej = tj - (int64_t)aj * st.N;
+    float* dst = obs + ((size_t)ej * total_channels + sp->ch_offset[aj]) * DD;
+    const float* src = s_planes + (size_t)j * stride;
+    const int n = sp->n_channels[aj] * DD;
+    for (int i = lane; i < n; i += 32) dst[i] = src[i];
+  }
+  (void)nfl;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -149,6 +173,12 @@ __global__ void __launch_bounds__(128) k_obs_redo(const MfgSpec* __restrict__ sp
   }
 }
 
+// Exact per-agent path over whole state blocks: CTA = one 128-env block, its integer slab staged in shared memory by one
+// bulk copy (like k_step), one thread per (env, agent) of the block.  The product path of full observability and of specs
+// the tiled kernel cannot take; with the rank table (Tables::rank_tab) the ray walk is a look-up.
+template <int AMAX>
+__global__ void __launch_bounds__(256) k_obs_block(const MfgSpec* __restrict__ sp, Tables tb, State st, float* obs, int total_channels);
+
 __device__ __forceinline__ void mbar_init1(unsigned long long* bar) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(bar)) : "memory");
   asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -163,6 +193,44 @@ __device__ __forceinline__ void mbar_wait0(unsigned long long* bar) {
       "bra MFG_OWAIT_%=;\n"
       "MFG_ODONE_%=:\n"
       "}\n" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int AMAX>
+__global__ void __launch_bounds__(256) k_obs_block(const MfgSpec* __restrict__ sp, Tables tb, State st, float* obs, int total_channels) {
+  extern __shared__ __align__(128) unsigned char stage[];
+  __shared__ __align__(8) unsigned long long bar;
+  const int A = sp->n_agents;
+  const int DD = obs_plane_cells(*sp);
+  const int64_t blk0 = (int64_t)blockIdx.x * ENV_BLOCK;
+  const int n_live = (int)(st.N - blk0 < ENV_BLOCK ? st.N - blk0 : ENV_BLOCK);
+  if (threadIdx.x == 0) {
+    mbar_init1(&bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(&bar)), "r"((uint32_t)st.blk_i) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(stage)),
+                 "l"(st.base_i + (size_t)blockIdx.x * st.blk_i), "r"((uint32_t)st.blk_i), "r"(smem_u32(&bar)) : "memory");
+  }
+  const State ss = staged_view(st, stage);
+  // the block's observations are one contiguous run of the output tensor: cleared here with coalesced stores (a per-thread
+  // clear of its own planes wrote every sector four times)
+  {
+    float* o0 = obs + (size_t)blk0 * total_channels * DD;
+    const size_t nfl = (size_t)n_live * total_channels * DD;
+    if ((reinterpret_cast<uintptr_t>(o0) & 15) == 0) {
+      float4* o4 = reinterpret_cast<float4*>(o0);
+      for (size_t i = threadIdx.x; i < (nfl >> 2); i += blockDim.x) o4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (size_t i = (nfl & ~(size_t)3) + threadIdx.x; i < nfl; i += blockDim.x) o0[i] = 0.f;
+    } else {
+      for (size_t i = threadIdx.x; i < nfl; i += blockDim.x) o0[i] = 0.f;
+    }
+  }
+  __syncthreads();
+  mbar_wait0(&bar);
+  // agent-major inside the block: consecutive threads = consecutive envs of the same agent
+  for (int i = threadIdx.x; i < n_live * A; i += blockDim.x) {
+    const int a = i / n_live, j = i - a * n_live;
+    const int64_t e = blk0 + j;
+    obs_agent_direct<AMAX>(*sp, tb, ss, j, a, obs + ((size_t)e * total_channels + sp->ch_offset[a]) * DD, e, false);
+  }
 }
 
 // CTA = one 128-env state block.  Every warp works on its own sub-groups of EPW = 32 / APAD envs (APAD = agent count
@@ -1161,12 +1229,36 @@ cudaError_t launch_obs_direct(MfgHandle* h, float* d_obs, cudaStream_t s) {
   const int64_t total = h->N * h->sp.n_agents;
   const unsigned blocks = (unsigned)((total + threads - 1) / threads);
   const int A = h->sp.n_agents;
-  if (A <= 1) k_obs_direct<1><<<blocks, threads, 0, s>>>(h->d_sp, h->tb, h->st, d_obs, h->total_channels);
-  else if (A <= 2) k_obs_direct<2><<<blocks, threads, 0, s>>>(h->d_sp, h->tb, h->st, d_obs, h->total_channels);
-  else if (A <= 4) k_obs_direct<4><<<blocks, threads, 0, s>>>(h->d_sp, h->tb, h->st, d_obs, h->total_channels);
-  else if (A <= 8) k_obs_direct<8><<<blocks, threads, 0, s>>>(h->d_sp, h->tb, h->st, d_obs, h->total_channels);
-  else k_obs_direct<16><<<blocks, threads, 0, s>>>(h->d_sp, h->tb, h->st, d_obs, h->total_channels);
-  return cudaGetLastError();
+  // per-thread shared-memory slice of the agent's planes when it is small (odd stride: no bank conflicts between threads)
+  int cmax = 0;
+  for (int a = 0; a < A; ++a) cmax = h->sp.n_channels[a] > cmax ? h->sp.n_channels[a] : cmax;
+  int stride = (cmax * h->DD) | 1;
+  size_t smem = (size_t)stride * threads * sizeof(float);
+  if (smem > 96 * 1024) { stride = 0; smem = 0; }
+  cudaError_t err = cudaSuccess;
+  if (h->obs_kernel != 3 && h->st.blk_i <= 200 * 1024 && h->st.blk_i % 16 == 0) {      // block-staged exact kernel (option 3: the plain one)
+    const unsigned nblk = (unsigned)((h->N + ENV_BLOCK - 1) / ENV_BLOCK);
+    auto gob = [&](auto kern) {
+      if (h->st.blk_i > 48 * 1024) err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->st.blk_i);
+      if (err == cudaSuccess) kern<<<nblk, 256, h->st.blk_i, s>>>(h->d_sp, h->tb, h->st, d_obs, h->total_channels);
+    };
+    if (A <= 1) gob(k_obs_block<1>);
+    else if (A <= 2) gob(k_obs_block<2>);
+    else if (A <= 4) gob(k_obs_block<4>);
+    else if (A <= 8) gob(k_obs_block<8>);
+    else gob(k_obs_block<16>);
+    return err != cudaSuccess ? err : cudaGetLastError();
+  }
+  auto go = [&](auto kern) {
+    if (smem > 48 * 1024) err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err == cudaSuccess) kern<<<blocks, threads, smem, s>>>(h->d_sp, h->tb, h->st, d_obs, h->total_channels, stride);
+  };
+  if (A <= 1) go(k_obs_direct<1>);
+  else if (A <= 2) go(k_obs_direct<2>);
+  else if (A <= 4) go(k_obs_direct<4>);
+  else if (A <= 8) go(k_obs_direct<8>);
+  else go(k_obs_direct<16>);
+  return err != cudaSuccess ? err : cudaGetLastError();
 }
 
 }  // namespace mfg
