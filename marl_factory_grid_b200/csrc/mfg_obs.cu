@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(256, FAITHFUL ? MFG_OBS_CTAS_F : 4) k_obs_tile
   Sprite* s_spr = reinterpret_cast<Sprite*>(wbase + part_bytes);                            // [EPW][cap]
   int* s_cnt = reinterpret_cast<int*>(wbase + part_bytes + (size_t)EPW * cap * 8);          // [EPW]
   unsigned char* misc = smem_raw + sl.prefix_bytes + (size_t)NW * per_warp;
-  unsigned long long* s_cm = reinterpret_cast<unsigned long long*>(misc) + (size_t)warp * 128 + lane;      // [NW][4][32]: word w of this lane = s_cm[w * 32]
+  uint32_t* s_cm = reinterpret_cast<uint32_t*>(misc) + (size_t)warp * 256 + lane;      // [NW][8][32] 32-bit words: word w of this lane = s_cm[w * 32]
   // the per-spec constant "observation program" (built once by plan_obs, see ObsProg): per-agent channel offsets and scalar
   // channels, the wall planes, term -> channel masks, the GlobalPosition encodings x / H, y / W (entity/util.py:56-66)
   uint32_t* s_prog = reinterpret_cast<uint32_t*>(misc + (FAITHFUL ? (size_t)NW * 1024 : 0));
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(256, FAITHFUL ? MFG_OBS_CTAS_F : 4) k_obs_tile
       // faithful mode: the phase-1 results phase 2 needs (wall mask, battery level, position) are handed over through the
       // lane's candidate-mask slots (dead once the lane's classification is done) instead of registers that would have to
       // live across the whole pass (80-register budget for three resident CTAs per SM)
-      if (FAITHFUL && !(a < A && in_range && !lane_skip)) { s_cm[0] = 0ull; s_cm[32] = 0ull; }
+      if (FAITHFUL && !(a < A && in_range && !lane_skip)) { s_cm[0] = 0u; s_cm[32] = 0u; s_cm[64] = 0u; s_cm[96] = 0u; }
       if (a < A && in_range && !lane_skip) {
         const BlkPos pos{blk16, eb};
         const unsigned long long dopen = n_doors ? blk_dopen[eb] : 0ull;
@@ -404,7 +404,8 @@ __global__ void __launch_bounds__(256, FAITHFUL ? MFG_OBS_CTAS_F : 4) k_obs_tile
             cm[w] = (cm[w] & ~(ROW << sh)) | (row << sh);
             if (sh + D > 64) cm[w + 1] = (cm[w + 1] & ~(ROW >> (64 - sh))) | (row >> (64 - sh));
           }
-          s_cm[0] = cm[0]; s_cm[32] = cm[1]; s_cm[64] = cm[2]; s_cm[96] = cm[3];
+#pragma unroll
+          for (int w = 0; w < 4; ++w) { s_cm[(2 * w) * 32] = (uint32_t)cm[w]; s_cm[(2 * w + 1) * 32] = (uint32_t)(cm[w] >> 32); }
         }
         // returns 0 = not a candidate, 1 = candidate on the ring, 3 = visible inside the window (branch-free)
         auto classify = [&](uint16_t q) -> int {
@@ -413,7 +414,7 @@ __global__ void __launch_bounds__(256, FAITHFUL ? MFG_OBS_CTAS_F : 4) k_obs_tile
           if (!FAITHFUL) return (inwin && ((vis >> ((bx + R) * D + by + R)) & 1ull)) ? 3 : 0;
           const bool inbox = (unsigned)(bx + D) < (unsigned)BW && (unsigned)(by + D) < (unsigned)BW;
           const int ci = inbox ? (bx + D) * BW + by + D : 0;
-          const uint32_t bit = (uint32_t)(s_cm[(ci >> 6) * 32] >> (ci & 63)) & 1u;
+          const uint32_t bit = (s_cm[(ci >> 5) * 32] >> (ci & 31)) & 1u;
           return inbox ? (int)(bit | ((inwin ? bit : 0u) << 1)) : 0;
         };
         unsigned long long door_w = 0ull, dirt_w = 0ull, grp_w = 0ull;
@@ -607,7 +608,7 @@ __global__ void __launch_bounds__(256, FAITHFUL ? MFG_OBS_CTAS_F : 4) k_obs_tile
         // the battery level (f64 in HBM) of this (env, agent) lane: Battery channel, written in phase 2
         if (s_hasbat[a]) batv = (float)field_at(st, st.bat, a, e);
         lane_on = true;
-        if (FAITHFUL) { s_cm[0] = wv; s_cm[32] = (unsigned long long)__float_as_uint(batv) | ((unsigned long long)axy << 32); }
+        if (FAITHFUL) { s_cm[0] = (uint32_t)wv; s_cm[32] = (uint32_t)(wv >> 32); s_cm[64] = __float_as_uint(batv); s_cm[96] = axy; }
       }
     }
     __syncwarp();
@@ -643,14 +644,14 @@ __global__ void __launch_bounds__(256, FAITHFUL ? MFG_OBS_CTAS_F : 4) k_obs_tile
       // walls: lane L handles one third (17 / 17 / 15 window cells) of wall plane L / 3 and sets its cells one by one - a
       // handful of iterations for all planes at once (lane = window cell took two predicated stores per plane)
       const int src0 = elx << apad_log2;
-      const unsigned long long* s_res = s_cm - lane;           // faithful: [4][32], word 0 = wall mask, word 1 = battery | position << 32
+      const uint32_t* s_res = s_cm - lane;                     // faithful: [8][32], words 0 / 1 = wall mask, 2 = battery level, 3 = position
       int w_pl = -1, w_base = 0;                                // this lane's wall plane (packed channel index) / first cell
       uint32_t w_bits = 0u;                                     // visible walls among the cells [w_base, w_base + 17)
       {
         const int j = lane / 3, t = lane - 3 * j;
         const uint32_t rec = j < n_wp ? s_wplane[j] : 0u;
         unsigned long long m;
-        if (FAITHFUL) m = s_res[src0 + (int)(rec >> 10)];
+        if (FAITHFUL) m = (unsigned long long)s_res[src0 + (int)(rec >> 10)] | ((unsigned long long)s_res[32 + src0 + (int)(rec >> 10)] << 32);
         else m = (unsigned long long)__shfl_sync(0xffffffffu, wv_lo, src0 + (int)(rec >> 10)) |
                  ((unsigned long long)__shfl_sync(0xffffffffu, wv_hi, src0 + (int)(rec >> 10)) << 32);
         if (j < n_wp) { w_pl = (int)(rec & 1023u); w_base = 17 * t; w_bits = (uint32_t)(m >> w_base) & 0x1FFFFu; }
@@ -665,8 +666,7 @@ __global__ void __launch_bounds__(256, FAITHFUL ? MFG_OBS_CTAS_F : 4) k_obs_tile
         float bv;
         uint32_t pp;
         if (FAITHFUL) {
-          const unsigned long long v = s_res[32 + src0 + (int)(rec >> 16)];
-          bv = __uint_as_float((uint32_t)v); pp = (uint32_t)(v >> 32);
+          bv = __uint_as_float(s_res[64 + src0 + (int)(rec >> 16)]); pp = s_res[96 + src0 + (int)(rec >> 16)];
         } else {
           bv = __shfl_sync(0xffffffffu, batv, src0 + (int)(rec >> 16));
           pp = __shfl_sync(0xffffffffu, axy, src0 + (int)(rec >> 16));
@@ -689,8 +689,12 @@ __global__ void __launch_bounds__(256, FAITHFUL ? MFG_OBS_CTAS_F : 4) k_obs_tile
         {
           float4* t4 = reinterpret_cast<float4*>(tile);
           const int n4 = (nfl + 3) >> 2;
+          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+          int i = lane;
 #pragma unroll 1
-          for (int i = lane; i < n4; i += 32) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (; i + 96 < n4; i += 128) { t4[i] = z; t4[i + 32] = z; t4[i + 64] = z; t4[i + 96] = z; }
+#pragma unroll 1
+          for (; i < n4; i += 32) t4[i] = z;
         }
         if (!resolved) {       // (after the clear has been issued: the dirt amounts had time to arrive)
           resolved = true;
@@ -724,7 +728,7 @@ __global__ void __launch_bounds__(256, FAITHFUL ? MFG_OBS_CTAS_F : 4) k_obs_tile
           const bool valid = L < 3 * n_wp;
           const uint32_t rec = valid ? s_wplane[j] : 0u;
           unsigned long long m;
-          if (FAITHFUL) m = s_res[src0 + (int)(rec >> 10)];
+          if (FAITHFUL) m = (unsigned long long)s_res[src0 + (int)(rec >> 10)] | ((unsigned long long)s_res[32 + src0 + (int)(rec >> 10)] << 32);
           else m = (unsigned long long)__shfl_sync(0xffffffffu, wv_lo, src0 + (int)(rec >> 10)) |
                    ((unsigned long long)__shfl_sync(0xffffffffu, wv_hi, src0 + (int)(rec >> 10)) << 32);
           const int pl = (int)(rec & 1023u);
@@ -744,8 +748,7 @@ __global__ void __launch_bounds__(256, FAITHFUL ? MFG_OBS_CTAS_F : 4) k_obs_tile
             float bv;
             uint32_t pp;
             if (FAITHFUL) {
-              const unsigned long long v = s_res[32 + src0 + (int)(rec >> 16)];
-              bv = __uint_as_float((uint32_t)v); pp = (uint32_t)(v >> 32);
+              bv = __uint_as_float(s_res[64 + src0 + (int)(rec >> 16)]); pp = s_res[96 + src0 + (int)(rec >> 16)];
             } else {
               bv = __shfl_sync(0xffffffffu, batv, src0 + (int)(rec >> 16));
               pp = __shfl_sync(0xffffffffu, axy, src0 + (int)(rec >> 16));
