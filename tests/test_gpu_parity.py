@@ -209,6 +209,28 @@ def test_freerun_steady_state_matches_host_build(cfg, faithful):
 
 
 @pytest.mark.parametrize('faithful', [False, True])
+@pytest.mark.parametrize('cfg', ['eight_puzzle', 'narrow_corridor', 'obs_test', 'cfg2', 'cfg4'])
+def test_exact_kernel_variants_agree_at_scale(cfg, faithful):
+    """The exact per-agent path in its two forms - block-staged state with the first-visit rank table where there is one
+    (obs_kernel 1: the product path of full observability) and plain global state with the ray walk (3) - at a ragged batch
+    size, free-running."""
+    es = spec_for(cfg)
+    N = 1024 + 37
+    eng = _engine(es, N, faithful=faithful, seed=11)
+    eng.reset()
+    acts = torch.zeros((N, es.n_agents), dtype=torch.int32, device='cuda:0')
+    for t in range(24):
+        eng.random_actions(acts, seed=5, step_index=t)
+        eng.step(acts, auto_reset=True)
+        if t % 6 == 5:
+            eng.set_option('obs_kernel', 1)
+            o1 = eng.observe().clone()
+            eng.set_option('obs_kernel', 3)
+            assert torch.equal(o1, eng.observe()), f'{cfg} t={t}: block-staged exact kernel != plain exact kernel'
+    eng.close()
+
+
+@pytest.mark.parametrize('faithful', [False, True])
 @pytest.mark.parametrize('cfg', ['cfg1', 'cfg2', 'cfg4', 'stress'])
 def test_tiled_observation_kernel_equals_direct_kernel_at_scale(cfg, faithful):
     """Size-independent property at a larger batch: both observation kernels produce identical tensors, agents never
