@@ -80,6 +80,17 @@ struct HostTables {
   std::vector<uint16_t> rank_tab;
 };
 
+// light blocking for the rank tables: walls and the closed doors of the subset
+struct RankTabLight {
+  const uint8_t* wall; const uint8_t* door_map; int H, W; uint32_t sub;
+  MFG_HD bool operator()(int xx, int yy) const {
+    if (xx < 0 || yy < 0 || xx >= H || yy >= W) return false;
+    if (wall[(size_t)xx * W + yy]) return true;
+    const int d = door_map[(size_t)xx * W + yy];
+    return d != 0xFF && ((sub >> d) & 1u);
+  }
+};
+
 // first-visit rank tables of the exact observation path (Tables::rank_tab): full observability, at most 4 doors, bounded size.
 // Built with the very ray walk the kernels use (ray_walk, mfg_core.cuh) over every (tile, closed door subset).
 inline void build_rank_table(const MfgSpec& sp, HostTables& t) {
@@ -94,12 +105,7 @@ inline void build_rank_table(const MfgSpec& sp, HostTables& t) {
     for (int y = 0; y < W; ++y) {
       if (t.wall[(size_t)x * W + y]) continue;
       for (size_t sub = 0; sub < nsub; ++sub) {
-        auto blocks = [&](int xx, int yy) -> bool {
-          if (xx < 0 || yy < 0 || xx >= H || yy >= W) return false;
-          if (t.wall[(size_t)xx * W + yy]) return true;
-          const int d = t.door_map[(size_t)xx * W + yy];
-          return d != 0xFF && ((sub >> d) & 1);
-        };
+        const RankTabLight blocks{t.wall.data(), t.door_map.data(), H, W, (uint32_t)sub};
         ray_walk(sp, x, y, R, BW, blocks, &t.rank_tab[(((size_t)x * W + y) * nsub + sub) * cells]);
       }
     }
