@@ -3,20 +3,23 @@
 //
 //   k_obs_tiled<R, FAITHFUL>   CTA = one 128-env state block (its positional prefix staged by one TMA bulk copy), 8 autonomous
 //                warps; both parity modes.  A list mode observes the envs of a device-side id list (re-spawned envs).
-//       phase 1  lane = (env, agent), 32 / A_pad envs per warp pass: 49-bit light-block mask (walls from a per-tile table +
-//                closed doors), ray march over the constexpr window-ray trie (straight-line bit tests, no table loads),
-//                one pass over the listed entities -> visibility masks per class, then every visible in-window entity
+//       phase 1  lane = (env, agent), 32 / A_pad envs per warp pass: window visibility from a per-tile table keyed by the
+//                closed doors of the window (<= 4 doors; else the 49-bit light-block mask + ray march over the constexpr
+//                window-ray trie: straight-line bit tests), one pass over the listed entities -> visibility masks per class, then every visible in-window entity
 //                becomes an 8-byte "sprite" (plane-cell index, kind, value) in shared memory; walls stay a 49-bit mask.
 //                Faithful mode adds the uid de-duplication of `set(visible_entities)`: candidate mask of the radius-D box,
 //                uid conflict masks, first-visit ranks on demand (first_visit_rank).
-//       phase 2  the same warp, one env at a time: zero the env's channel tile in shared memory, expand wall masks, add
-//                sprites (integer stacks first, fractional encodings last => the f64 sums of the reference are reproduced
-//                with one rounding), then ONE TMA bulk store (cp.async.bulk shared -> global) of the 16-byte aligned
-//                tile.  The observation write is 87-93 % of the algorithmic bytes of an env-step.
+//       phase 2  the same warp, one env at a time, `ppp` planes (a part of the tile) at a time: zero the part buffer in
+//                shared memory, set the wall cells (lane = a third of a wall plane), write the scalar channels (lane = list
+//                entry) and the sprites (lanes that hit the same cell are grouped by a warp match: integer stacks first,
+//                fractional encodings last => the f64 sums of the reference are reproduced with one rounding), then ONE TMA
+//                bulk store (cp.async.bulk shared -> global) of the 16-byte aligned part.  The observation write is
+//                87-93 % of the algorithmic bytes of an env-step.  Identity: 64 registers / 53 KB => 4 CTAs per SM.
+//   k_obs_block   exact per-agent path over whole state blocks (slab staged by one bulk copy): full observability and specs
+//                the tiled kernel cannot take; first-visit ranks from a per-(tile, closed-door subset) table when built.
 //   k_obs_redo    exact per-agent path over a device-side env list (sprite / conflict list overflow), columns staged in
 //                shared memory.
-//   k_obs_direct  one thread per (env, agent), every parity mode and full observability (mfg_core.cuh obs_agent_direct);
-//                the checker of the tiled kernel.
+//   k_obs_direct  the same exact path on plain global state, one thread per (env, agent) (obs_kernel option 3).
 #include <utility>
 #include "mfg_internal.hpp"
 #include "mfg_rays_gen.h"
