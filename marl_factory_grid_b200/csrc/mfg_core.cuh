@@ -159,6 +159,21 @@ MFG_HD uint16_t mkpos(int x, int y) { return (uint16_t)((x << 8) | y); }
 MFG_HD int dir_dx(int d) { return d == 0 || d == 4 || d == 7 ? -1 : (d == 2 || d == 5 || d == 6 ? 1 : 0); }
 MFG_HD int dir_dy(int d) { return d == 1 || d == 4 || d == 5 ? 1 : (d == 3 || d == 6 || d == 7 ? -1 : 0); }
 
+// run-time index into a small register-resident array: a select chain instead of a local-memory array (lets the agent
+// loop of env_step stay rolled - one copy of the action code in the instruction stream instead of AMAX)
+template <int N, typename T>
+MFG_HD T sel_get(const T (&a)[N], int i) {
+  T r = a[0];
+  MFG_UNROLL
+  for (int j = 1; j < N; ++j) r = (j == i) ? a[j] : r;
+  return r;
+}
+template <int N, typename T>
+MFG_HD void sel_set(T (&a)[N], int i, T x) {
+  MFG_UNROLL
+  for (int j = 0; j < N; ++j) a[j] = (j == i) ? x : a[j];
+}
+
 // ------------------------------------------------------------------------------------------------
 // Philox4x32-10, counter-based: key = seed ^ global env id, counter = (block, step, episode, stream)
 // ------------------------------------------------------------------------------------------------
@@ -206,8 +221,11 @@ struct Philox {
 // Compact copy of the spec fields the step path reads, small enough to be passed BY VALUE as a kernel parameter
 // (constant bank: uniform reads are broadcast, no L1/L2 round trip).  Member names equal MfgSpec's so that the same
 // templated code runs against either.
-template <int AMAX>
+// STRIDE: envs per row of the staged image the spec is used with (128 = whole block, 32 = one warp's quarter, which also
+// means the combined wall / door map, see Env::is_wall)
+template <int AMAX, int STRIDE_ = ENV_BLOCK>
 struct HotSpec {
+  static constexpr int STRIDE = STRIDE_;
   int32_t H, W, pomdp_r, n_agents, individual_rewards, faithful, n_floor, n_doors, n_walls, has_dirt, dirt_slots,
       dirt_quantity, has_batteries, has_globalpos, n_items, n_dropoff, n_pods, n_dest, n_machines, n_maint, n_rules, n_groups;
   double dirt_initial_amount, dirt_clean_amount, dirt_max_global, dirt_n_var, dirt_amount_var, battery_initial;
@@ -225,8 +243,8 @@ struct HotSpec {
   double act_cost[AMAX][MFG_MAX_ACTIONS + 1];
 };
 
-template <int AMAX>
-inline void fill_hot_spec(const MfgSpec& s, HotSpec<AMAX>& h) {
+template <int AMAX, int STRIDE>
+inline void fill_hot_spec(const MfgSpec& s, HotSpec<AMAX, STRIDE>& h) {
 #define CP(x) h.x = s.x;
   CP(H) CP(W) CP(pomdp_r) CP(n_agents) CP(individual_rewards) CP(faithful) CP(n_floor) CP(n_doors) CP(n_walls) CP(has_dirt)
   CP(dirt_slots) CP(dirt_quantity) CP(has_batteries) CP(has_globalpos) CP(n_items) CP(n_dropoff) CP(n_pods) CP(n_dest)
@@ -255,41 +273,57 @@ inline void fill_hot_spec(const MfgSpec& s, HotSpec<AMAX>& h) {
 
 // k_step runs against a shared-memory image of the block (integer fields) and of the small level tables; telling the
 // compiler so turns the generic loads / stores of that path into LDS / STS.
-template <typename SpecT> struct spec_traits { static constexpr bool staged = false; };
-template <int AMAX> struct spec_traits<HotSpec<AMAX>> { static constexpr bool staged = true; };
-template <bool STAGED, typename T>
-MFG_HD T& in_stage(T& r) {
+template <typename SpecT> struct spec_traits { static constexpr bool staged = false; static constexpr int stride = ENV_BLOCK; };
+template <int AMAX, int STRIDE> struct spec_traits<HotSpec<AMAX, STRIDE>> { static constexpr bool staged = true; static constexpr int stride = STRIDE; };
+constexpr uint8_t CMAP_WALL = 0xFE;      // combined map of the warp-sized step kernel: door index, 0xFE = wall, 0xFF = neither
+// The staged view carries 32-bit OFFSETS in its integer field pointers (built on the host, so they sit in the constant
+// bank): an access is `opaque shared base register + offset + index`, three instructions.  (With generic pointers into
+// the shared image the compiler re-derived the 64-bit address from scratch at every one of the hundreds of access sites.)
+template <typename T>
+MFG_HD T& stage_ref(uint32_t sbase, const T* off, int idx) {
 #if defined(__CUDA_ARCH__)
-  if constexpr (STAGED) __builtin_assume(__isShared(&r));
+  const uint32_t a = sbase + (uint32_t)reinterpret_cast<uintptr_t>(off) + (uint32_t)idx * (uint32_t)sizeof(T);
+  T* p = reinterpret_cast<T*>(__cvta_shared_to_generic(a));
+  __builtin_assume(__isShared(p));
+  return *p;
+#else
+  (void)sbase;
+  return const_cast<T*>(off)[idx];
 #endif
-  return r;
 }
 
 template <int AMAX, typename SpecT = MfgSpec>
 struct Env {
   static constexpr bool STAGED = spec_traits<SpecT>::staged;
+  static constexpr int STRIDE = spec_traits<SpecT>::stride;
+  static constexpr bool CMAP = STAGED && STRIDE != ENV_BLOCK;      // tb.door_map = combined wall / door map, tb.wall unused
   const SpecT& sp;
   const Tables& tb;
   const State& st;
   int64_t e;        // env index inside `st`'s integer region (== eg unless that region was staged into a per-CTA copy)
   int64_t eg;       // global env index: f64 fields (never staged), actions / reward / done, tape, Philox key
+  uint32_t sbase;   // staged view only: shared-memory address of the block image
   int A;
   uint16_t apos[AMAX];
   uint64_t dopen, dlisted, dirt_listed;
   int dirt_end, dirt_n;
 
-  MFG_HD Env(const SpecT& sp_, const Tables& tb_, const State& st_, int64_t e_, int64_t eg_ = -1)
-      : sp(sp_), tb(tb_), st(st_), e(e_), eg(eg_ < 0 ? e_ : eg_) {
+  MFG_HD Env(const SpecT& sp_, const Tables& tb_, const State& st_, int64_t e_, int64_t eg_ = -1, uint32_t sbase_ = 0)
+      : sp(sp_), tb(tb_), st(st_), e(e_), eg(eg_ < 0 ? e_ : eg_), sbase(sbase_) {
     A = sp.n_agents;
     dopen = dlisted = dirt_listed = 0;
     dirt_end = dirt_n = 0;
   }
   template <typename T> MFG_HD T& at(T* base, int row) const {
     if constexpr (std::is_same<T, double>::value) return field_at(st, base, row, eg);
-    else return in_stage<STAGED>(field_at(st, base, row, e));
+    else if constexpr (STAGED) return stage_ref(sbase, base, row * STRIDE + (int)e);
+    else return field_at(st, base, row, e);
   }
   // small level tables (wall map, tile -> door map, door positions): staged copies in k_step
-  template <typename T> MFG_HD T tbl(const T* base, int i) const { return in_stage<STAGED>(base[i]); }
+  template <typename T> MFG_HD T tbl(const T* base, int i) const {
+    if constexpr (STAGED) return stage_ref(sbase, base, i);
+    else return base[i];
+  }
 
   MFG_HD void load() {
 #pragma unroll
@@ -320,7 +354,15 @@ struct Env {
 
   // ---------------------------------------------------------------- tile queries
   MFG_HD bool in_grid(int x, int y) const { return x >= 0 && y >= 0 && x < sp.H && y < sp.W; }
-  MFG_HD int door_at(int x, int y) const { int d = tbl(tb.door_map, x * sp.W + y); return d == 0xFF ? -1 : d; }
+  MFG_HD bool is_wall(int idx) const {
+    if constexpr (CMAP) return tbl(tb.door_map, idx) == CMAP_WALL;
+    else return tbl(tb.wall, idx) != 0;
+  }
+  MFG_HD int door_idx(int idx) const {          // door index of a tile or -1
+    const int d = tbl(tb.door_map, idx);
+    return d >= (CMAP ? (int)CMAP_WALL : 0xFF) ? -1 : d;
+  }
+  MFG_HD int door_at(int x, int y) const { return door_idx(x * sp.W + y); }
   MFG_HD bool closed_listed_door(int x, int y) const {
     if (!sp.n_doors) return false;
     int d = door_at(x, y);
@@ -343,7 +385,7 @@ struct Env {
   }
   // states.py:259-270 check_pos_validity (negated): wall / off-grid / closed listed door / blocking agent
   MFG_HD bool blocked(int x, int y) const {
-    if (!in_grid(x, y) || tbl(tb.wall, x * sp.W + y)) return true;
+    if (!in_grid(x, y) || is_wall(x * sp.W + y)) return true;
     if (closed_listed_door(x, y)) return true;
     uint16_t p = mkpos(x, y);
 #pragma unroll
@@ -353,7 +395,7 @@ struct Env {
   // number of collidable LISTED entities on an in-grid tile: agents, maintainers, closed doors, walls
   MFG_HD int n_coll(int x, int y) const {
     uint16_t p = mkpos(x, y);
-    return agents_at(p) + listed_maints_at(p) + (closed_listed_door(x, y) ? 1 : 0) + (tbl(tb.wall, x * sp.W + y) ? 1 : 0);
+    return agents_at(p) + listed_maints_at(p) + (closed_listed_door(x, y) ? 1 : 0) + (is_wall(x * sp.W + y) ? 1 : 0);
   }
   MFG_HD bool is_free(int x, int y) const { return !blocked(x, y) && n_coll(x, y) == 0; }
 
@@ -679,7 +721,7 @@ MFG_HD void env_reset_inl(const MfgSpec& sp, const Tables& tb, const State& st, 
       int nn = 0;
       for (int d = 0; d < 4; ++d) {                         // POS_MASK_4, restricted to floor tiles
         const int x = px(fp) + dir_dx(d), y = py(fp) + dir_dy(d);
-        if (v.in_grid(x, y) && !v.tbl(tb.wall, x * sp.W + y)) nb[nn++] = mkpos(x, y);
+        if (v.in_grid(x, y) && !v.is_wall(x * sp.W + y)) nb[nn++] = mkpos(x, y);
       }
       if (!nn) continue;
       const uint16_t from = nb[rng.below((uint32_t)nn)];
@@ -759,8 +801,8 @@ MFG_HD int maint_policy(Env<AMAX, SpecT>& v, int k, uint32_t step) {
 // FLAGS: also write the per-agent result flags (StepIO.flags); a compile-time switch so that the plain step does not carry it
 template <int AMAX, typename SpecT, bool FLAGS = true>
 MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, const State& st, int64_t e_local,
-                      const StepIO& io, int64_t eg = -1) {
-  Env<AMAX, SpecT> v(sp, tb, st, e_local, eg);
+                      const StepIO& io, int64_t eg = -1, uint32_t sbase = 0) {
+  Env<AMAX, SpecT> v(sp, tb, st, e_local, eg, sbase);
   const int64_t e = v.eg;            // index into the caller's actions / tape / reward / done buffers
   v.load();
   const int A = v.A;
@@ -776,24 +818,23 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
   // front with independent loads (one round trip instead of a dependent one per use) and keep them in registers.
   double bat[AMAX], epr[AMAX];
   int act[AMAX];
-  bool skipped[AMAX];
+  uint32_t skipmask = 0u;                  // paralysed agents of this step
 #pragma unroll
   for (int i = 0; i < AMAX; ++i) {
-    skipped[i] = false;
     bat[i] = (i < A && sp.has_batteries) ? v.at(st.bat, i) : 1.0;
     epr[i] = i < A ? v.at(st.ep_ret, i) : 0.0;
     act[i] = i < A ? io.actions[(size_t)e * A + i] : 0;
   }
 
   // ---- agents act sequentially against the live state (states.py:189-198)
-#pragma unroll
-  for (int i = 0; i < AMAX; ++i) {
-    if (i >= A) break;
-    if (v.at(st.aflag, i) & 1) { skipped[i] = true; continue; }      // paralysed: skipped entirely
-    int a = act[i];
+  // (rolled: ONE copy of the action code; the per-agent registers are reached through select chains)
+  MFG_NOUNROLL
+  for (int i = 0; i < A; ++i) {
+    if (v.at(st.aflag, i) & 1) { skipmask |= 1u << i; continue; }      // paralysed: skipped entirely
+    int a = sel_get(act, i);
     if (a < 0 || a >= sp.n_actions[i]) a = 0;
     const int op = sp.act_opcode[i][a];
-    const uint16_t p = v.apos[i];
+    const uint16_t p = sel_get(v.apos, i);
     bool ok = false;
     double r_extra = 0.0;
     bool use_extra = false;
@@ -801,7 +842,7 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
       uint16_t t;
       ok = v.try_move(p, sp.act_dir[i][a], sp.agent_blocking[i] != 0, t);
       if (ok) {
-        v.apos[i] = t;
+        sel_set(v.apos, i, t);
         uint32_t c = v.at(st.clock, 0);
         v.at(st.astamp, i) = c;
         v.at(st.clock, 0) = c + 1;
@@ -837,8 +878,8 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
       MFG_NOUNROLL
       for (int k = 0; k < sp.n_pods; ++k) on_pod |= v.at(st.pod_pos, k) == p;
       if (on_pod) {
-        double b = bat[i];
-        if (!(b >= 1.0) && !(v.agents_at(p) > 1)) { bat[i] = fmin(1.0, CHARGE_RATE + b); ok = true; }
+        double b = sel_get(bat, i);
+        if (!(b >= 1.0) && !(v.agents_at(p) > 1)) { sel_set(bat, i, fmin(1.0, CHARGE_RATE + b)); ok = true; }
       }
     } else if (op == MFG_OP_DEST) {                            // destinations/actions.py:17-24 (reference raises on a dest)
       ok = false;
@@ -846,7 +887,9 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
       MFG_NOUNROLL
       for (int k = 0; k < sp.n_machines; ++k) ok |= v.at(st.mach_pos, k) == p;
     }
-    rew[i] += use_extra ? r_extra : (ok ? sp.act_valid[i][a] : sp.act_fail[i][a]);
+    const double r_act = use_extra ? r_extra : (ok ? sp.act_valid[i][a] : sp.act_fail[i][a]);
+#pragma unroll
+    for (int j = 0; j < AMAX; ++j) if (j == i) rew[j] += r_act;
     if (FLAGS && ok) okmask |= 1u << i;
     if (FLAGS && use_extra) auxmask |= 1u << i;
   }
@@ -860,8 +903,8 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
       uint64_t c0 = v.dlisted, c1 = 0;
       auto add = [&](uint16_t q) {
         if (q == NO_POS) return;
-        int d = v.tbl(tb.door_map, px(q) * sp.W + py(q));
-        if (d == 0xFF) return;
+        int d = v.door_idx(px(q) * sp.W + py(q));
+        if (d < 0) return;
         uint64_t b = 1ull << d, carry = c0 & b;
         c0 ^= b;
         uint64_t carry2 = c1 & carry;
@@ -947,7 +990,7 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
         if (P[5] != 0) {                      // per_action_costs as a dict: keyed by the class of the action taken this tick
           int a = act[i];
           if (a < 0 || a >= sp.n_actions[i]) a = 0;
-          cost = sp.act_cost[i][skipped[i] ? sp.n_actions[i] : a];          // a paralysed agent's default state is a 'Noop'
+          cost = sp.act_cost[i][((skipmask >> i) & 1u) ? sp.n_actions[i] : a];          // a paralysed agent's default state is a 'Noop'
         }
         if (bat[i] != 0) bat[i] = fmax(0.0, cost + bat[i]);
       }
@@ -1079,7 +1122,7 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
     uint8_t* f = io.flags + (size_t)e * (A + 1);
 #pragma unroll
     for (int i = 0; i < AMAX; ++i)
-      if (i < A) f[i] = (uint8_t)((((okmask >> i) & 1u) ? MFG_FLAG_VALID : 0) | (skipped[i] ? MFG_FLAG_SKIPPED : 0) |
+      if (i < A) f[i] = (uint8_t)((((okmask >> i) & 1u) ? MFG_FLAG_VALID : 0) | (((skipmask >> i) & 1u) ? MFG_FLAG_SKIPPED : 0) |
                                   (((collmask >> i) & 1u) ? MFG_FLAG_COLLISION : 0) |
                                   (((mcollmask >> i) & 1u) ? MFG_FLAG_MOVE_COLLISION : 0) |
                                   (((auxmask >> i) & 1u) ? MFG_FLAG_AUX_REWARD : 0));
@@ -1115,8 +1158,22 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
       {
         // copies: the call must not make the caller's State / Tables escape (they would then live in local memory and
         // every field access of the hot path would become a dependent local load)
-        const State st2 = st;
-        const Tables tb2 = tb;
+        State st2 = st;
+        Tables tb2 = tb;
+#if defined(__CUDA_ARCH__)
+        if constexpr (Env<AMAX, SpecT>::CMAP) return;     // warp-sized image: launched with the deferred reset list only
+        if constexpr (Env<AMAX, SpecT>::STAGED) {       // offsets of the staged view -> generic pointers into the image
+          char* g = reinterpret_cast<char*>(__cvta_shared_to_generic(v.sbase));
+#define F(type, name, rows_expr) \
+  if constexpr (!std::is_same<type, double>::value) st2.name = reinterpret_cast<type*>(g + reinterpret_cast<uintptr_t>(st.name));
+          MFG_STATE_FIELDS(F)
+#undef F
+          st2.base_i = g;
+          tb2.wall = reinterpret_cast<const uint8_t*>(g + reinterpret_cast<uintptr_t>(tb.wall));
+          tb2.door_map = reinterpret_cast<const uint8_t*>(g + reinterpret_cast<uintptr_t>(tb.door_map));
+          tb2.door_pos = reinterpret_cast<const uint16_t*>(g + reinterpret_cast<uintptr_t>(tb.door_pos));
+        }
+#endif
         env_reset<AMAX>(full, tb2, st2, v.e, v.at(st.episode, 0) + 1, v.eg);
       }
     }

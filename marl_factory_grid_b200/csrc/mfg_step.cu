@@ -82,9 +82,12 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, uint32
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
 }
 
+// `so` = the state view of the shared-memory image: integer field pointers hold byte OFFSETS into the image (see
+// stage_ref), f64 field pointers are the global ones.  Built by launch_step_kernel.
 template <int AMAX, bool FLAGS>
 __global__ void __launch_bounds__(STEP_ENVS, 5) k_step(const __grid_constant__ HotSpec<AMAX> hs, const MfgSpec* __restrict__ full,
-                                                    Tables tb, State st, StepIO io) {
+                                                    const __grid_constant__ Tables tb, const __grid_constant__ State st,
+                                                    const __grid_constant__ State so, const __grid_constant__ StepIO io) {
   extern __shared__ __align__(128) unsigned char stage[];
   __shared__ __align__(8) unsigned long long bar;
   const int el = threadIdx.x;
@@ -109,26 +112,17 @@ __global__ void __launch_bounds__(STEP_ENVS, 5) k_step(const __grid_constant__ H
     for (int i = el; i < HW4; i += STEP_ENVS) { s_wall[i] = gw[i]; s_dmap[i] = gd[i]; }
   }
   if (el < hs.n_doors) s_dpos[el] = tb.door_pos[el];
-  Tables tbs = tb;
-  tbs.wall = reinterpret_cast<const uint8_t*>(s_wall);
-  tbs.door_map = reinterpret_cast<const uint8_t*>(s_dmap);
-  tbs.door_pos = s_dpos;
+  Tables tbs = tb;                  // staged tables: offsets into the image, like the integer fields of `so`
+  tbs.wall = reinterpret_cast<const uint8_t*>((uintptr_t)bytes);
+  tbs.door_map = reinterpret_cast<const uint8_t*>((uintptr_t)bytes + (uintptr_t)HW4 * 4);
+  tbs.door_pos = reinterpret_cast<const uint16_t*>((uintptr_t)bytes + (uintptr_t)HW4 * 8);
+  uint32_t sbase;
+  asm volatile("mov.u32 %0, %1;\n" : "=r"(sbase) : "r"(smem_u32(stage)));      // opaque: kept in ONE register, never re-derived
 
-  // staged view of the state: same field offsets, block 0 == the shared-memory copy
-  State ss = st;
-  ss.N = STEP_ENVS;
-  ss.base_i = reinterpret_cast<char*>(stage);
-  {
-    const char* g0 = st.base_i;
-#define F(type, name, rows_expr) \
-  if constexpr (!std::is_same<type, double>::value) ss.name = reinterpret_cast<type*>(stage + (reinterpret_cast<const char*>(st.name) - g0));
-    MFG_STATE_FIELDS(F)
-#undef F
-  }
   __syncthreads();                  // barrier init + table copies visible
   mbar_wait(&bar, 0);
 
-  if (eg < st.N) env_step<AMAX, HotSpec<AMAX>, FLAGS>(hs, *full, tbs, ss, el, io, eg);
+  if (eg < st.N) env_step<AMAX, HotSpec<AMAX>, FLAGS>(hs, *full, tbs, so, el, io, eg, sbase);
 
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   __syncthreads();
@@ -136,6 +130,57 @@ __global__ void __launch_bounds__(STEP_ENVS, 5) k_step(const __grid_constant__ H
     bulk_s2g(gblock, stage, bytes);
     asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");     // shared memory must outlive the copy
+  }
+}
+
+// k_step_w: the same step with ONE WARP per CTA (a quarter of a state block, 32 envs).  A warp of k_step waits at the
+// CTA barrier for the slowest of 128 lanes before the block is written back, and its registers / shared memory stay
+// allocated until then; here every warp stages, advances and writes back its own 32 columns and retires on its own.  The
+// quarter-block is not contiguous in HBM (row slabs of 128 envs), so it is moved as 16-byte pieces: cp.async in,
+// LDS.128 / STG.128 out, piece -> block offset from a table built at mfg_bind_state (`chunks`).  The image has the block's
+// row order with a 32-env stride, i.e. every field offset is a quarter of the block's.  Wall map and tile -> door map are
+// staged as ONE byte map (CMAP_WALL).
+constexpr int WARP_ENVS = 32;
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst_smem), "l"(src) : "memory");
+}
+template <int AMAX, bool FLAGS>
+__global__ void __launch_bounds__(WARP_ENVS, 18) k_step_w(const __grid_constant__ HotSpec<AMAX, WARP_ENVS> hs, const MfgSpec* __restrict__ full,
+                                                        const __grid_constant__ Tables tb, const __grid_constant__ State st,
+                                                        const __grid_constant__ State so, const __grid_constant__ StepIO io,
+                                                        const uint32_t* __restrict__ chunks, const int n_chunks,
+                                                        const uint8_t* __restrict__ cmap) {
+  extern __shared__ __align__(128) unsigned char stage[];
+  const int lane = threadIdx.x;
+  const uint32_t q = blockIdx.x & 3u;
+  const int64_t eg = (int64_t)blockIdx.x * WARP_ENVS + lane;
+  char* gblock = st.base_i + (size_t)(blockIdx.x >> 2) * st.blk_i;
+  const uint32_t bytes = (uint32_t)(st.blk_i >> 2);
+  uint32_t sbase;
+  asm volatile("mov.u32 %0, %1;\n" : "=r"(sbase) : "r"(smem_u32(stage)));      // opaque: kept in ONE register, never re-derived
+
+  for (int i = lane; i < n_chunks; i += WARP_ENVS) {
+    const uint32_t rec = __ldg(chunks + i);
+    cp_async16(sbase + 16u * i, gblock + (rec & 0x0FFFFFFFu) + ((size_t)q << (5 + (rec >> 28))));
+  }
+  const int HW16 = (hs.H * hs.W + 15) >> 4;                 // (build_tables pads the map to a multiple of 16 bytes)
+  for (int i = lane; i < HW16; i += WARP_ENVS) cp_async16(sbase + bytes + 16u * i, cmap + 16 * i);
+  uint16_t* s_dpos = reinterpret_cast<uint16_t*>(stage + bytes + HW16 * 16);
+  for (int d = lane; d < hs.n_doors; d += WARP_ENVS) s_dpos[d] = tb.door_pos[d];
+  Tables tbs = tb;                  // staged tables: offsets into the image, like the integer fields of `so`
+  tbs.wall = nullptr;
+  tbs.door_map = reinterpret_cast<const uint8_t*>((uintptr_t)bytes);
+  tbs.door_pos = reinterpret_cast<const uint16_t*>((uintptr_t)bytes + (uintptr_t)HW16 * 16);
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
+  __syncwarp();
+
+  if (eg < st.N) env_step<AMAX, HotSpec<AMAX, WARP_ENVS>, FLAGS>(hs, *full, tbs, so, lane, io, eg, sbase);
+
+  __syncwarp();
+  for (int i = lane; i < n_chunks; i += WARP_ENVS) {
+    const uint32_t rec = __ldg(chunks + i);
+    const uint4 v = *reinterpret_cast<const uint4*>(stage + 16 * i);
+    *reinterpret_cast<uint4*>(gblock + (rec & 0x0FFFFFFFu) + ((size_t)q << (5 + (rec >> 28)))) = v;
   }
 }
 
@@ -170,7 +215,33 @@ cudaError_t launch_reset(MfgHandle* h, const uint8_t* d_mask, cudaStream_t s) {
 }
 
 // k_step alone (the deferred auto-reset list is filled but not consumed)
+static cudaError_t launch_step_warp(MfgHandle* h, const StepIO& io, cudaStream_t s) {
+  const unsigned blocks = (unsigned)((h->N + WARP_ENVS - 1) / WARP_ENVS);
+  const size_t hw16 = ((size_t)h->sp.H * h->sp.W + 15) / 16 * 16;
+  const size_t smem = h->st.blk_i / 4 + hw16 + 2 * MFG_MAX_DOORS;
+  cudaError_t err = cudaSuccess;
+  dispatch_amax(h->sp.n_agents, [&](auto amax) {
+    constexpr int AMAX = decltype(amax)::value;
+    auto kern = io.flags ? k_step_w<AMAX, true> : k_step_w<AMAX, false>;
+    HotSpec<AMAX, WARP_ENVS> hs;
+    fill_hot_spec(h->sp, hs);
+    if (smem > 48 * 1024) err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err == cudaSuccess && io.auto_reset && io.reset_list) err = cudaMemsetAsync(io.reset_count, 0, sizeof(uint32_t), s);
+    State so = h->st;                 // offsets into the 32-env image: a quarter of the block's
+    so.N = WARP_ENVS;
+    so.base_i = nullptr;
+#define F(type, name, rows_expr) \
+  if (!std::is_same<type, double>::value) so.name = reinterpret_cast<type*>((reinterpret_cast<char*>(h->st.name) - h->st.base_i) / 4);
+    MFG_STATE_FIELDS(F)
+#undef F
+    if (err == cudaSuccess) kern<<<blocks, WARP_ENVS, smem, s>>>(hs, h->d_sp, h->tb, h->st, so, io, h->d_chunk_tab, h->n_chunk_tab, h->d_cmap);
+  });
+  return err != cudaSuccess ? err : cudaGetLastError();
+}
+
 cudaError_t launch_step_kernel(MfgHandle* h, const StepIO& io, cudaStream_t s) {
+  // one warp per CTA unless the re-spawn has to run inside the step kernel (auto-reset without the deferred list)
+  if (h->step_kernel == 1 && h->d_chunk_tab && !(io.auto_reset && !io.reset_list)) return launch_step_warp(h, io, s);
   const unsigned blocks = (unsigned)((h->N + STEP_ENVS - 1) / STEP_ENVS);
   const size_t hw4 = ((size_t)h->sp.H * h->sp.W + 3) / 4 * 4;
   const size_t smem = h->st.blk_i + 2 * hw4 + 2 * MFG_MAX_DOORS + 16;
@@ -179,10 +250,17 @@ cudaError_t launch_step_kernel(MfgHandle* h, const StepIO& io, cudaStream_t s) {
     constexpr int AMAX = decltype(amax)::value;
     auto kern = io.flags ? k_step<AMAX, true> : k_step<AMAX, false>;
     HotSpec<AMAX> hs;
-    fill_hot_spec<AMAX>(h->sp, hs);
+    fill_hot_spec(h->sp, hs);
     if (smem > 48 * 1024) err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err == cudaSuccess && io.auto_reset && io.reset_list) err = cudaMemsetAsync(io.reset_count, 0, sizeof(uint32_t), s);
-    if (err == cudaSuccess) kern<<<blocks, STEP_ENVS, smem, s>>>(hs, h->d_sp, h->tb, h->st, io);
+    State so = h->st;
+    so.N = STEP_ENVS;
+    so.base_i = nullptr;
+#define F(type, name, rows_expr) \
+  if (!std::is_same<type, double>::value) so.name = reinterpret_cast<type*>(reinterpret_cast<char*>(h->st.name) - h->st.base_i);
+    MFG_STATE_FIELDS(F)
+#undef F
+    if (err == cudaSuccess) kern<<<blocks, STEP_ENVS, smem, s>>>(hs, h->d_sp, h->tb, h->st, so, io);
   });
   return err != cudaSuccess ? err : cudaGetLastError();
 }
