@@ -85,7 +85,7 @@ int mfg_create(const MfgSpec* spec, int64_t n_envs, int64_t env_id_offset, MfgHa
     h->dev_allocs.push_back(d);
     cudaMemcpy(d, cmap.data(), hw16, cudaMemcpyHostToDevice);
     h->d_cmap = static_cast<uint8_t*>(d);
-    if (const char* ev = getenv("MFG_STEP_KERNEL")) h->step_kernel = atoi(ev) != 0;      // development aid (A/B runs)
+    if (const char* ev = getenv("MFG_STEP_KERNEL")) h->step_kernel = atoi(ev);      // development aid (A/B runs)
   }
   if (cudaMalloc(&d, sizeof(unsigned long long) * MFG_N_STATS) != cudaSuccess) { mfg_destroy(h); return fail(MFG_E_NOMEM, "stats alloc"); }
   h->dev_allocs.push_back(d);
@@ -343,7 +343,7 @@ int mfg_set_option(MfgHandle* h, const char* name, int64_t value) {
   if (strcmp(name, "reseed") == 0) { h->ever_reset = false; return MFG_OK; }      // the next full reset starts again at episode 0
   if (strcmp(name, "timing") == 0) { h->timing = value != 0; return MFG_OK; }
   if (strcmp(name, "step_kernel") == 0) {      // 1 = one warp per CTA (k_step_w, default), 0 = one 128-env block per CTA (k_step)
-    h->step_kernel = value != 0;
+    h->step_kernel = (int)value;
     return MFG_OK;
   }
   if (strcmp(name, "obs_store") == 0) {        // 1 = TMA bulk store of the tile (default), 0 = LDS/STG loop

@@ -799,7 +799,19 @@ MFG_HD int maint_policy(Env<AMAX, SpecT>& v, int k, uint32_t step) {
 
 // `sp` may be the full MfgSpec or its compact HotSpec copy; `full` (the MfgSpec) is only read by the in-kernel reset
 // FLAGS: also write the per-agent result flags (StepIO.flags); a compile-time switch so that the plain step does not carry it
-template <int AMAX, typename SpecT, bool FLAGS = true>
+// SYNC (k_step only): CTA barriers at the convergent points of the step - the top of every agent iteration and of every
+// rule-loop iteration - keep the warps of a CTA at the same place in the (long, mostly straight-line) program, so they
+// share instruction-cache lines instead of each streaming the program from L2 on its own.  STEP_SYNC_POINTS = how many
+// barriers one call executes (threads without an env execute the same number).
+#define MFG_STEP_SYNC_POINTS(A, n_rules) ((A) + 3 * (n_rules) + 1)
+template <bool SYNC>
+MFG_HD void step_sync() {
+#if defined(__CUDA_ARCH__)
+  // (per-thread barrier, not the warp-aligned __syncthreads: lanes of a partly filled last warp arrive from elsewhere)
+  if constexpr (SYNC) asm volatile("barrier.sync 0;\n" ::: "memory");
+#endif
+}
+template <int AMAX, typename SpecT, bool FLAGS = true, bool SYNC = false>
 MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, const State& st, int64_t e_local,
                       const StepIO& io, int64_t eg = -1, uint32_t sbase = 0) {
   Env<AMAX, SpecT> v(sp, tb, st, e_local, eg, sbase);
@@ -830,6 +842,7 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
   // (rolled: ONE copy of the action code; the per-agent registers are reached through select chains)
   MFG_NOUNROLL
   for (int i = 0; i < A; ++i) {
+    step_sync<SYNC>();
     if (v.at(st.aflag, i) & 1) { skipmask |= 1u << i; continue; }      // paralysed: skipped entirely
     int a = sel_get(act, i);
     if (a < 0 || a >= sp.n_actions[i]) a = 0;
@@ -896,6 +909,7 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
 
   // ---- tick_step hooks in yaml order (states.py:56-61)
   for (int r = 0; r < sp.n_rules; ++r) {
+    step_sync<SYNC>();
     const int op = sp.rule_op[r];
     const double* P = sp.rule_param[r];
     if (op == MFG_R_DOOR_AUTO_CLOSE) {
@@ -1030,6 +1044,7 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
   // ---- tick_post_step hooks (states.py:70-75)
   int n_collisions = 0;
   for (int r = 0; r < sp.n_rules; ++r) {
+    step_sync<SYNC>();
     const int op = sp.rule_op[r];
     const double* P = sp.rule_param[r];
     if (op == MFG_R_WATCH_COLLISIONS) {                          // rules.py:276-306, states.py:228-238
@@ -1058,6 +1073,7 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
   bool done = false;
   int reason = -1;
   for (int r = 0; r < sp.n_rules; ++r) {
+    step_sync<SYNC>();
     const int op = sp.rule_op[r];
     const double* P = sp.rule_param[r];
     bool fired = false;
@@ -1108,6 +1124,7 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
   // ---- reward fold (factory.py:222-259), individual rewards: agent's own results + the global ones.  The scalar form
   // (individual_rewards: false) does not exist: the reference raises at factory.py:217 (`sum(reward)` of a float) on the
   // first step, so mfg_create rejects such a spec.
+  step_sync<SYNC>();
 #pragma unroll
   for (int i = 0; i < AMAX; ++i) {
     if (i < A) {

@@ -84,50 +84,54 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, uint32
 
 // `so` = the state view of the shared-memory image: integer field pointers hold byte OFFSETS into the image (see
 // stage_ref), f64 field pointers are the global ones.  Built by launch_step_kernel.
-template <int AMAX, bool FLAGS>
-__global__ void __launch_bounds__(STEP_ENVS, 5) k_step(const __grid_constant__ HotSpec<AMAX> hs, const MfgSpec* __restrict__ full,
-                                                    const __grid_constant__ Tables tb, const __grid_constant__ State st,
-                                                    const __grid_constant__ State so, const __grid_constant__ StepIO io) {
+// NB = state blocks per CTA (128 threads each, own image); SYNC = barriers at the step's convergent points (env_step).
+template <int AMAX, bool FLAGS, int NB, bool SYNC>
+__global__ void __launch_bounds__(STEP_ENVS * NB, NB == 1 ? 5 : NB == 2 ? 2 : 1)
+k_step(const __grid_constant__ HotSpec<AMAX> hs, const MfgSpec* __restrict__ full, const __grid_constant__ Tables tb,
+       const __grid_constant__ State st, const __grid_constant__ State so, const __grid_constant__ StepIO io, const int n_blocks) {
   extern __shared__ __align__(128) unsigned char stage[];
   __shared__ __align__(8) unsigned long long bar;
-  const int el = threadIdx.x;
-  const int64_t e0 = (int64_t)blockIdx.x * STEP_ENVS, eg = e0 + el;
-  char* gblock = st.base_i + (size_t)blockIdx.x * st.blk_i;
+  const int t = threadIdx.x, g = NB == 1 ? 0 : t >> 7, el = t & (STEP_ENVS - 1);
+  const int b0 = blockIdx.x * NB, nb_here = n_blocks - b0 < NB ? n_blocks - b0 : NB;       // state blocks of this CTA
+  const int64_t eg = (int64_t)(b0 + g) * STEP_ENVS + el;
+  char* gblock = st.base_i + (size_t)b0 * st.blk_i;
   const uint32_t bytes = (uint32_t)st.blk_i;
 
-  if (el == 0) {
+  if (t == 0) {
     mbar_init(&bar, 1);
-    mbar_expect_tx(&bar, bytes);
-    bulk_g2s(stage, gblock, bytes, &bar);
+    mbar_expect_tx(&bar, bytes * nb_here);
+    for (int k = 0; k < nb_here; ++k) bulk_g2s(stage + (size_t)k * bytes, gblock + (size_t)k * bytes, bytes, &bar);
   }
   // level tables the step touches with divergent indices: wall map, tile -> door map, door positions.  With most of
   // the SM's unified cache carved out as shared memory they would otherwise be L2 round trips.
   const int HW = hs.H * hs.W, HW4 = (HW + 3) >> 2;
-  uint32_t* s_wall = reinterpret_cast<uint32_t*>(stage + bytes);
+  uint32_t* s_wall = reinterpret_cast<uint32_t*>(stage + (size_t)NB * bytes);
   uint32_t* s_dmap = s_wall + HW4;
   uint16_t* s_dpos = reinterpret_cast<uint16_t*>(s_dmap + HW4);
   {   // 32-bit copies (build_tables pads both tables to a multiple of 4 bytes)
     const uint32_t* gw = reinterpret_cast<const uint32_t*>(tb.wall);
     const uint32_t* gd = reinterpret_cast<const uint32_t*>(tb.door_map);
-    for (int i = el; i < HW4; i += STEP_ENVS) { s_wall[i] = gw[i]; s_dmap[i] = gd[i]; }
+    for (int i = t; i < HW4; i += STEP_ENVS * NB) { s_wall[i] = gw[i]; s_dmap[i] = gd[i]; }
   }
-  if (el < hs.n_doors) s_dpos[el] = tb.door_pos[el];
-  Tables tbs = tb;                  // staged tables: offsets into the image, like the integer fields of `so`
-  tbs.wall = reinterpret_cast<const uint8_t*>((uintptr_t)bytes);
-  tbs.door_map = reinterpret_cast<const uint8_t*>((uintptr_t)bytes + (uintptr_t)HW4 * 4);
-  tbs.door_pos = reinterpret_cast<const uint16_t*>((uintptr_t)bytes + (uintptr_t)HW4 * 8);
+  if (t < hs.n_doors) s_dpos[t] = tb.door_pos[t];
+  Tables tbs = tb;                  // staged tables: offsets relative to the thread's image, like the integer fields of `so`
+  const uintptr_t toff = (uintptr_t)(NB - g) * bytes;
+  tbs.wall = reinterpret_cast<const uint8_t*>(toff);
+  tbs.door_map = reinterpret_cast<const uint8_t*>(toff + (uintptr_t)HW4 * 4);
+  tbs.door_pos = reinterpret_cast<const uint16_t*>(toff + (uintptr_t)HW4 * 8);
   uint32_t sbase;
-  asm volatile("mov.u32 %0, %1;\n" : "=r"(sbase) : "r"(smem_u32(stage)));      // opaque: kept in ONE register, never re-derived
+  asm volatile("mov.u32 %0, %1;\n" : "=r"(sbase) : "r"(smem_u32(stage) + (uint32_t)g * bytes));      // opaque: kept in ONE register, never re-derived
 
   __syncthreads();                  // barrier init + table copies visible
   mbar_wait(&bar, 0);
 
-  if (eg < st.N) env_step<AMAX, HotSpec<AMAX>, FLAGS>(hs, *full, tbs, so, el, io, eg, sbase);
+  if (eg < st.N) env_step<AMAX, HotSpec<AMAX>, FLAGS, SYNC>(hs, *full, tbs, so, el, io, eg, sbase);
+  else if (SYNC) { for (int k = MFG_STEP_SYNC_POINTS(hs.n_agents, hs.n_rules); k > 0; --k) step_sync<true>(); }
 
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   __syncthreads();
-  if (el == 0) {
-    bulk_s2g(gblock, stage, bytes);
+  if (t == 0) {
+    for (int k = 0; k < nb_here; ++k) bulk_s2g(gblock + (size_t)k * bytes, stage + (size_t)k * bytes, bytes);
     asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");     // shared memory must outlive the copy
   }
@@ -242,17 +246,14 @@ static cudaError_t launch_step_warp(MfgHandle* h, const StepIO& io, cudaStream_t
 cudaError_t launch_step_kernel(MfgHandle* h, const StepIO& io, cudaStream_t s) {
   // one warp per CTA unless the re-spawn has to run inside the step kernel (auto-reset without the deferred list)
   if (h->step_kernel == 1 && h->d_chunk_tab && !(io.auto_reset && !io.reset_list)) return launch_step_warp(h, io, s);
-  const unsigned blocks = (unsigned)((h->N + STEP_ENVS - 1) / STEP_ENVS);
+  const int n_blocks = (int)((h->N + STEP_ENVS - 1) / STEP_ENVS);
   const size_t hw4 = ((size_t)h->sp.H * h->sp.W + 3) / 4 * 4;
-  const size_t smem = h->st.blk_i + 2 * hw4 + 2 * MFG_MAX_DOORS + 16;
   cudaError_t err = cudaSuccess;
   dispatch_amax(h->sp.n_agents, [&](auto amax) {
     constexpr int AMAX = decltype(amax)::value;
-    auto kern = io.flags ? k_step<AMAX, true> : k_step<AMAX, false>;
     HotSpec<AMAX> hs;
     fill_hot_spec(h->sp, hs);
-    if (smem > 48 * 1024) err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err == cudaSuccess && io.auto_reset && io.reset_list) err = cudaMemsetAsync(io.reset_count, 0, sizeof(uint32_t), s);
+    if (io.auto_reset && io.reset_list) err = cudaMemsetAsync(io.reset_count, 0, sizeof(uint32_t), s);
     State so = h->st;
     so.N = STEP_ENVS;
     so.base_i = nullptr;
@@ -260,7 +261,19 @@ cudaError_t launch_step_kernel(MfgHandle* h, const StepIO& io, cudaStream_t s) {
   if (!std::is_same<type, double>::value) so.name = reinterpret_cast<type*>(reinterpret_cast<char*>(h->st.name) - h->st.base_i);
     MFG_STATE_FIELDS(F)
 #undef F
-    if (err == cudaSuccess) kern<<<blocks, STEP_ENVS, smem, s>>>(hs, h->d_sp, h->tb, h->st, so, io);
+    auto go = [&](auto kern, int nb) {
+      const size_t smem = (size_t)nb * h->st.blk_i + 2 * hw4 + 2 * MFG_MAX_DOORS + 16;
+      if (err == cudaSuccess && smem > 48 * 1024) err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (err == cudaSuccess) kern<<<(unsigned)((n_blocks + nb - 1) / nb), STEP_ENVS * nb, smem, s>>>(hs, h->d_sp, h->tb, h->st, so, io, n_blocks);
+    };
+    // step_kernel: 0 = one block per CTA; 2 = the same with barriers at the convergent points; 3 = five blocks per CTA
+    // (one CTA per SM, all 20 warps kept together by the barriers)
+    constexpr int NBIG = 5;
+    const bool big_fits = (size_t)NBIG * h->st.blk_i + 2 * hw4 + 2 * MFG_MAX_DOORS + 16 <= 227 * 1024;
+    if (h->step_kernel == 4) { if (io.flags) go(k_step<AMAX, true, 2, true>, 2); else go(k_step<AMAX, false, 2, true>, 2); }
+    else if (h->step_kernel == 3 && big_fits) { if (io.flags) go(k_step<AMAX, true, NBIG, true>, NBIG); else go(k_step<AMAX, false, NBIG, true>, NBIG); }
+    else if (h->step_kernel >= 2) { if (io.flags) go(k_step<AMAX, true, 1, true>, 1); else go(k_step<AMAX, false, 1, true>, 1); }
+    else { if (io.flags) go(k_step<AMAX, true, 1, false>, 1); else go(k_step<AMAX, false, 1, false>, 1); }
   });
   return err != cudaSuccess ? err : cudaGetLastError();
 }
