@@ -77,16 +77,7 @@ int mfg_create(const MfgSpec* spec, int64_t n_envs, int64_t env_id_offset, MfgHa
 #undef UP
   h->tb.env_id_offset = env_id_offset;
   void* d = nullptr;
-  {   // k_step_w: wall map and tile -> door map as one byte map (padded to whole 16-byte pieces)
-    const size_t hw = (size_t)spec->H * spec->W, hw16 = (hw + 15) / 16 * 16;
-    std::vector<uint8_t> cmap(hw16, 0xFF);
-    for (size_t i = 0; i < hw; ++i) cmap[i] = ht.wall[i] ? mfg::CMAP_WALL : ht.door_map[i];
-    if (cudaMalloc(&d, hw16) != cudaSuccess) { mfg_destroy(h); return fail(MFG_E_NOMEM, "cmap alloc"); }
-    h->dev_allocs.push_back(d);
-    cudaMemcpy(d, cmap.data(), hw16, cudaMemcpyHostToDevice);
-    h->d_cmap = static_cast<uint8_t*>(d);
-    if (const char* ev = getenv("MFG_STEP_KERNEL")) h->step_kernel = atoi(ev);      // development aid (A/B runs)
-  }
+  if (const char* ev = getenv("MFG_STEP_KERNEL")) h->step_kernel = atoi(ev);      // development aid (A/B runs)
   if (cudaMalloc(&d, sizeof(unsigned long long) * MFG_N_STATS) != cudaSuccess) { mfg_destroy(h); return fail(MFG_E_NOMEM, "stats alloc"); }
   h->dev_allocs.push_back(d);
   cudaMemset(d, 0, sizeof(unsigned long long) * MFG_N_STATS);
@@ -121,7 +112,6 @@ void mfg_destroy(MfgHandle* h) {
   if (h->d_redo) cudaFree(h->d_redo);
   if (h->d_obs_prog) cudaFree(h->d_obs_prog);
   if (h->d_row_tab) cudaFree(h->d_row_tab);
-  if (h->d_chunk_tab) cudaFree(h->d_chunk_tab);
   drain_ns(h->t_step); drain_ns(h->t_obs); drain_ns(h->t_reset);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -157,17 +147,6 @@ int mfg_bind_state(MfgHandle* h, void* d_state) {
     h->row_tab_host = rows;
     CUDA_TRY(cudaMalloc(&h->d_row_tab, rows.size() * sizeof(uint32_t)));
     CUDA_TRY(cudaMemcpy(h->d_row_tab, rows.data(), rows.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    // k_step_w: the 32-env image keeps the row order (row r at a quarter of its block offset); 16-byte piece -> block offset
-    std::vector<uint32_t> chunks;
-    for (uint32_t rec : rows) {
-      const uint32_t off = rec & 0x0FFFFFFFu, lg = rec >> 28;
-      for (uint32_t c = 0; c < (32u << lg); c += 16) chunks.push_back((off + c) | (lg << 28));
-    }
-    h->n_chunk_tab = (int)chunks.size();
-    if ((size_t)h->n_chunk_tab * 16 == h->st.blk_i / 4) {          // rows are packed back to back (always, by compute_layout)
-      CUDA_TRY(cudaMalloc(&h->d_chunk_tab, chunks.size() * sizeof(uint32_t)));
-      CUDA_TRY(cudaMemcpy(h->d_chunk_tab, chunks.data(), chunks.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    }
   }
   h->bound = true;
   return MFG_OK;
@@ -342,7 +321,7 @@ int mfg_set_option(MfgHandle* h, const char* name, int64_t value) {
   if (strcmp(name, "overlap_reset") == 0) { h->overlap_reset = value != 0; return MFG_OK; }
   if (strcmp(name, "reseed") == 0) { h->ever_reset = false; return MFG_OK; }      // the next full reset starts again at episode 0
   if (strcmp(name, "timing") == 0) { h->timing = value != 0; return MFG_OK; }
-  if (strcmp(name, "step_kernel") == 0) {      // 1 = one warp per CTA (k_step_w, default), 0 = one 128-env block per CTA (k_step)
+  if (strcmp(name, "step_kernel") == 0) {      // 1 = barriers + dirt uids left in HBM (default), 2 = barriers only, 0 = neither
     h->step_kernel = (int)value;
     return MFG_OK;
   }

@@ -221,11 +221,10 @@ struct Philox {
 // Compact copy of the spec fields the step path reads, small enough to be passed BY VALUE as a kernel parameter
 // (constant bank: uniform reads are broadcast, no L1/L2 round trip).  Member names equal MfgSpec's so that the same
 // templated code runs against either.
-// STRIDE: envs per row of the staged image the spec is used with (128 = whole block, 32 = one warp's quarter, which also
-// means the combined wall / door map, see Env::is_wall)
-template <int AMAX, int STRIDE_ = ENV_BLOCK>
+// UIDG: the staged image the spec is used with leaves the dirt-uid rows in global memory (see k_step)
+template <int AMAX, bool UIDG_ = false>
 struct HotSpec {
-  static constexpr int STRIDE = STRIDE_;
+  static constexpr bool UIDG = UIDG_;
   int32_t H, W, pomdp_r, n_agents, individual_rewards, faithful, n_floor, n_doors, n_walls, has_dirt, dirt_slots,
       dirt_quantity, has_batteries, has_globalpos, n_items, n_dropoff, n_pods, n_dest, n_machines, n_maint, n_rules, n_groups;
   double dirt_initial_amount, dirt_clean_amount, dirt_max_global, dirt_n_var, dirt_amount_var, battery_initial;
@@ -243,8 +242,8 @@ struct HotSpec {
   double act_cost[AMAX][MFG_MAX_ACTIONS + 1];
 };
 
-template <int AMAX, int STRIDE>
-inline void fill_hot_spec(const MfgSpec& s, HotSpec<AMAX, STRIDE>& h) {
+template <int AMAX, bool UIDG>
+inline void fill_hot_spec(const MfgSpec& s, HotSpec<AMAX, UIDG>& h) {
 #define CP(x) h.x = s.x;
   CP(H) CP(W) CP(pomdp_r) CP(n_agents) CP(individual_rewards) CP(faithful) CP(n_floor) CP(n_doors) CP(n_walls) CP(has_dirt)
   CP(dirt_slots) CP(dirt_quantity) CP(has_batteries) CP(has_globalpos) CP(n_items) CP(n_dropoff) CP(n_pods) CP(n_dest)
@@ -273,9 +272,8 @@ inline void fill_hot_spec(const MfgSpec& s, HotSpec<AMAX, STRIDE>& h) {
 
 // k_step runs against a shared-memory image of the block (integer fields) and of the small level tables; telling the
 // compiler so turns the generic loads / stores of that path into LDS / STS.
-template <typename SpecT> struct spec_traits { static constexpr bool staged = false; static constexpr int stride = ENV_BLOCK; };
-template <int AMAX, int STRIDE> struct spec_traits<HotSpec<AMAX, STRIDE>> { static constexpr bool staged = true; static constexpr int stride = STRIDE; };
-constexpr uint8_t CMAP_WALL = 0xFE;      // combined map of the warp-sized step kernel: door index, 0xFE = wall, 0xFF = neither
+template <typename SpecT> struct spec_traits { static constexpr bool staged = false; static constexpr bool uid_global = false; };
+template <int AMAX, bool UIDG> struct spec_traits<HotSpec<AMAX, UIDG>> { static constexpr bool staged = true; static constexpr bool uid_global = UIDG; };
 // The staged view carries 32-bit OFFSETS in its integer field pointers (built on the host, so they sit in the constant
 // bank): an access is `opaque shared base register + offset + index`, three instructions.  (With generic pointers into
 // the shared image the compiler re-derived the 64-bit address from scratch at every one of the hundreds of access sites.)
@@ -295,8 +293,7 @@ MFG_HD T& stage_ref(uint32_t sbase, const T* off, int idx) {
 template <int AMAX, typename SpecT = MfgSpec>
 struct Env {
   static constexpr bool STAGED = spec_traits<SpecT>::staged;
-  static constexpr int STRIDE = spec_traits<SpecT>::stride;
-  static constexpr bool CMAP = STAGED && STRIDE != ENV_BLOCK;      // tb.door_map = combined wall / door map, tb.wall unused
+  static constexpr bool UIDG = spec_traits<SpecT>::uid_global;     // st.dirt_uid is the global slab (indexed by eg), not part of the image
   const SpecT& sp;
   const Tables& tb;
   const State& st;
@@ -316,7 +313,7 @@ struct Env {
   }
   template <typename T> MFG_HD T& at(T* base, int row) const {
     if constexpr (std::is_same<T, double>::value) return field_at(st, base, row, eg);
-    else if constexpr (STAGED) return stage_ref(sbase, base, row * STRIDE + (int)e);
+    else if constexpr (STAGED) return stage_ref(sbase, base, row * ENV_BLOCK + (int)e);
     else return field_at(st, base, row, e);
   }
   // small level tables (wall map, tile -> door map, door positions): staged copies in k_step
@@ -354,13 +351,15 @@ struct Env {
 
   // ---------------------------------------------------------------- tile queries
   MFG_HD bool in_grid(int x, int y) const { return x >= 0 && y >= 0 && x < sp.H && y < sp.W; }
-  MFG_HD bool is_wall(int idx) const {
-    if constexpr (CMAP) return tbl(tb.door_map, idx) == CMAP_WALL;
-    else return tbl(tb.wall, idx) != 0;
+  // dirt uids: rarely touched (uid listing in faithful mode, create / compact), so k_step keeps their rows out of its image
+  MFG_HD uint16_t& uid_at(int k) const {
+    if constexpr (UIDG) return field_at(st, st.dirt_uid, k, eg);
+    else return at(st.dirt_uid, k);
   }
+  MFG_HD bool is_wall(int idx) const { return tbl(tb.wall, idx) != 0; }
   MFG_HD int door_idx(int idx) const {          // door index of a tile or -1
     const int d = tbl(tb.door_map, idx);
-    return d >= (CMAP ? (int)CMAP_WALL : 0xFF) ? -1 : d;
+    return d == 0xFF ? -1 : d;
   }
   MFG_HD int door_at(int x, int y) const { return door_idx(x * sp.W + y); }
   MFG_HD bool closed_listed_door(int x, int y) const {
@@ -400,14 +399,19 @@ struct Env {
   MFG_HD bool is_free(int x, int y) const { return !blocked(x, y) && n_coll(x, y) == 0; }
 
   // ---------------------------------------------------------------- uid listing (objects.py:193-214)
-  MFG_HD bool find_listed(int uid, uint16_t p, int& cls, int& idx) const {
+  // own_dirt: the query is for the uid of a dirt pile itself.  Dirt uids are unique among the piles, so the pile part of
+  // the search is then known without a scan: k >= 0 = only slot k can match (dirt_delete), -1 = a fresh uid matches no
+  // pile (dirt_create); -2 = some other entity's uid: scan.
+  MFG_HD bool find_listed(int uid, uint16_t p, int& cls, int& idx, int own_dirt = -2) const {
     if (uid < sp.n_doors && tbl(tb.door_pos, uid) == p && ((dlisted >> uid) & 1)) { cls = C_DOOR; idx = uid; return true; }
-    if (sp.has_dirt && uid < (int)at(st.dirt_next_uid, 0)) {
+    if (own_dirt >= 0) {
+      if ((dirt_listed >> own_dirt) & 1) { cls = C_DIRT; idx = own_dirt; return true; }
+    } else if (own_dirt == -2 && sp.has_dirt && uid < (int)at(st.dirt_next_uid, 0)) {
       // slots are in creation order and uids only grow (deleted slots keep theirs, compaction keeps the order), so the
       // scan can stop at the first larger uid - the uids asked for (maintainers, items, doors ...) are small
       MFG_NOUNROLL
       for (int k = 0; k < dirt_end; ++k) {
-        const int du = at(st.dirt_uid, k);
+        const int du = uid_at(k);
         if (du > uid) break;
         if (du == uid && at(st.dirt_pos, k) == p && ((dirt_listed >> k) & 1)) { cls = C_DIRT; idx = k; return true; }
       }
@@ -423,15 +427,15 @@ struct Env {
     else if (cls == C_DIRT) dirt_listed = v ? (dirt_listed | (1ull << idx)) : (dirt_listed & ~(1ull << idx));
     else { uint32_t& l = at(cls_listed(cls), 0); l = v ? (l | (1u << idx)) : (l & ~(1u << idx)); }
   }
-  MFG_HD void l_add(int cls, int idx, int uid, uint16_t p) {
+  MFG_HD void l_add(int cls, int idx, int uid, uint16_t p, int own_dirt = -2) {
     int c2, i2;
-    if (sp.faithful && find_listed(uid, p, c2, i2)) set_listed(cls, idx, false);
+    if (sp.faithful && find_listed(uid, p, c2, i2, own_dirt)) set_listed(cls, idx, false);
     else set_listed(cls, idx, true);
   }
-  MFG_HD void l_del(int cls, int idx, int uid, uint16_t p) {
+  MFG_HD void l_del(int cls, int idx, int uid, uint16_t p, int own_dirt = -2) {
     if (sp.faithful) {
       int c2, i2;
-      if (find_listed(uid, p, c2, i2)) set_listed(c2, i2, false);
+      if (find_listed(uid, p, c2, i2, own_dirt)) set_listed(c2, i2, false);
     } else {
       set_listed(cls, idx, false);
     }
@@ -482,7 +486,7 @@ struct Env {
     for (int k = 0; k < dirt_end; ++k) {
       uint16_t p = at(st.dirt_pos, k);
       if (p == NO_POS) continue;
-      if (w != k) { at(st.dirt_pos, w) = p; at(st.dirt_amt, w) = at(st.dirt_amt, k); at(st.dirt_uid, w) = at(st.dirt_uid, k); }
+      if (w != k) { at(st.dirt_pos, w) = p; at(st.dirt_amt, w) = at(st.dirt_amt, k); uid_at(w) = uid_at(k); }
       if ((dirt_listed >> k) & 1) nl |= 1ull << w;
       ++w;
     }
@@ -503,12 +507,12 @@ struct Env {
       return;
     }
     int k = dirt_end++;
-    at(st.dirt_pos, k) = p; at(st.dirt_amt, k) = amount; at(st.dirt_uid, k) = uid;
+    at(st.dirt_pos, k) = p; at(st.dirt_amt, k) = amount; uid_at(k) = uid;
     ++dirt_n;
-    l_add(C_DIRT, k, uid, p);
+    l_add(C_DIRT, k, uid, p, -1);
   }
   MFG_HD void dirt_delete(int k) {
-    l_del(C_DIRT, k, at(st.dirt_uid, k), at(st.dirt_pos, k));
+    l_del(C_DIRT, k, sp.faithful ? (int)uid_at(k) : 0, at(st.dirt_pos, k), k);
     dirt_listed &= ~(1ull << k);
     at(st.dirt_pos, k) = NO_POS;
     --dirt_n;
@@ -803,7 +807,18 @@ MFG_HD int maint_policy(Env<AMAX, SpecT>& v, int k, uint32_t step) {
 // rule-loop iteration - keep the warps of a CTA at the same place in the (long, mostly straight-line) program, so they
 // share instruction-cache lines instead of each streaming the program from L2 on its own.  STEP_SYNC_POINTS = how many
 // barriers one call executes (threads without an env execute the same number).
-#define MFG_STEP_SYNC_POINTS(A, n_rules) ((A) + 3 * (n_rules) + 1)
+#ifndef MFG_STEP_SYNC_FINE
+#define MFG_STEP_SYNC_FINE 1           // 1 = more barriers inside the agent iteration, DoorAutoClose and MoveMaintainers
+#endif
+// number of barriers one env_step<SYNC = true> call executes (threads of a partly filled block execute the same number)
+template <typename SpecT>
+MFG_HD int step_sync_points(const SpecT& sp) {
+  int n = sp.n_agents + 3 * sp.n_rules + 1;
+  if (MFG_STEP_SYNC_FINE)
+    for (int r = 0; r < sp.n_rules; ++r)
+      n += sp.rule_op[r] == MFG_R_DOOR_AUTO_CLOSE ? 2 : sp.rule_op[r] == MFG_R_MOVE_MAINTAINERS ? sp.n_maint : 0;
+  return n;
+}
 template <bool SYNC>
 MFG_HD void step_sync() {
 #if defined(__CUDA_ARCH__)
@@ -927,6 +942,7 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
       };
 #pragma unroll
       for (int i = 0; i < AMAX; ++i) if (i < A) add(v.apos[i]);
+      step_sync<SYNC && MFG_STEP_SYNC_FINE>();
       if (sp.has_dirt) for (int k = 0; k < v.dirt_end; ++k) if ((v.dirt_listed >> k) & 1) add(v.at(st.dirt_pos, k));
       MFG_UNROLL
       for (int c = C_ITEM; c <= C_MAINT; ++c) {
@@ -938,6 +954,7 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
       }
       // count n = c0 + 2 c1 (saturating at 3).  Only open doors (count down / close) and crowded tiles (n = 3: timer
       // reset) change state, so only those doors are visited.
+      step_sync<SYNC && MFG_STEP_SYNC_FINE>();
       const uint64_t all = sp.n_doors >= 64 ? ~0ull : ((1ull << sp.n_doors) - 1ull);
       const uint64_t crowded = c0 & c1 & all;
       for (uint64_t m = (v.dopen | crowded) & all; m; m &= m - 1) {
@@ -953,6 +970,7 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
     } else if (op == MFG_R_MOVE_MAINTAINERS) {
       for (int k = 0; k < sp.n_maint; ++k) {
         int code = io.maint_act ? (int)io.maint_act[(size_t)e * sp.n_maint + k] : maint_policy<AMAX, SpecT>(v, k, (uint32_t)step);
+        step_sync<SYNC && MFG_STEP_SYNC_FINE>();
         uint16_t p = v.at(st.maint_pos, k);
         if (code < 8) {
           uint16_t t;
@@ -1178,7 +1196,7 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
         State st2 = st;
         Tables tb2 = tb;
 #if defined(__CUDA_ARCH__)
-        if constexpr (Env<AMAX, SpecT>::CMAP) return;     // warp-sized image: launched with the deferred reset list only
+        if constexpr (Env<AMAX, SpecT>::UIDG) return;     // split image: launched with the deferred reset list only
         if constexpr (Env<AMAX, SpecT>::STAGED) {       // offsets of the staged view -> generic pointers into the image
           char* g = reinterpret_cast<char*>(__cvta_shared_to_generic(v.sbase));
 #define F(type, name, rows_expr) \
@@ -1264,7 +1282,7 @@ MFG_HD bool uid_shadowed(const ObsCtx<AMAX>& o, int cls, int idx, int uid, int m
   if (sp.has_dirt && uid < (int)v.at(st.dirt_next_uid, 0)) {
     for (int k = 0; k < v.dirt_end; ++k) {
       if (cls == C_DIRT && k == idx) continue;
-      if (v.at(st.dirt_uid, k) == uid && ((v.dirt_listed >> k) & 1) && o.rank_of(v.at(st.dirt_pos, k)) < my_rank) return true;
+      if (v.uid_at(k) == uid && ((v.dirt_listed >> k) & 1) && o.rank_of(v.at(st.dirt_pos, k)) < my_rank) return true;
     }
   }
   for (int c = C_ITEM; c <= C_MAINT; ++c) {
@@ -1330,7 +1348,7 @@ MFG_HDN void obs_agent_exact(const MfgSpec& sp, const Tables& tb, const State& s
         if (uid < sp.n_doors && ((v.dlisted >> uid) & 1) && o.rank_of(v.tbl(tb.door_pos, uid)) < rk) sh = true;
         if (!sh && sp.has_dirt && uid < (int)v.at(st.dirt_next_uid, 0))
           for (int k = 0; k < v.dirt_end && !sh; ++k)
-            sh = v.at(st.dirt_uid, k) == uid && ((v.dirt_listed >> k) & 1) && o.rank_of(v.at(st.dirt_pos, k)) < rk;
+            sh = v.uid_at(k) == uid && ((v.dirt_listed >> k) & 1) && o.rank_of(v.at(st.dirt_pos, k)) < rk;
         if (uid < max_small)                  // (most walls have a larger uid than any small group has members)
           for (int c = C_ITEM; c <= C_MAINT && !sh; ++c)
             sh = uid < v.cls_count(c) && ((v.at(v.cls_listed(c), 0) >> uid) & 1) && o.rank_of(v.at(v.cls_pos(c), uid)) < rk;
@@ -1384,7 +1402,7 @@ MFG_HDN void obs_agent_exact(const MfgSpec& sp, const Tables& tb, const State& s
       if (p == NO_POS || !((v.dirt_listed >> k) & 1) || !in_window(p, cell)) continue;
       int rk = o.rank_of(p);
       if (rk == RANK_INF) continue;
-      if (sp.faithful && uid_shadowed(o, C_DIRT, k, v.at(st.dirt_uid, k), rk)) continue;
+      if (sp.faithful && uid_shadowed(o, C_DIRT, k, v.uid_at(k), rk)) continue;
       sink.ent(chm[MFG_G_DIRT], cell, OK_DIRT, k, v.at(st.dirt_amt, k));
     }
   }

@@ -146,10 +146,7 @@ struct MfgHandle {
   uint32_t* d_row_tab = nullptr;      // ColTab rows (built at mfg_bind_state)
   int n_row_tab = 0;
   std::vector<uint32_t> row_tab_host;
-  uint32_t* d_chunk_tab = nullptr;    // k_step_w: 16-byte piece i of a warp's 32-env image -> block offset (quarter 0) | log2(element size) << 28
-  int n_chunk_tab = 0;
-  uint8_t* d_cmap = nullptr;          // k_step_w: combined wall / door byte map (door index, CMAP_WALL, 0xFF)
-  int step_kernel = 2;                // 0 = one 128-env block per CTA (k_step); 1 = one warp per CTA (k_step_w); 2 = 0 + barriers at convergent points; 3 = five blocks per CTA + barriers
+  int step_kernel = 1;                // k_step: 1 = barriers at the convergent points + dirt uids left in HBM (6 CTAs per SM), 2 = barriers only, 0 = neither
   uint32_t* d_obs_prog = nullptr;     // device copy of plan.prog
   uint32_t* d_redo = nullptr;         // [1 + N] observation redo list: count, env ids (tiled kernel's rare exact path)
   int defer_reset = 1;

@@ -84,107 +84,69 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, uint32
 
 // `so` = the state view of the shared-memory image: integer field pointers hold byte OFFSETS into the image (see
 // stage_ref), f64 field pointers are the global ones.  Built by launch_step_kernel.
-// NB = state blocks per CTA (128 threads each, own image); SYNC = barriers at the step's convergent points (env_step).
-template <int AMAX, bool FLAGS, int NB, bool SYNC>
-__global__ void __launch_bounds__(STEP_ENVS * NB, NB == 1 ? 5 : NB == 2 ? 2 : 1)
-k_step(const __grid_constant__ HotSpec<AMAX> hs, const MfgSpec* __restrict__ full, const __grid_constant__ Tables tb,
-       const __grid_constant__ State st, const __grid_constant__ State so, const __grid_constant__ StepIO io, const int n_blocks) {
+// SYNC = CTA barriers at the step's convergent points (see env_step): the four warps of the block stay on the same
+// instruction-cache lines instead of each streaming the 7 k-instruction program from L2 on its own.
+// SPLIT = the dirt-uid rows [cut, cut + gap) of the block stay in HBM (so.dirt_uid is then the global slab): they are only
+// touched by the uid listing of faithful mode and by create / compact, and without their 10 KB a sixth CTA fits on the SM.
+template <int AMAX, bool FLAGS, bool SYNC, bool SPLIT>
+__global__ void __launch_bounds__(STEP_ENVS, SPLIT ? 6 : 5)
+k_step(const __grid_constant__ HotSpec<AMAX, SPLIT> hs, const MfgSpec* __restrict__ full, const __grid_constant__ Tables tb,
+       const __grid_constant__ State st, const __grid_constant__ State so, const __grid_constant__ StepIO io,
+       const uint32_t cut, const uint32_t gap) {
   extern __shared__ __align__(128) unsigned char stage[];
   __shared__ __align__(8) unsigned long long bar;
-  const int t = threadIdx.x, g = NB == 1 ? 0 : t >> 7, el = t & (STEP_ENVS - 1);
-  const int b0 = blockIdx.x * NB, nb_here = n_blocks - b0 < NB ? n_blocks - b0 : NB;       // state blocks of this CTA
-  const int64_t eg = (int64_t)(b0 + g) * STEP_ENVS + el;
-  char* gblock = st.base_i + (size_t)b0 * st.blk_i;
-  const uint32_t bytes = (uint32_t)st.blk_i;
+  const int el = threadIdx.x;
+  const int64_t eg = (int64_t)blockIdx.x * STEP_ENVS + el;
+  char* gblock = st.base_i + (size_t)blockIdx.x * st.blk_i;
+  const uint32_t bytes = (uint32_t)st.blk_i - (SPLIT ? gap : 0u);          // image size
+  const uint32_t tail = bytes - cut;                                        // bytes after the gap
 
-  if (t == 0) {
+  if (el == 0) {
     mbar_init(&bar, 1);
-    mbar_expect_tx(&bar, bytes * nb_here);
-    for (int k = 0; k < nb_here; ++k) bulk_g2s(stage + (size_t)k * bytes, gblock + (size_t)k * bytes, bytes, &bar);
+    mbar_expect_tx(&bar, bytes);
+    if (SPLIT) {
+      if (cut) bulk_g2s(stage, gblock, cut, &bar);
+      if (tail) bulk_g2s(stage + cut, gblock + cut + gap, tail, &bar);
+    } else {
+      bulk_g2s(stage, gblock, bytes, &bar);
+    }
   }
   // level tables the step touches with divergent indices: wall map, tile -> door map, door positions.  With most of
   // the SM's unified cache carved out as shared memory they would otherwise be L2 round trips.
   const int HW = hs.H * hs.W, HW4 = (HW + 3) >> 2;
-  uint32_t* s_wall = reinterpret_cast<uint32_t*>(stage + (size_t)NB * bytes);
+  uint32_t* s_wall = reinterpret_cast<uint32_t*>(stage + bytes);
   uint32_t* s_dmap = s_wall + HW4;
   uint16_t* s_dpos = reinterpret_cast<uint16_t*>(s_dmap + HW4);
   {   // 32-bit copies (build_tables pads both tables to a multiple of 4 bytes)
     const uint32_t* gw = reinterpret_cast<const uint32_t*>(tb.wall);
     const uint32_t* gd = reinterpret_cast<const uint32_t*>(tb.door_map);
-    for (int i = t; i < HW4; i += STEP_ENVS * NB) { s_wall[i] = gw[i]; s_dmap[i] = gd[i]; }
+    for (int i = el; i < HW4; i += STEP_ENVS) { s_wall[i] = gw[i]; s_dmap[i] = gd[i]; }
   }
-  if (t < hs.n_doors) s_dpos[t] = tb.door_pos[t];
-  Tables tbs = tb;                  // staged tables: offsets relative to the thread's image, like the integer fields of `so`
-  const uintptr_t toff = (uintptr_t)(NB - g) * bytes;
-  tbs.wall = reinterpret_cast<const uint8_t*>(toff);
-  tbs.door_map = reinterpret_cast<const uint8_t*>(toff + (uintptr_t)HW4 * 4);
-  tbs.door_pos = reinterpret_cast<const uint16_t*>(toff + (uintptr_t)HW4 * 8);
+  if (el < hs.n_doors) s_dpos[el] = tb.door_pos[el];
+  Tables tbs = tb;                  // staged tables: offsets into the image, like the integer fields of `so`
+  tbs.wall = reinterpret_cast<const uint8_t*>((uintptr_t)bytes);
+  tbs.door_map = reinterpret_cast<const uint8_t*>((uintptr_t)bytes + (uintptr_t)HW4 * 4);
+  tbs.door_pos = reinterpret_cast<const uint16_t*>((uintptr_t)bytes + (uintptr_t)HW4 * 8);
   uint32_t sbase;
-  asm volatile("mov.u32 %0, %1;\n" : "=r"(sbase) : "r"(smem_u32(stage) + (uint32_t)g * bytes));      // opaque: kept in ONE register, never re-derived
+  asm volatile("mov.u32 %0, %1;\n" : "=r"(sbase) : "r"(smem_u32(stage)));      // opaque: kept in ONE register, never re-derived
 
   __syncthreads();                  // barrier init + table copies visible
   mbar_wait(&bar, 0);
 
-  if (eg < st.N) env_step<AMAX, HotSpec<AMAX>, FLAGS, SYNC>(hs, *full, tbs, so, el, io, eg, sbase);
-  else if (SYNC) { for (int k = MFG_STEP_SYNC_POINTS(hs.n_agents, hs.n_rules); k > 0; --k) step_sync<true>(); }
+  if (eg < st.N) env_step<AMAX, HotSpec<AMAX, SPLIT>, FLAGS, SYNC>(hs, *full, tbs, so, el, io, eg, sbase);
+  else if (SYNC) { for (int k = step_sync_points(hs); k > 0; --k) step_sync<true>(); }
 
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   __syncthreads();
-  if (t == 0) {
-    for (int k = 0; k < nb_here; ++k) bulk_s2g(gblock + (size_t)k * bytes, stage + (size_t)k * bytes, bytes);
+  if (el == 0) {
+    if (SPLIT) {
+      if (cut) bulk_s2g(gblock, stage, cut);
+      if (tail) bulk_s2g(gblock + cut + gap, stage + cut, tail);
+    } else {
+      bulk_s2g(gblock, stage, bytes);
+    }
     asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");     // shared memory must outlive the copy
-  }
-}
-
-// k_step_w: the same step with ONE WARP per CTA (a quarter of a state block, 32 envs).  A warp of k_step waits at the
-// CTA barrier for the slowest of 128 lanes before the block is written back, and its registers / shared memory stay
-// allocated until then; here every warp stages, advances and writes back its own 32 columns and retires on its own.  The
-// quarter-block is not contiguous in HBM (row slabs of 128 envs), so it is moved as 16-byte pieces: cp.async in,
-// LDS.128 / STG.128 out, piece -> block offset from a table built at mfg_bind_state (`chunks`).  The image has the block's
-// row order with a 32-env stride, i.e. every field offset is a quarter of the block's.  Wall map and tile -> door map are
-// staged as ONE byte map (CMAP_WALL).
-constexpr int WARP_ENVS = 32;
-__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst_smem), "l"(src) : "memory");
-}
-template <int AMAX, bool FLAGS>
-__global__ void __launch_bounds__(WARP_ENVS, 18) k_step_w(const __grid_constant__ HotSpec<AMAX, WARP_ENVS> hs, const MfgSpec* __restrict__ full,
-                                                        const __grid_constant__ Tables tb, const __grid_constant__ State st,
-                                                        const __grid_constant__ State so, const __grid_constant__ StepIO io,
-                                                        const uint32_t* __restrict__ chunks, const int n_chunks,
-                                                        const uint8_t* __restrict__ cmap) {
-  extern __shared__ __align__(128) unsigned char stage[];
-  const int lane = threadIdx.x;
-  const uint32_t q = blockIdx.x & 3u;
-  const int64_t eg = (int64_t)blockIdx.x * WARP_ENVS + lane;
-  char* gblock = st.base_i + (size_t)(blockIdx.x >> 2) * st.blk_i;
-  const uint32_t bytes = (uint32_t)(st.blk_i >> 2);
-  uint32_t sbase;
-  asm volatile("mov.u32 %0, %1;\n" : "=r"(sbase) : "r"(smem_u32(stage)));      // opaque: kept in ONE register, never re-derived
-
-  for (int i = lane; i < n_chunks; i += WARP_ENVS) {
-    const uint32_t rec = __ldg(chunks + i);
-    cp_async16(sbase + 16u * i, gblock + (rec & 0x0FFFFFFFu) + ((size_t)q << (5 + (rec >> 28))));
-  }
-  const int HW16 = (hs.H * hs.W + 15) >> 4;                 // (build_tables pads the map to a multiple of 16 bytes)
-  for (int i = lane; i < HW16; i += WARP_ENVS) cp_async16(sbase + bytes + 16u * i, cmap + 16 * i);
-  uint16_t* s_dpos = reinterpret_cast<uint16_t*>(stage + bytes + HW16 * 16);
-  for (int d = lane; d < hs.n_doors; d += WARP_ENVS) s_dpos[d] = tb.door_pos[d];
-  Tables tbs = tb;                  // staged tables: offsets into the image, like the integer fields of `so`
-  tbs.wall = nullptr;
-  tbs.door_map = reinterpret_cast<const uint8_t*>((uintptr_t)bytes);
-  tbs.door_pos = reinterpret_cast<const uint16_t*>((uintptr_t)bytes + (uintptr_t)HW16 * 16);
-  asm volatile("cp.async.wait_all;\n" ::: "memory");
-  __syncwarp();
-
-  if (eg < st.N) env_step<AMAX, HotSpec<AMAX, WARP_ENVS>, FLAGS>(hs, *full, tbs, so, lane, io, eg, sbase);
-
-  __syncwarp();
-  for (int i = lane; i < n_chunks; i += WARP_ENVS) {
-    const uint32_t rec = __ldg(chunks + i);
-    const uint4 v = *reinterpret_cast<const uint4*>(stage + 16 * i);
-    *reinterpret_cast<uint4*>(gblock + (rec & 0x0FFFFFFFu) + ((size_t)q << (5 + (rec >> 28)))) = v;
   }
 }
 
@@ -219,61 +181,38 @@ cudaError_t launch_reset(MfgHandle* h, const uint8_t* d_mask, cudaStream_t s) {
 }
 
 // k_step alone (the deferred auto-reset list is filled but not consumed)
-static cudaError_t launch_step_warp(MfgHandle* h, const StepIO& io, cudaStream_t s) {
-  const unsigned blocks = (unsigned)((h->N + WARP_ENVS - 1) / WARP_ENVS);
-  const size_t hw16 = ((size_t)h->sp.H * h->sp.W + 15) / 16 * 16;
-  const size_t smem = h->st.blk_i / 4 + hw16 + 2 * MFG_MAX_DOORS;
-  cudaError_t err = cudaSuccess;
-  dispatch_amax(h->sp.n_agents, [&](auto amax) {
-    constexpr int AMAX = decltype(amax)::value;
-    auto kern = io.flags ? k_step_w<AMAX, true> : k_step_w<AMAX, false>;
-    HotSpec<AMAX, WARP_ENVS> hs;
-    fill_hot_spec(h->sp, hs);
-    if (smem > 48 * 1024) err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err == cudaSuccess && io.auto_reset && io.reset_list) err = cudaMemsetAsync(io.reset_count, 0, sizeof(uint32_t), s);
-    State so = h->st;                 // offsets into the 32-env image: a quarter of the block's
-    so.N = WARP_ENVS;
-    so.base_i = nullptr;
-#define F(type, name, rows_expr) \
-  if (!std::is_same<type, double>::value) so.name = reinterpret_cast<type*>((reinterpret_cast<char*>(h->st.name) - h->st.base_i) / 4);
-    MFG_STATE_FIELDS(F)
-#undef F
-    if (err == cudaSuccess) kern<<<blocks, WARP_ENVS, smem, s>>>(hs, h->d_sp, h->tb, h->st, so, io, h->d_chunk_tab, h->n_chunk_tab, h->d_cmap);
-  });
-  return err != cudaSuccess ? err : cudaGetLastError();
-}
-
 cudaError_t launch_step_kernel(MfgHandle* h, const StepIO& io, cudaStream_t s) {
-  // one warp per CTA unless the re-spawn has to run inside the step kernel (auto-reset without the deferred list)
-  if (h->step_kernel == 1 && h->d_chunk_tab && !(io.auto_reset && !io.reset_list)) return launch_step_warp(h, io, s);
-  const int n_blocks = (int)((h->N + STEP_ENVS - 1) / STEP_ENVS);
+  const unsigned blocks = (unsigned)((h->N + STEP_ENVS - 1) / STEP_ENVS);
   const size_t hw4 = ((size_t)h->sp.H * h->sp.W + 3) / 4 * 4;
   cudaError_t err = cudaSuccess;
   dispatch_amax(h->sp.n_agents, [&](auto amax) {
     constexpr int AMAX = decltype(amax)::value;
-    HotSpec<AMAX> hs;
-    fill_hot_spec(h->sp, hs);
     if (io.auto_reset && io.reset_list) err = cudaMemsetAsync(io.reset_count, 0, sizeof(uint32_t), s);
-    State so = h->st;
+    // the in-kernel re-spawn (auto-reset without the deferred list) works on the whole block image
+    const bool split = h->step_kernel == 1 && !(io.auto_reset && !io.reset_list);
+    const uint32_t cut = (uint32_t)(reinterpret_cast<char*>(h->st.dirt_uid) - h->st.base_i);
+    const uint32_t gap = h->sp.has_dirt ? (uint32_t)h->sp.dirt_slots * ENV_BLOCK * (uint32_t)sizeof(uint16_t) : 0u;
+    State so = h->st;                 // integer fields: offsets into the image
     so.N = STEP_ENVS;
-    so.base_i = nullptr;
-#define F(type, name, rows_expr) \
-  if (!std::is_same<type, double>::value) so.name = reinterpret_cast<type*>(reinterpret_cast<char*>(h->st.name) - h->st.base_i);
+#define F(type, name, rows_expr)                                                                              \
+  if (!std::is_same<type, double>::value) {                                                                    \
+    size_t off = (size_t)(reinterpret_cast<char*>(h->st.name) - h->st.base_i);                                 \
+    if (split && off > cut) off -= gap;                                                                        \
+    so.name = reinterpret_cast<type*>(off);                                                                    \
+  }
     MFG_STATE_FIELDS(F)
 #undef F
-    auto go = [&](auto kern, int nb) {
-      const size_t smem = (size_t)nb * h->st.blk_i + 2 * hw4 + 2 * MFG_MAX_DOORS + 16;
+    if (split) so.dirt_uid = h->st.dirt_uid;       // stays global (Env::uid_at)
+    const size_t smem = h->st.blk_i - (split ? gap : 0) + 2 * hw4 + 2 * MFG_MAX_DOORS + 16;
+    auto go = [&](auto kern, auto hs) {
+      fill_hot_spec(h->sp, hs);
       if (err == cudaSuccess && smem > 48 * 1024) err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (err == cudaSuccess) kern<<<(unsigned)((n_blocks + nb - 1) / nb), STEP_ENVS * nb, smem, s>>>(hs, h->d_sp, h->tb, h->st, so, io, n_blocks);
+      if (err == cudaSuccess) kern<<<blocks, STEP_ENVS, smem, s>>>(hs, h->d_sp, h->tb, h->st, so, io, cut, gap);
     };
-    // step_kernel: 0 = one block per CTA; 2 = the same with barriers at the convergent points; 3 = five blocks per CTA
-    // (one CTA per SM, all 20 warps kept together by the barriers)
-    constexpr int NBIG = 5;
-    const bool big_fits = (size_t)NBIG * h->st.blk_i + 2 * hw4 + 2 * MFG_MAX_DOORS + 16 <= 227 * 1024;
-    if (h->step_kernel == 4) { if (io.flags) go(k_step<AMAX, true, 2, true>, 2); else go(k_step<AMAX, false, 2, true>, 2); }
-    else if (h->step_kernel == 3 && big_fits) { if (io.flags) go(k_step<AMAX, true, NBIG, true>, NBIG); else go(k_step<AMAX, false, NBIG, true>, NBIG); }
-    else if (h->step_kernel >= 2) { if (io.flags) go(k_step<AMAX, true, 1, true>, 1); else go(k_step<AMAX, false, 1, true>, 1); }
-    else { if (io.flags) go(k_step<AMAX, true, 1, false>, 1); else go(k_step<AMAX, false, 1, false>, 1); }
+    // step_kernel: 1 = barriers + split image (default); 2 = barriers, whole image; 0 = neither (the round-2 baseline)
+    if (split) { if (io.flags) go(k_step<AMAX, true, true, true>, HotSpec<AMAX, true>()); else go(k_step<AMAX, false, true, true>, HotSpec<AMAX, true>()); }
+    else if (h->step_kernel != 0) { if (io.flags) go(k_step<AMAX, true, true, false>, HotSpec<AMAX, false>()); else go(k_step<AMAX, false, true, false>, HotSpec<AMAX, false>()); }
+    else { if (io.flags) go(k_step<AMAX, true, false, false>, HotSpec<AMAX, false>()); else go(k_step<AMAX, false, false, false>, HotSpec<AMAX, false>()); }
   });
   return err != cudaSuccess ? err : cudaGetLastError();
 }
