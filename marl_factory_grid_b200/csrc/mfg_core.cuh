@@ -24,6 +24,7 @@
 #define MFG_HDNI __host__ __device__ __noinline__      // rare, large: kept out of the callers' instruction stream
 // tiny run-time trip counts, inlined at dozens of call sites: unrolling them quadruples the kernel image (icache misses)
 #define MFG_NOUNROLL _Pragma("unroll 1")
+#define MFG_UNROLL4 _Pragma("unroll 4")
 #define MFG_UNROLL _Pragma("unroll")
 #else
 #define MFG_HD inline
@@ -31,6 +32,7 @@
 #define MFG_HDNI inline
 #define MFG_UNROLL
 #define MFG_NOUNROLL
+#define MFG_UNROLL4
 #endif
 
 namespace mfg {
@@ -455,10 +457,21 @@ struct Env {
   }
 
   // ---------------------------------------------------------------- dirt (clean_up/groups.py:70-95, actions.py:19-36)
-  MFG_HD int dirt_at(uint16_t p) const {
-    MFG_NOUNROLL
-    for (int k = 0; k < dirt_end; ++k) if (at(st.dirt_pos, k) == p) return k;
-    return -1;
+  // bit k = pred(position of slot k) for the slots below dirt_end: branch-free, four independent loads in flight (an
+  // early-exit scan is one dependent shared-memory round trip per slot)
+  template <typename Pred>
+  MFG_HD uint64_t dirt_scan(Pred pred) const {
+    uint32_t lo = 0u, hi = 0u;
+    const int n_lo = dirt_end < 32 ? dirt_end : 32;
+    MFG_UNROLL4
+    for (int k = 0; k < n_lo; ++k) lo |= pred(at(st.dirt_pos, k)) ? (1u << k) : 0u;
+    MFG_UNROLL4
+    for (int k = 32; k < dirt_end; ++k) hi |= pred(at(st.dirt_pos, k)) ? (1u << (k - 32)) : 0u;
+    return (uint64_t)lo | ((uint64_t)hi << 32);
+  }
+  MFG_HD int dirt_at(uint16_t p) const {        // first slot on tile p (tombstones hold NO_POS) or -1
+    const uint64_t m = dirt_scan([&](uint16_t q) { return q == p; });
+    return m ? ctz64(m) : -1;
   }
   MFG_HD double dirt_sum() const {
     // left-to-right f64 sum over the live piles (clean_up/groups.py:27-32).  The amounts live in HBM: fetch eight at a
@@ -943,7 +956,16 @@ MFG_HDN void env_step(const SpecT& sp, const MfgSpec& full, const Tables& tb, co
 #pragma unroll
       for (int i = 0; i < AMAX; ++i) if (i < A) add(v.apos[i]);
       step_sync<SYNC && MFG_STEP_SYNC_FINE>();
-      if (sp.has_dirt) for (int k = 0; k < v.dirt_end; ++k) if ((v.dirt_listed >> k) & 1) add(v.at(st.dirt_pos, k));
+      if (sp.has_dirt) {
+        // listed piles on door tiles: one branch-free pass marks the slots whose tile holds a door (a tombstone's NO_POS is
+        // clamped into the map and masked out by the listing bits), the few hits are then counted
+        const int last = sp.H * sp.W - 1;
+        uint64_t hits = v.dirt_scan([&](uint16_t q) {
+          const int idx = px(q) * sp.W + py(q);
+          return v.tbl(tb.door_map, idx < last ? idx : last) != 0xFF;
+        }) & v.dirt_listed;
+        for (; hits; hits &= hits - 1) add(v.at(st.dirt_pos, ctz64(hits)));
+      }
       MFG_UNROLL
       for (int c = C_ITEM; c <= C_MAINT; ++c) {
         int n = v.cls_count(c);
