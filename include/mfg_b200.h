@@ -191,7 +191,8 @@ int mfg_bind_step_flags(MfgHandle* h, uint8_t* d_flags);
 /* copies the MFG_N_STATS int64 statistics vector (device) into d_out; zero_after != 0 clears it afterwards */
 int mfg_stats(MfgHandle* h, int64_t* d_out, int zero_after, void* stream);
 /* options: "obs_kernel" (0 auto, 1 exact per-agent kernel over block-staged state, 2 tiled shared-memory kernel, 3 exact kernel on plain global state), "obs_store" (1 TMA bulk store),
- * "obs_cap" (sprite slots per env), "defer_reset" (1 packed reset kernel), "overlap_reset" (1 side stream in
+ * "obs_cap" (sprite slots per env), "step_kernel" (k_step launch shape: 1 barriers at the convergent points + dirt uids left in HBM, 2 barriers
+ * only, 0 neither), "step_blocks" (state blocks per k_step CTA, 0 auto), "defer_reset" (1 packed reset kernel), "overlap_reset" (1 side stream in
  * mfg_step_observe), "timing" (1: CUDA event pairs around the kernels, read with mfg_get_info "step_ns" / "obs_ns" /
  * "reset_ns").  info: "launches", "tiled_ok", "obs_smem", "obs_threads", "obs_ctas_per_sm", "obs_cap", "obs_cap_max". */
 int mfg_set_option(MfgHandle* h, const char* name, int64_t value);

@@ -78,6 +78,7 @@ int mfg_create(const MfgSpec* spec, int64_t n_envs, int64_t env_id_offset, MfgHa
   h->tb.env_id_offset = env_id_offset;
   void* d = nullptr;
   if (const char* ev = getenv("MFG_STEP_KERNEL")) h->step_kernel = atoi(ev);      // development aid (A/B runs)
+  if (const char* ev = getenv("MFG_STEP_BLOCKS")) h->step_blocks = atoi(ev);
   if (cudaMalloc(&d, sizeof(unsigned long long) * MFG_N_STATS) != cudaSuccess) { mfg_destroy(h); return fail(MFG_E_NOMEM, "stats alloc"); }
   h->dev_allocs.push_back(d);
   cudaMemset(d, 0, sizeof(unsigned long long) * MFG_N_STATS);
@@ -322,7 +323,13 @@ int mfg_set_option(MfgHandle* h, const char* name, int64_t value) {
   if (strcmp(name, "reseed") == 0) { h->ever_reset = false; return MFG_OK; }      // the next full reset starts again at episode 0
   if (strcmp(name, "timing") == 0) { h->timing = value != 0; return MFG_OK; }
   if (strcmp(name, "step_kernel") == 0) {      // 1 = barriers + dirt uids left in HBM (default), 2 = barriers only, 0 = neither
+    if (value < 0 || value > 2) return fail(MFG_E_INVALID, "step_kernel must be 0, 1 or 2");
     h->step_kernel = (int)value;
+    return MFG_OK;
+  }
+  if (strcmp(name, "step_blocks") == 0) {      // state blocks per k_step CTA: 0 = auto (default), 1..3
+    if (value < 0 || value > 3) return fail(MFG_E_INVALID, "step_blocks must be in 0..3");
+    h->step_blocks = (int)value;
     return MFG_OK;
   }
   if (strcmp(name, "obs_store") == 0) {        // 1 = TMA bulk store of the tile (default), 0 = LDS/STG loop

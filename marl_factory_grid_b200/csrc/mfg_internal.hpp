@@ -146,6 +146,7 @@ struct MfgHandle {
   uint32_t* d_row_tab = nullptr;      // ColTab rows (built at mfg_bind_state)
   int n_row_tab = 0;
   std::vector<uint32_t> row_tab_host;
+  int step_blocks = 0;                // k_step: state blocks per CTA (0 = auto, 1..3; split image only)
   int step_kernel = 1;                // k_step: 1 = barriers at the convergent points + dirt uids left in HBM (6 CTAs per SM), 2 = barriers only, 0 = neither
   uint32_t* d_obs_prog = nullptr;     // device copy of plan.prog
   uint32_t* d_redo = nullptr;         // [1 + N] observation redo list: count, env ids (tiled kernel's rare exact path)

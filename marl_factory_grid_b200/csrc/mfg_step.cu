@@ -88,47 +88,55 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, uint32
 // instruction-cache lines instead of each streaming the 7 k-instruction program from L2 on its own.
 // SPLIT = the dirt-uid rows [cut, cut + gap) of the block stay in HBM (so.dirt_uid is then the global slab): they are only
 // touched by the uid listing of faithful mode and by create / compact, and without their 10 KB a sixth CTA fits on the SM.
-template <int AMAX, bool FLAGS, bool SYNC, bool SPLIT>
-__global__ void __launch_bounds__(STEP_ENVS, SPLIT ? 6 : 5)
+// NB = state blocks per CTA (128 threads and one image each): larger lockstep groups share more instruction fetches and wait
+// longer at the barriers.
+template <int AMAX, bool FLAGS, bool SYNC, bool SPLIT, int NB>
+__global__ void __launch_bounds__(STEP_ENVS * NB, (SPLIT ? 6 : 5) / NB)
 k_step(const __grid_constant__ HotSpec<AMAX, SPLIT> hs, const MfgSpec* __restrict__ full, const __grid_constant__ Tables tb,
        const __grid_constant__ State st, const __grid_constant__ State so, const __grid_constant__ StepIO io,
-       const uint32_t cut, const uint32_t gap) {
+       const uint32_t cut, const uint32_t gap, const int n_blocks) {
   extern __shared__ __align__(128) unsigned char stage[];
   __shared__ __align__(8) unsigned long long bar;
-  const int el = threadIdx.x;
-  const int64_t eg = (int64_t)blockIdx.x * STEP_ENVS + el;
-  char* gblock = st.base_i + (size_t)blockIdx.x * st.blk_i;
+  const int t = threadIdx.x, g = NB == 1 ? 0 : t >> 7, el = t & (STEP_ENVS - 1);
+  const int b0 = blockIdx.x * NB, nb_here = n_blocks - b0 < NB ? n_blocks - b0 : NB;        // state blocks of this CTA
+  const int64_t eg = (int64_t)(b0 + g) * STEP_ENVS + el;
+  char* gblock = st.base_i + (size_t)b0 * st.blk_i;
   const uint32_t bytes = (uint32_t)st.blk_i - (SPLIT ? gap : 0u);          // image size
   const uint32_t tail = bytes - cut;                                        // bytes after the gap
 
-  if (el == 0) {
+  if (t == 0) {
     mbar_init(&bar, 1);
-    mbar_expect_tx(&bar, bytes);
-    if (SPLIT) {
-      if (cut) bulk_g2s(stage, gblock, cut, &bar);
-      if (tail) bulk_g2s(stage + cut, gblock + cut + gap, tail, &bar);
-    } else {
-      bulk_g2s(stage, gblock, bytes, &bar);
+    mbar_expect_tx(&bar, bytes * nb_here);
+    for (int k = 0; k < nb_here; ++k) {
+      unsigned char* img = stage + (size_t)k * bytes;
+      const char* src = gblock + (size_t)k * st.blk_i;
+      if (SPLIT) {
+        if (cut) bulk_g2s(img, src, cut, &bar);
+        if (tail) bulk_g2s(img + cut, src + cut + gap, tail, &bar);
+      } else {
+        bulk_g2s(img, src, bytes, &bar);
+      }
     }
   }
   // level tables the step touches with divergent indices: wall map, tile -> door map, door positions.  With most of
   // the SM's unified cache carved out as shared memory they would otherwise be L2 round trips.
   const int HW = hs.H * hs.W, HW4 = (HW + 3) >> 2;
-  uint32_t* s_wall = reinterpret_cast<uint32_t*>(stage + bytes);
+  uint32_t* s_wall = reinterpret_cast<uint32_t*>(stage + (size_t)NB * bytes);
   uint32_t* s_dmap = s_wall + HW4;
   uint16_t* s_dpos = reinterpret_cast<uint16_t*>(s_dmap + HW4);
   {   // 32-bit copies (build_tables pads both tables to a multiple of 4 bytes)
     const uint32_t* gw = reinterpret_cast<const uint32_t*>(tb.wall);
     const uint32_t* gd = reinterpret_cast<const uint32_t*>(tb.door_map);
-    for (int i = el; i < HW4; i += STEP_ENVS) { s_wall[i] = gw[i]; s_dmap[i] = gd[i]; }
+    for (int i = t; i < HW4; i += STEP_ENVS * NB) { s_wall[i] = gw[i]; s_dmap[i] = gd[i]; }
   }
-  if (el < hs.n_doors) s_dpos[el] = tb.door_pos[el];
-  Tables tbs = tb;                  // staged tables: offsets into the image, like the integer fields of `so`
-  tbs.wall = reinterpret_cast<const uint8_t*>((uintptr_t)bytes);
-  tbs.door_map = reinterpret_cast<const uint8_t*>((uintptr_t)bytes + (uintptr_t)HW4 * 4);
-  tbs.door_pos = reinterpret_cast<const uint16_t*>((uintptr_t)bytes + (uintptr_t)HW4 * 8);
+  if (t < hs.n_doors) s_dpos[t] = tb.door_pos[t];
+  Tables tbs = tb;                  // staged tables: offsets relative to the thread's image, like the integer fields of `so`
+  const uintptr_t toff = (uintptr_t)(NB - g) * bytes;
+  tbs.wall = reinterpret_cast<const uint8_t*>(toff);
+  tbs.door_map = reinterpret_cast<const uint8_t*>(toff + (uintptr_t)HW4 * 4);
+  tbs.door_pos = reinterpret_cast<const uint16_t*>(toff + (uintptr_t)HW4 * 8);
   uint32_t sbase;
-  asm volatile("mov.u32 %0, %1;\n" : "=r"(sbase) : "r"(smem_u32(stage)));      // opaque: kept in ONE register, never re-derived
+  asm volatile("mov.u32 %0, %1;\n" : "=r"(sbase) : "r"(smem_u32(stage) + (uint32_t)g * bytes));      // opaque: kept in ONE register, never re-derived
 
   __syncthreads();                  // barrier init + table copies visible
   mbar_wait(&bar, 0);
@@ -138,12 +146,16 @@ k_step(const __grid_constant__ HotSpec<AMAX, SPLIT> hs, const MfgSpec* __restric
 
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   __syncthreads();
-  if (el == 0) {
-    if (SPLIT) {
-      if (cut) bulk_s2g(gblock, stage, cut);
-      if (tail) bulk_s2g(gblock + cut + gap, stage + cut, tail);
-    } else {
-      bulk_s2g(gblock, stage, bytes);
+  if (t == 0) {
+    for (int k = 0; k < nb_here; ++k) {
+      const unsigned char* img = stage + (size_t)k * bytes;
+      char* dst = gblock + (size_t)k * st.blk_i;
+      if (SPLIT) {
+        if (cut) bulk_s2g(dst, img, cut);
+        if (tail) bulk_s2g(dst + cut + gap, img + cut, tail);
+      } else {
+        bulk_s2g(dst, img, bytes);
+      }
     }
     asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");     // shared memory must outlive the copy
@@ -203,16 +215,23 @@ cudaError_t launch_step_kernel(MfgHandle* h, const StepIO& io, cudaStream_t s) {
     MFG_STATE_FIELDS(F)
 #undef F
     if (split) so.dirt_uid = h->st.dirt_uid;       // stays global (Env::uid_at)
-    const size_t smem = h->st.blk_i - (split ? gap : 0) + 2 * hw4 + 2 * MFG_MAX_DOORS + 16;
-    auto go = [&](auto kern, auto hs) {
+    const int n_blocks = (int)blocks;
+    auto go = [&](auto kern, auto hs, int nb) {
+      const size_t smem = (size_t)nb * (h->st.blk_i - (split ? gap : 0)) + 2 * hw4 + 2 * MFG_MAX_DOORS + 16;
       fill_hot_spec(h->sp, hs);
       if (err == cudaSuccess && smem > 48 * 1024) err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (err == cudaSuccess) kern<<<blocks, STEP_ENVS, smem, s>>>(hs, h->d_sp, h->tb, h->st, so, io, cut, gap);
+      if (err == cudaSuccess) kern<<<(unsigned)((n_blocks + nb - 1) / nb), STEP_ENVS * nb, smem, s>>>(hs, h->d_sp, h->tb, h->st, so, io, cut, gap, n_blocks);
     };
     // step_kernel: 1 = barriers + split image (default); 2 = barriers, whole image; 0 = neither (the round-2 baseline)
-    if (split) { if (io.flags) go(k_step<AMAX, true, true, true>, HotSpec<AMAX, true>()); else go(k_step<AMAX, false, true, true>, HotSpec<AMAX, true>()); }
-    else if (h->step_kernel != 0) { if (io.flags) go(k_step<AMAX, true, true, false>, HotSpec<AMAX, false>()); else go(k_step<AMAX, false, true, false>, HotSpec<AMAX, false>()); }
-    else { if (io.flags) go(k_step<AMAX, true, false, false>, HotSpec<AMAX, false>()); else go(k_step<AMAX, false, false, false>, HotSpec<AMAX, false>()); }
+    // blocks per CTA: two when three such CTAs still fit on the SM (same 24 warps, half as many lockstep groups: 0.56 -> 0.49 ms
+    // on cfg4; three blocks: 0.51), else one
+    const size_t img = h->st.blk_i - (split ? gap : 0), extra = 2 * hw4 + 2 * MFG_MAX_DOORS + 16 + 1024;
+    const int nb = h->step_blocks ? h->step_blocks : (3 * (2 * img + extra) <= (size_t)228 * 1024 ? 2 : 1);
+    if (split && nb == 2) { if (io.flags) go(k_step<AMAX, true, true, true, 2>, HotSpec<AMAX, true>(), 2); else go(k_step<AMAX, false, true, true, 2>, HotSpec<AMAX, true>(), 2); }
+    else if (split && nb == 3) { if (io.flags) go(k_step<AMAX, true, true, true, 3>, HotSpec<AMAX, true>(), 3); else go(k_step<AMAX, false, true, true, 3>, HotSpec<AMAX, true>(), 3); }
+    else if (split) { if (io.flags) go(k_step<AMAX, true, true, true, 1>, HotSpec<AMAX, true>(), 1); else go(k_step<AMAX, false, true, true, 1>, HotSpec<AMAX, true>(), 1); }
+    else if (h->step_kernel != 0) { if (io.flags) go(k_step<AMAX, true, true, false, 1>, HotSpec<AMAX, false>(), 1); else go(k_step<AMAX, false, true, false, 1>, HotSpec<AMAX, false>(), 1); }
+    else { if (io.flags) go(k_step<AMAX, true, false, false, 1>, HotSpec<AMAX, false>(), 1); else go(k_step<AMAX, false, false, false, 1>, HotSpec<AMAX, false>(), 1); }
   });
   return err != cudaSuccess ? err : cudaGetLastError();
 }
