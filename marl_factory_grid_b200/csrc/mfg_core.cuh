@@ -242,6 +242,10 @@ struct HotSpec {
   double rule_param[MFG_MAX_RULES][MFG_RULE_NPARAM];
   int8_t dest_bound[MFG_MAX_SMALL];
   double act_cost[AMAX][MFG_MAX_ACTIONS + 1];
+  // UIDG only: the first uid_head_rows dirt-uid rows ARE part of the image (at byte offset uid_head_off): the uid listing
+  // asks for small uids (class members), and slot j always holds a uid >= j, so those queries never look further
+  uint32_t uid_head_off;
+  int32_t uid_head_rows;
 };
 
 template <int AMAX, bool UIDG>
@@ -355,8 +359,12 @@ struct Env {
   MFG_HD bool in_grid(int x, int y) const { return x >= 0 && y >= 0 && x < sp.H && y < sp.W; }
   // dirt uids: rarely touched (uid listing in faithful mode, create / compact), so k_step keeps their rows out of its image
   MFG_HD uint16_t& uid_at(int k) const {
-    if constexpr (UIDG) return field_at(st, st.dirt_uid, k, eg);
-    else return at(st.dirt_uid, k);
+    if constexpr (UIDG) {
+      if (k < sp.uid_head_rows) return stage_ref(sbase, reinterpret_cast<const uint16_t*>((uintptr_t)sp.uid_head_off), k * ENV_BLOCK + (int)e);
+      return field_at(st, st.dirt_uid, k, eg);
+    } else {
+      return at(st.dirt_uid, k);
+    }
   }
   MFG_HD bool is_wall(int idx) const { return tbl(tb.wall, idx) != 0; }
   MFG_HD int door_idx(int idx) const {          // door index of a tile or -1
@@ -410,9 +418,10 @@ struct Env {
       if ((dirt_listed >> own_dirt) & 1) { cls = C_DIRT; idx = own_dirt; return true; }
     } else if (own_dirt == -2 && sp.has_dirt && uid < (int)at(st.dirt_next_uid, 0)) {
       // slots are in creation order and uids only grow (deleted slots keep theirs, compaction keeps the order), so the
-      // scan can stop at the first larger uid - the uids asked for (maintainers, items, doors ...) are small
+      // scan can stop at the first larger uid - the uids asked for (maintainers, items, doors ...) are small.  The uids
+      // of an episode start at 0, so slot k holds a uid >= k: nothing beyond slot `uid` can match.
       MFG_NOUNROLL
-      for (int k = 0; k < dirt_end; ++k) {
+      for (int k = 0; k < dirt_end && k <= uid; ++k) {
         const int du = uid_at(k);
         if (du > uid) break;
         if (du == uid && at(st.dirt_pos, k) == p && ((dirt_listed >> k) & 1)) { cls = C_DIRT; idx = k; return true; }

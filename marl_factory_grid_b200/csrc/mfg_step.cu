@@ -202,8 +202,15 @@ cudaError_t launch_step_kernel(MfgHandle* h, const StepIO& io, cudaStream_t s) {
     if (io.auto_reset && io.reset_list) err = cudaMemsetAsync(io.reset_count, 0, sizeof(uint32_t), s);
     // the in-kernel re-spawn (auto-reset without the deferred list) works on the whole block image
     const bool split = h->step_kernel == 1 && !(io.auto_reset && !io.reset_list);
-    const uint32_t cut = (uint32_t)(reinterpret_cast<char*>(h->st.dirt_uid) - h->st.base_i);
-    const uint32_t gap = h->sp.has_dirt ? (uint32_t)h->sp.dirt_slots * ENV_BLOCK * (uint32_t)sizeof(uint16_t) : 0u;
+    // the rows left in HBM: all dirt-uid rows but the first few (as many as the largest small class has members - the uid
+    // listing never looks further for a class member's uid, see Env::find_listed)
+    const uint32_t uid_off = (uint32_t)(reinterpret_cast<char*>(h->st.dirt_uid) - h->st.base_i), row_b = ENV_BLOCK * (uint32_t)sizeof(uint16_t);
+    int head = 0;
+    for (int n : {h->sp.n_items, h->sp.n_pods, h->sp.n_dest, h->sp.n_dropoff, h->sp.n_machines, h->sp.n_maint}) head = n > head ? n : head;
+    const int uid_rows = h->sp.has_dirt ? h->sp.dirt_slots : 0;
+    if (head > uid_rows) head = uid_rows;
+    const uint32_t cut = uid_off + (uint32_t)head * row_b;
+    const uint32_t gap = (uint32_t)(uid_rows - head) * row_b;
     State so = h->st;                 // integer fields: offsets into the image
     so.N = STEP_ENVS;
 #define F(type, name, rows_expr)                                                                              \
@@ -219,6 +226,8 @@ cudaError_t launch_step_kernel(MfgHandle* h, const StepIO& io, cudaStream_t s) {
     auto go = [&](auto kern, auto hs, int nb) {
       const size_t smem = (size_t)nb * (h->st.blk_i - (split ? gap : 0)) + 2 * hw4 + 2 * MFG_MAX_DOORS + 16;
       fill_hot_spec(h->sp, hs);
+      hs.uid_head_off = uid_off;
+      hs.uid_head_rows = head;
       if (err == cudaSuccess && smem > 48 * 1024) err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (err == cudaSuccess) kern<<<(unsigned)((n_blocks + nb - 1) / nb), STEP_ENVS * nb, smem, s>>>(hs, h->d_sp, h->tb, h->st, so, io, cut, gap, n_blocks);
     };
