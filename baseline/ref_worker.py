@@ -47,7 +47,13 @@ def worker_run(steps: int):
     t0 = time.perf_counter()
     with contextlib.redirect_stdout(out):
         for _ in range(steps):
-            _, _, _, done, _ = env.step([rng.randrange(n) for n in n_act])
+            try:
+                _, _, _, done, _ = env.step([rng.randrange(n) for n in n_act])
+            except Exception:
+                # the reference's own defect: Maintainer.get_move_action pops an exhausted route list
+                # (modules/maintenance/entities.py:89) every few thousand steps; an unattended run would stop here.  The episode is
+                # abandoned (the step still counts as CPU work done) and the env re-spawned.
+                done = True
             if done:
                 env.reset()
             if out.tell() > 1 << 20:

@@ -452,21 +452,29 @@ def run_engine(args):
     if world == 1 and not args.no_cpu:
         procs = os.cpu_count() or 1
         faithful = args.parity == 'faithful'
-        v, per, slowest, kind = cpu_sample(args.config, faithful, procs, 'auto', args.cpu_seconds)
+        try:
+            v, per, slowest, kind = cpu_sample(args.config, faithful, procs, 'auto', args.cpu_seconds)
+        except Exception as exc:          # a crash inside the reference must not cost the GPU line: time the oracle port instead
+            print(f'[bench] reference CPU sample failed ({exc!r}); timing the oracle port', file=sys.stderr)
+            v, per, slowest, kind = cpu_sample(args.config, faithful, procs, 'port', args.cpu_seconds)
         what = 'UNMODIFIED reference from baseline/_ref, SURVEY 8d protocol' if kind == 'reference' else 'oracle port of the reference step+obs'
         line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': procs, 'kind': kind,
                                 'sample': f'{procs} procs x {per} env-steps of {args.config}, {what} (own Factory per worker, '
                                           f'random actions, in-place reset on done), {slowest:.1f} s'}
         if kind == 'reference':
             # the port beside it (what round 1 reported), and the other BASELINE configs on the reference (short samples)
-            pv, pper, ps, _ = cpu_sample(args.config, faithful, procs, 'port', min(args.cpu_seconds, 6.0))
-            line['cpu_baseline']['port'] = {'value': pv, 'sample': f'{procs} procs x {pper} env-steps, oracle port, {ps:.1f} s'}
-            others = {}
-            for c in ('cfg1', 'cfg2', 'cfg3'):
-                if c != args.config and not args.no_cpu_sweep:
-                    ov, oper, os_, _ = cpu_sample(c, faithful, procs, 'reference', 4.0)
-                    others[c] = {'value': ov, 'sample': f'{procs} procs x {oper} env-steps, {os_:.1f} s'}
-            line['cpu_baseline']['other_configs'] = others
+            try:
+                pv, pper, ps, _ = cpu_sample(args.config, faithful, procs, 'port', min(args.cpu_seconds, 6.0))
+                line['cpu_baseline']['port'] = {'value': pv, 'sample': f'{procs} procs x {pper} env-steps, oracle port, {ps:.1f} s'}
+                others = {}
+                for c in ('cfg1', 'cfg2', 'cfg3'):
+                    if c != args.config and not args.no_cpu_sweep:
+                        ov, oper, os_, _ = cpu_sample(c, faithful, procs, 'reference', 4.0)
+                        others[c] = {'value': ov, 'sample': f'{procs} procs x {oper} env-steps, {os_:.1f} s'}
+                line['cpu_baseline']['other_configs'] = others
+            except Exception as exc:
+                line['cpu_baseline']['note'] = f'secondary CPU samples failed: {exc!r}'
+
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

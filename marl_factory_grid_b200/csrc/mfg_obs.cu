@@ -454,7 +454,8 @@ __global__ void __launch_bounds__(256, FAITHFUL ? MFG_OBS_CTAS_F : 4) k_obs_tile
           const uint32_t wrng = FAITHFUL ? tb.wall_cand_rng[tile_id] : 0xFFFFu;     // [lo, hi] of the candidate wall uids >= 64
           // listed piles (identity mode: the live ones); the 64-bit slot mask is walked as two 32-bit words
 #pragma unroll
-          for (int half = 0; half < 2; ++half)
+          for (int half = 0; half < 2; ++half) {
+          uint32_t cand = 0u;               // slots of this half that are candidates (visible in the window or on the ring)
           for (uint32_t dm = half ? (uint32_t)(dirtlisted >> 32) : (uint32_t)dirtlisted; dm; dm &= dm - 1) {
             const int k = __ffs(dm) - 1 + 32 * half;
             const uint16_t q = pos[k];
@@ -464,7 +465,16 @@ __global__ void __launch_bounds__(256, FAITHFUL ? MFG_OBS_CTAS_F : 4) k_obs_tile
               // the pile's f64 amount is read in phase 2 (HBM, uncoalesced): start the fetch now
               asm volatile("prefetch.global.L2 [%0];\n" ::"l"(&field_at(st, st.dirt_amt, k, e)));
             }
-            if (FAITHFUL && c) {
+            if (FAITHFUL && c) cand |= 1u << (k & 31);
+          }
+          // faithful: the uid bookkeeping of the candidates runs as a second, short loop over the lane's candidate slots only
+          // (~1 of ~20 listed piles per lane) instead of as a divergent tail of every iteration of the walk above.  Pile
+          // uids are unique among the piles, so the order of the two loops does not matter to `seen / win_uids`.
+          if (FAITHFUL)
+          for (uint32_t cm2 = cand; cm2; cm2 &= cm2 - 1) {
+            const int k = __ffs(cm2) - 1 + 32 * half;
+            const int c = ((dirt_w >> k) & 1ull) ? 3 : 1;
+            {
               const uint32_t uid = blk_dirt_uid[k * ENV_BLOCK + eb];
               bool cf;
               if (uid < 64) {
@@ -490,6 +500,7 @@ __global__ void __launch_bounds__(256, FAITHFUL ? MFG_OBS_CTAS_F : 4) k_obs_tile
                 else overflow = true;
               }
             }
+          }
           }
         }
         if (FAITHFUL) {
