@@ -455,18 +455,18 @@ __global__ void __launch_bounds__(256, FAITHFUL ? MFG_OBS_CTAS_F : 4) k_obs_tile
           // listed piles (identity mode: the live ones); the 64-bit slot mask is walked as two 32-bit words
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
-          uint32_t cand = 0u;               // slots of this half that are candidates (visible in the window or on the ring)
+          // branch-free walk: bit 1 of the class = visible inside the window, bit 0 = candidate (window or ring)
+          uint32_t cand = 0u, dw = 0u;
           for (uint32_t dm = half ? (uint32_t)(dirtlisted >> 32) : (uint32_t)dirtlisted; dm; dm &= dm - 1) {
-            const int k = __ffs(dm) - 1 + 32 * half;
-            const uint16_t q = pos[k];
-            const int c = classify(q);
-            if (c == 3) {
-              dirt_w |= 1ull << k;
-              // the pile's f64 amount is read in phase 2 (HBM, uncoalesced): start the fetch now
-              asm volatile("prefetch.global.L2 [%0];\n" ::"l"(&field_at(st, st.dirt_amt, k, e)));
-            }
-            if (FAITHFUL && c) cand |= 1u << (k & 31);
+            const int kk = __ffs(dm) - 1;
+            const uint32_t c = (uint32_t)classify(pos[kk + 32 * half]);
+            dw |= ((c >> 1) & 1u) << kk;
+            cand |= (c & 1u) << kk;
           }
+          dirt_w |= (unsigned long long)dw << (32 * half);
+          // the visible piles' f64 amounts are read in phase 2 (HBM, uncoalesced): start the fetches now
+          for (uint32_t m = dw; m; m &= m - 1)
+            asm volatile("prefetch.global.L2 [%0];\n" ::"l"(&field_at(st, st.dirt_amt, __ffs(m) - 1 + 32 * half, e)));
           // faithful: the uid bookkeeping of the candidates runs as a second, short loop over the lane's candidate slots only
           // (~1 of ~20 listed piles per lane) instead of as a divergent tail of every iteration of the walk above.  Pile
           // uids are unique among the piles, so the order of the two loops does not matter to `seen / win_uids`.
