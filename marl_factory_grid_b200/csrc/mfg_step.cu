@@ -50,11 +50,11 @@ __global__ void __launch_bounds__(STEP_ENVS_R) k_reset_list(const MfgSpec* __res
   }
 }
 
-// k_step: CTA = one 128-env state block.  The block's integer / byte fields are ONE contiguous slab in HBM (blocked
-// layout, see State): a single TMA bulk copy (cp.async.bulk, completion on an mbarrier) stages it in shared memory,
-// the whole step runs against that copy (tile look-ups, slot scans and rule hooks hit shared memory instead of
-// dependent HBM round trips), and a single bulk store writes it back.  f64 fields (dirt amounts, battery, returns)
-// stay in HBM: few actions / rules touch them.
+// k_step: CTA = one or two 128-env state blocks.  A block's integer / byte fields are ONE contiguous slab in HBM (blocked
+// layout, see State): TMA bulk copies (cp.async.bulk, completion on an mbarrier) stage it in shared memory, the whole
+// step runs against that copy (tile look-ups, slot scans and rule hooks hit shared memory instead of dependent HBM
+// round trips), and bulk stores write it back.  f64 fields (dirt amounts, battery, returns) stay in HBM: few actions /
+// rules touch them.  Launch shapes: see the comment on the kernel below.
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
