@@ -63,6 +63,10 @@ def snapshot_to_columns(es: EnvSpec, snap: dict) -> Dict[str, np.ndarray]:
             dpos[k] = pos16(snap['dirt_pos'][k])
             damt[k] = snap['dirt_amt'][k]
             duid[k] = snap['dirt_uid'][k] if 'dirt_uid' in snap else k
+        # the uid model of a fresh episode (object.py:103-113 counters start at 0): strictly increasing in creation order, so
+        # slot k holds a uid >= k; the step kernel's uid listing relies on it (Env::find_listed)
+        if n and (np.any(np.diff(duid[:n].astype(np.int64)) <= 0) or np.any(duid[:n] < np.arange(n))):
+            raise ValueError('snapshot: dirt uids must increase strictly in creation order (fresh-episode uid model)')
         listed = snap['dirt_listed'][:n] if 'dirt_listed' in snap else np.ones(n)
         col.update(dirt_pos=dpos, dirt_amt=damt, dirt_uid=duid,
                    dirt_listed=np.array([_mask(listed)], np.uint64),

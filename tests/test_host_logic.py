@@ -99,6 +99,19 @@ def test_snapshot_roundtrip(cfg):
             np.testing.assert_array_equal(back[key], snap[key], err_msg=key)
 
 
+def test_snapshot_with_a_foreign_uid_model_is_rejected():
+    """The step kernel's uid listing relies on the fresh-episode uid model (pile uids strictly increasing in creation order);
+    a hand-made state that breaks it must not load."""
+    es = spec_for('cfg4')
+    snap = dict(snap_at(episodes('cfg4')[0], 0))
+    assert int(snap['dirt_n']) >= 2
+    uid = np.array(snap['dirt_uid']).copy()
+    uid[1] = uid[0]
+    snap['dirt_uid'] = uid
+    with pytest.raises(ValueError, match='dirt uids'):
+        snapshot_to_columns(es, snap)
+
+
 def _write(tmp_path, mutate):
     cfg = yaml.safe_load((CONFIGS / 'cfg4.yaml').read_text())
     mutate(cfg)
